@@ -1,0 +1,239 @@
+"""ctypes view of the Dirac C API for the direction-dependent calibration hot path.
+
+The structs and prototypes below are the *interface* the reference driver (`sagecal_gpu`,
+src/MS/fullbatch_mode.cpp:371-446) binds against; they are restated from
+src/lib/Dirac/Dirac_common.h:173-195 (clus_source_t, baseline_t), Dirac.h:1651,1683
+(sagefit_visibilities, bfgsfit_visibilities) and src/lib/Radio/Dirac_radio.h:209,659
+(precalculate_coherencies, predict_visibilities_multifreq).
+
+`DiracAPI(path)` binds any shared library that implements this ABI.  The product library is
+`sagecal_b200/libdirac_b200.so` (see `sagecal_b200.lib`); tests additionally bind the
+compiled reference (`oracle/_ref/libdirac_ref.so`) through the very same class, which is what
+makes the parity tests read like "call both, compare".
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_ubyte_p = C.POINTER(C.c_ubyte)
+
+STYPE_POINT = 0
+STYPE_GAUSSIAN = 1
+STYPE_DISK = 2
+STYPE_RING = 3
+STYPE_SHAPELET = 4
+
+# solver_mode values, Dirac.h:1607-1613
+SM_OSLM_LBFGS = 0
+SM_LM_LBFGS = 1
+SM_RLM_RLBFGS = 2
+SM_OSLM_OSRLM_RLBFGS = 3
+SM_RTR_OSLM_LBFGS = 4
+SM_RTR_OSRLM_RLBFGS = 5
+SM_NSD_RLBFGS = 6
+
+
+class baseline_t(C.Structure):
+    """Dirac_common.h:190-195 — row -> (sta1, sta2, flag)."""
+    _fields_ = [("sta1", C.c_int), ("sta2", C.c_int), ("flag", C.c_ubyte)]
+
+
+class clus_source_t(C.Structure):
+    """Dirac_common.h:173-187 — one cluster (direction) of the sky model."""
+    _fields_ = [
+        ("N", C.c_int), ("id", C.c_int),
+        ("ll", c_double_p), ("mm", c_double_p), ("nn", c_double_p),
+        ("sI", c_double_p), ("sQ", c_double_p), ("sU", c_double_p), ("sV", c_double_p),
+        ("ra", c_double_p), ("dec", c_double_p),
+        ("stype", c_ubyte_p), ("ex", C.POINTER(C.c_void_p)),
+        ("nchunk", C.c_int), ("p", c_int_p),
+        ("sI0", c_double_p), ("sQ0", c_double_p), ("sU0", c_double_p), ("sV0", c_double_p),
+        ("f0", c_double_p), ("spec_idx", c_double_p), ("spec_idx1", c_double_p),
+        ("spec_idx2", c_double_p),
+    ]
+
+
+class exinfo_gaussian(C.Structure):
+    """Dirac_radio.h exinfo_gaussian — extended (Gaussian) source shape."""
+    _fields_ = [("eX", C.c_double), ("eY", C.c_double), ("eP", C.c_double),
+                ("cxi", C.c_double), ("sxi", C.c_double), ("cphi", C.c_double),
+                ("sphi", C.c_double), ("use_projection", C.c_int)]
+
+
+assert C.sizeof(baseline_t) == 12
+
+
+def dptr(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_double_p)
+
+
+def cptr(a: np.ndarray):
+    """complex128 array viewed as the `complex double *` the API expects."""
+    assert a.dtype == np.complex128 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_double_p)
+
+
+class SkyModel:
+    """Owns the numpy buffers behind an array of clus_source_t."""
+
+    def __init__(self, clusters, N, keep_alive=None):
+        """clusters: list of dict(ll,mm,nn,sI,sQ,sU,sV[,stype,nchunk,f0,spec_idx...,gauss])."""
+        self.M = len(clusters)
+        self.arr = (clus_source_t * self.M)()
+        self._keep = []
+        off = 0
+        self.nchunk = []
+        for k, cl in enumerate(clusters):
+            K = len(cl["ll"])
+            cs = self.arr[k]
+            cs.N = K
+            cs.id = int(cl.get("id", k))
+            for name in ("ll", "mm", "nn", "sI", "sQ", "sU", "sV"):
+                a = np.ascontiguousarray(cl[name], dtype=np.float64)
+                self._keep.append(a)
+                setattr(cs, name, dptr(a))
+            for name in ("ra", "dec"):
+                a = np.ascontiguousarray(cl.get(name, np.zeros(K)), dtype=np.float64)
+                self._keep.append(a)
+                setattr(cs, name, dptr(a))
+            st = np.ascontiguousarray(cl.get("stype", np.zeros(K)), dtype=np.uint8)
+            self._keep.append(st)
+            cs.stype = st.ctypes.data_as(c_ubyte_p)
+            ex = (C.c_void_p * K)()
+            gauss = cl.get("gauss")
+            if gauss is not None:
+                for s in range(K):
+                    if st[s] == STYPE_GAUSSIAN:
+                        g = exinfo_gaussian(*[float(v) for v in gauss[s][:7]], int(gauss[s][7]))
+                        self._keep.append(g)
+                        ex[s] = C.cast(C.pointer(g), C.c_void_p)
+            self._keep.append(ex)
+            cs.ex = C.cast(ex, C.POINTER(C.c_void_p))
+            nchunk = int(cl.get("nchunk", 1))
+            cs.nchunk = nchunk
+            self.nchunk.append(nchunk)
+            p = np.array([off + c * 8 * N for c in range(nchunk)], dtype=np.int32)
+            off += nchunk * 8 * N
+            self._keep.append(p)
+            cs.p = p.ctypes.data_as(c_int_p)
+            # multi-channel spectral model (residual.c:1177-1210); default: flat spectrum
+            for name, src in (("sI0", "sI"), ("sQ0", "sQ"), ("sU0", "sU"), ("sV0", "sV")):
+                a = np.ascontiguousarray(cl.get(name, cl[src]), dtype=np.float64)
+                self._keep.append(a)
+                setattr(cs, name, dptr(a))
+            f0 = np.ascontiguousarray(cl.get("f0", np.full(K, 150e6)), dtype=np.float64)
+            self._keep.append(f0)
+            cs.f0 = dptr(f0)
+            for name in ("spec_idx", "spec_idx1", "spec_idx2"):
+                a = np.ascontiguousarray(cl.get(name, np.zeros(K)), dtype=np.float64)
+                self._keep.append(a)
+                setattr(cs, name, dptr(a))
+        self.Mt = sum(self.nchunk)
+        self.nparam = off
+
+
+def make_barr(sta1, sta2, flag):
+    n = len(sta1)
+    barr = (baseline_t * n)()
+    view = np.ctypeslib.as_array(C.cast(barr, C.POINTER(C.c_int)), shape=(n, 3))
+    view[:, 0] = sta1
+    view[:, 1] = sta2
+    view[:, 2] = 0
+    fl = np.ctypeslib.as_array(C.cast(barr, c_ubyte_p), shape=(n, 12))
+    fl[:, 8] = np.asarray(flag, dtype=np.uint8)
+    return barr
+
+
+def barr_to_numpy(barr, n):
+    view = np.ctypeslib.as_array(C.cast(barr, C.POINTER(C.c_int)), shape=(n, 3))
+    fl = np.ctypeslib.as_array(C.cast(barr, c_ubyte_p), shape=(n, 12))
+    return view[:, 0].copy(), view[:, 1].copy(), fl[:, 8].copy()
+
+
+class DiracAPI:
+    """Binds the hot-path entry points of a Dirac-ABI shared library."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L = self.lib
+        bp = C.POINTER(baseline_t)
+        cp = C.POINTER(clus_source_t)
+        d = C.c_double
+        i = C.c_int
+        dp = c_double_p
+
+        L.sagefit_visibilities.restype = i
+        L.sagefit_visibilities.argtypes = [dp, dp, dp, dp, i, i, i, bp, cp, dp, i, i, d, d, dp, d,
+                                           i, i, i, i, i, i, i, i, d, d, i, dp, dp, dp]
+        L.bfgsfit_visibilities.restype = i
+        L.bfgsfit_visibilities.argtypes = [dp, dp, dp, dp, i, i, i, bp, cp, dp, i, i, d, d, dp, d,
+                                           i, i, i, i, i, d, dp, dp]
+        L.precalculate_coherencies.restype = i
+        L.precalculate_coherencies.argtypes = [dp, dp, dp, dp, i, i, bp, cp, i, d, d, d, d, d, d, i]
+        L.predict_visibilities_multifreq.restype = i
+        L.predict_visibilities_multifreq.argtypes = [dp, dp, dp, dp, i, i, i, bp, cp, i, dp, i,
+                                                     d, d, d, i, i]
+        L.generate_baselines.restype = i
+        L.generate_baselines.argtypes = [i, i, i, bp, i]
+        L.preset_flags_and_data.restype = i
+        L.preset_flags_and_data.argtypes = [i, dp, bp, dp, i]
+        if hasattr(L, "calculate_residuals_multifreq"):
+            L.calculate_residuals_multifreq.restype = i
+            L.calculate_residuals_multifreq.argtypes = [dp, dp, dp, dp, dp, i, i, i, bp, cp, i, dp,
+                                                        i, d, d, d, i, i, d, i]
+
+    # -- thin pythonic wrappers (argument order and meaning exactly as the C API) -----------------
+    def generate_baselines(self, Nbase, tilesz, N, Nt=4):
+        barr = (baseline_t * (Nbase * tilesz))()
+        self.lib.generate_baselines(Nbase, tilesz, N, barr, Nt)
+        return barr
+
+    def preset_flags_and_data(self, flag, barr, x, Nt=4):
+        return self.lib.preset_flags_and_data(len(flag), dptr(flag), barr, dptr(x), Nt)
+
+    def precalculate_coherencies(self, u, v, w, N, Nbase1, barr, sky: SkyModel, freq0, fdelta,
+                                 tdelta=10.0, dec0=1.0, uvmin=0.0, uvmax=1e9, Nt=4):
+        coh = np.zeros(4 * sky.M * Nbase1, dtype=np.complex128)
+        self.lib.precalculate_coherencies(dptr(u), dptr(v), dptr(w), cptr(coh), N, Nbase1, barr,
+                                          sky.arr, sky.M, freq0, fdelta, tdelta, dec0, uvmin,
+                                          uvmax, Nt)
+        return coh
+
+    def predict_visibilities_multifreq(self, u, v, w, x, N, Nbase, tilesz, barr, sky: SkyModel,
+                                       freqs, fdelta, tdelta=10.0, dec0=1.0, Nt=4, add_to_data=0):
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        return self.lib.predict_visibilities_multifreq(
+            dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M,
+            dptr(freqs), len(freqs), fdelta, tdelta, dec0, Nt, add_to_data)
+
+    def sagefit_visibilities(self, u, v, w, x, N, Nbase, tilesz, barr, sky: SkyModel, coh, pp,
+                             freq0=150e6, fdelta=195.3e3, uvmin=0.0, Nt=4, max_emiter=3,
+                             max_iter=2, max_lbfgs=10, lbfgs_m=7, gpu_threads=128, linsolv=0,
+                             solver_mode=SM_LM_LBFGS, nulow=2.0, nuhigh=30.0, randomize=0):
+        """x (data -> residual) and pp (Jones) are updated in place; returns
+        (retval, mean_nu, res_0, res_1)."""
+        mean_nu = C.c_double(0.0)
+        res0 = C.c_double(0.0)
+        res1 = C.c_double(0.0)
+        rv = self.lib.sagefit_visibilities(
+            dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, cptr(coh),
+            sky.M, sky.Mt, freq0, fdelta, dptr(pp), uvmin, Nt, max_emiter, max_iter, max_lbfgs,
+            lbfgs_m, gpu_threads, linsolv, solver_mode, nulow, nuhigh, randomize,
+            C.byref(mean_nu), C.byref(res0), C.byref(res1))
+        return rv, mean_nu.value, res0.value, res1.value
+
+    def bfgsfit_visibilities(self, u, v, w, x, N, Nbase, tilesz, barr, sky: SkyModel, coh, pp,
+                             freq0=150e6, fdelta=195.3e3, uvmin=0.0, Nt=4, max_lbfgs=10,
+                             lbfgs_m=7, gpu_threads=128, solver_mode=SM_LM_LBFGS, mean_nu=2.0):
+        res0 = C.c_double(0.0)
+        res1 = C.c_double(0.0)
+        rv = self.lib.bfgsfit_visibilities(
+            dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, cptr(coh),
+            sky.M, sky.Mt, freq0, fdelta, dptr(pp), uvmin, Nt, max_lbfgs, lbfgs_m, gpu_threads,
+            solver_mode, mean_nu, C.byref(res0), C.byref(res1))
+        return rv, res0.value, res1.value

@@ -1,0 +1,177 @@
+/*
+ * dirac_b200 — Blackwell (sm_100a) implementation of the Dirac direction-dependent calibration hot
+ * path.  C ABI only: plain pointers and sizes, host memory unless a name says otherwise.
+ *
+ * Two layers:
+ *  (1) the reference's own entry points, same names / argument order / meaning / error behaviour,
+ *      so that `sagecal_gpu` (src/MS/fullbatch_mode.cpp:371-446) links unchanged;
+ *  (2) a thin `dirac_b200_*` layer that exposes the device-resident problem and the individual
+ *      E-step passes (cost, gradient, normal equations), used by the parity tests, bench.py and
+ *      the multi-GPU driver.
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference
+ * repository root).
+ */
+#ifndef DIRAC_B200_H
+#define DIRAC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- ABI-compatible restatement of the reference structs ------------------------------------ */
+
+/* src/lib/Dirac/Dirac_common.h:190-195 */
+typedef struct baseline_t_ {
+  int sta1, sta2;
+  unsigned char flag; /* 0 ok, 1 flagged, 2 excluded from the solution (uv cut) but subtracted */
+} baseline_t;
+
+/* src/lib/Dirac/Dirac_common.h:173-187 */
+typedef struct clus_source_t_ {
+  int N;  /* sources in this cluster */
+  int id;
+  double *ll, *mm, *nn, *sI, *sQ, *sU, *sV;
+  double *ra, *dec;
+  unsigned char *stype;
+  void **ex;
+  int nchunk; /* hybrid time chunks */
+  int *p;     /* nchunk offsets into the parameter array */
+  double *sI0, *sQ0, *sU0, *sV0, *f0, *spec_idx, *spec_idx1, *spec_idx2;
+} clus_source_t;
+
+/* src/lib/Dirac/Dirac_common.h:56-61 */
+typedef struct exinfo_gaussian_ {
+  double eX, eY, eP;
+  double cxi, sxi, cphi, sphi;
+  int use_projection;
+} exinfo_gaussian;
+
+#define STYPE_POINT 0    /* src/lib/Radio/Dirac_radio.h:71-75 */
+#define STYPE_GAUSSIAN 1
+#define STYPE_DISK 2
+#define STYPE_RING 3
+#define STYPE_SHAPELET 4
+
+/* solver_mode, src/lib/Dirac/Dirac.h:1607-1613 */
+#define SM_LM_LBFGS 1
+#define SM_OSLM_LBFGS 0
+#define SM_OSLM_OSRLM_RLBFGS 3
+#define SM_RLM_RLBFGS 2
+#define SM_RTR_OSLM_LBFGS 4
+#define SM_RTR_OSRLM_RLBFGS 5
+#define SM_NSD_RLBFGS 6
+
+/* ---- (1) reference entry points --------------------------------------------------------------
+ * `coh` is `complex double *` in the reference (C99); it is declared `double *` here (re,im pairs,
+ * identical memory) so that the header is valid C++ as well. */
+
+/* replaces sagefit_visibilities, src/lib/Dirac/Dirac.h:1651 (lmfit.c:778-1053).
+ * x: data in, residual out (in place).  pp: Jones in/out.  returns 0, or -1 if res_1 > res_0. */
+int sagefit_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz,
+                         baseline_t *barr, clus_source_t *carr, double *coh, int M, int Mt,
+                         double freq0, double fdelta, double *pp, double uvmin, int Nt,
+                         int max_emiter, int max_iter, int max_lbfgs, int lbfgs_m, int gpu_threads,
+                         int linsolv, int solver_mode, double nulow, double nuhigh, int randomize,
+                         double *mean_nu, double *res_0, double *res_1);
+
+/* GPU-build names of the same call, src/lib/Dirac/Dirac.h:1783,1788,1793 (lmfit_cuda.c:575,1102,
+ * 1601; call sites src/MS/fullbatch_mode.cpp:442,446).  Aliases of sagefit_visibilities. */
+int sagefit_visibilities_dual_pt_flt(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                     int tilesz, baseline_t *barr, clus_source_t *carr,
+                                     double *coh, int M, int Mt, double freq0, double fdelta,
+                                     double *pp, double uvmin, int Nt, int max_emiter,
+                                     int max_iter, int max_lbfgs, int lbfgs_m, int gpu_threads,
+                                     int linsolv, int solver_mode, double nulow, double nuhigh,
+                                     int randomize, double *mean_nu, double *res_0, double *res_1);
+int sagefit_visibilities_dual_pt(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                 int tilesz, baseline_t *barr, clus_source_t *carr, double *coh,
+                                 int M, int Mt, double freq0, double fdelta, double *pp,
+                                 double uvmin, int Nt, int max_emiter, int max_iter, int max_lbfgs,
+                                 int lbfgs_m, int gpu_threads, int linsolv, int solver_mode,
+                                 double nulow, double nuhigh, int randomize, double *mean_nu,
+                                 double *res_0, double *res_1);
+int sagefit_visibilities_dual_pt_one_gpu(double *u, double *v, double *w, double *x, int N,
+                                         int Nbase, int tilesz, baseline_t *barr,
+                                         clus_source_t *carr, double *coh, int M, int Mt,
+                                         double freq0, double fdelta, double *pp, double uvmin,
+                                         int Nt, int max_emiter, int max_iter, int max_lbfgs,
+                                         int lbfgs_m, int gpu_threads, int linsolv,
+                                         int solver_mode, double nulow, double nuhigh,
+                                         int randomize, double *mean_nu, double *res_0,
+                                         double *res_1);
+
+/* replaces bfgsfit_visibilities, src/lib/Dirac/Dirac.h:1683 (lmfit.c:1127-1212) and its GPU-build
+ * twin bfgsfit_visibilities_gpu, Dirac.h:1690 (lmfit_cuda.c:1375). */
+int bfgsfit_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz,
+                         baseline_t *barr, clus_source_t *carr, double *coh, int M, int Mt,
+                         double freq0, double fdelta, double *pp, double uvmin, int Nt,
+                         int max_lbfgs, int lbfgs_m, int gpu_threads, int solver_mode,
+                         double mean_nu, double *res_0, double *res_1);
+int bfgsfit_visibilities_gpu(double *u, double *v, double *w, double *x, int N, int Nbase,
+                             int tilesz, baseline_t *barr, clus_source_t *carr, double *coh, int M,
+                             int Mt, double freq0, double fdelta, double *pp, double uvmin, int Nt,
+                             int max_lbfgs, int lbfgs_m, int gpu_threads, int solver_mode,
+                             double mean_nu, double *res_0, double *res_1);
+
+/* replaces precalculate_coherencies, src/lib/Radio/Dirac_radio.h:209 (predict.c:503-578).
+ * x: coherencies out, [row][cluster][4] complex.  Also sets barr[].flag=2 outside [uvmin,uvmax]. */
+int precalculate_coherencies(double *u, double *v, double *w, double *x, int N, int Nbase,
+                             baseline_t *barr, clus_source_t *carr, int M, double freq0,
+                             double fdelta, double tdelta, double dec0, double uvmin, double uvmax,
+                             int Nt);
+
+/* replaces predict_visibilities_multifreq, src/lib/Radio/Dirac_radio.h:659 (residual.c:1257-1340) */
+int predict_visibilities_multifreq(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                   int tilesz, baseline_t *barr, clus_source_t *carr, int M,
+                                   double *freqs, int Nchan, double fdelta, double tdelta,
+                                   double dec0, int Nt, int add_to_data);
+
+/* helpers the driver calls directly: src/lib/Dirac/Dirac.h generate_baselines
+ * (baseline_utils.c:469), preset_flags_and_data (baseline_utils.c:239).  Bit-exact index work. */
+int generate_baselines(int Nbase, int tilesz, int N, baseline_t *barr, int Nt);
+int preset_flags_and_data(int Nbase, double *flag, baseline_t *barr, double *x, int Nt);
+
+/* ---- (2) thin device layer ------------------------------------------------------------------- */
+
+typedef struct dirac_b200_problem dirac_b200_problem; /* opaque, device resident */
+
+/* Upload one solve interval.  coh may be NULL when the coherencies are generated on the device
+ * (dirac_b200_precalculate).  Replaces the per-call H2D churn of clmfit_fl.c:193-225 /
+ * lbfgs_cuda.c:93-131 with one resident copy.  Exits (reference convention) on CUDA failure. */
+dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz, const baseline_t *barr,
+                                      const clus_source_t *carr, int M, int Mt, const double *coh,
+                                      const double *x);
+void dirac_b200_destroy(dirac_b200_problem *pr);
+/* replace the data vector (8*Nbase*tilesz doubles, API layout) */
+void dirac_b200_set_data(dirac_b200_problem *pr, const double *x);
+/* device-side precalculate_coherencies (predict.c:345-497) into the resident planar layout;
+ * writes the uv-cut flags (value 2) into the resident flag array and, if barr != NULL, into barr. */
+void dirac_b200_precalculate(dirac_b200_problem *pr, const double *u, const double *v,
+                             const double *w, const clus_source_t *carr, double freq0,
+                             double fdelta, double uvmin, double uvmax, baseline_t *barr);
+/* copy the resident coherencies back in API layout ([row][cluster][4] complex) */
+void dirac_b200_get_coherencies(dirac_b200_problem *pr, double *coh);
+
+/* model / residual / cost over all clusters at Jones pp (minimize_viz_full_pth, lmfit.c:692;
+ * cost_func / robust_cost_func, robust_lbfgs.c:674,707).
+ * out_mode: 0 none, 1 out = x - V, 2 out = V (8*Nbase*tilesz doubles, API layout; out may be NULL)
+ * cost_mode: 0 none, 1 sum e^2, 2 sum log(1+e^2/nu) */
+double dirac_b200_predict(dirac_b200_problem *pr, const double *pp, double *out, int out_mode,
+                          int cost_mode, double nu);
+/* LBFGS gradient in the reference's sign convention (func_grad / func_grad_robust,
+ * robust_lbfgs.c:569-669,322-416); g has 8*N*Mt doubles. */
+void dirac_b200_grad(dirac_b200_problem *pr, const double *pp, double *g, int robust, double nu);
+/* per-cluster normal equations at pblk (8N doubles) for hybrid chunk `chunk` of cluster `clus`
+ * against the hidden data xd (API layout, full interval): JTJ (8N x 8N), JTe (8N), returns
+ * ||e||^2.  Equivalent of mylm_jac_single_pth + dgemm/dgemv (lmfit.c:484, clmfit.c:307-315). */
+double dirac_b200_normal_eq(dirac_b200_problem *pr, int clus, int chunk, const double *pblk,
+                            const double *xd, double *JTJ, double *JTe);
+
+/* number of kernels this library launched since load (bench.py's gpu_launches) */
+unsigned long long dirac_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

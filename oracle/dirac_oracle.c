@@ -1,0 +1,1 @@
+int dirac_oracle_placeholder(void){return 0;}

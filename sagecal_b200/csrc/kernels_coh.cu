@@ -1,0 +1,230 @@
+// Coherency prediction from the sky model on the device.
+//
+//   k_coherencies        one frequency, every cluster -> resident planar coh[k][4][R]
+//                        (replaces precal_threadfn, predict.c:345-497)
+//   k_predict_multifreq  sum over clusters per channel with spectral-index fluxes -> x[chan][row][8]
+//                        (replaces visibilities_threadfn_multifreq, residual.c:1067-1248)
+//
+// One thread per row (u,v,w coalesced in, 16-byte planar stores out).  The sources of a direction
+// are staged in shared memory by a 1-D TMA bulk copy (cp.async.bulk + mbarrier complete_tx),
+// double buffered so the copy of direction k+1 overlaps the trigonometry of direction k.  This
+// kernel is SFU/FP64-ALU bound (three sin/cos per source-row), not HBM bound.
+#include "internal.cuh"
+#include "coh.h"
+
+// ---- mbarrier / bulk-copy helpers (PTX ISA 8.x, sm_90+) ----------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared, bytes multiple of 16, both 16-byte aligned; completion on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                         unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- per-source term ------------------------------------------------------------------------------
+// phase * |sinc| smearing * shape factor for one source at one frequency (predict.c:411-470)
+__device__ __forceinline__ double2 source_phase(const DevSource &s, double u, double v, double w,
+                                                double freq, double fdelta2) {
+  const double G = 2.0 * M_PI * (u * s.ll + v * s.mm + w * s.nn);
+  double sp, cp;
+  sincos(G * freq, &sp, &cp);
+  double fac = 1.0;
+  if (G != 0.0) {
+    const double sm = G * fdelta2;
+    fac = fabs(sin(sm) / sm);
+  }
+  double2 ph = make_double2(cp * fac, sp * fac);
+  const int st = (int)s.stype;
+  if (st != STYPE_POINT_) {
+    const double uf = u * freq, vf = v * freq, wf = w * freq;
+    double up, vp;
+    if (st == STYPE_GAUSSIAN_ && s.use_projection == 0.0) {
+      up = uf;
+      vp = vf;
+    } else {
+      up = uf * s.cxi - vf * s.cphi * s.sxi + wf * s.sphi * s.sxi;
+      vp = uf * s.sxi + vf * s.cphi * s.cxi - wf * s.sphi * s.cxi;
+    }
+    double shape = 1.0;
+    if (st == STYPE_GAUSSIAN_) {
+      double sph, cph;
+      sincos(s.eP, &sph, &cph);
+      const double ut = s.eX * (cph * up - sph * vp);
+      const double vt = s.eY * (sph * up + cph * vp);
+      shape = exp(-2.0 * M_PI * M_PI * (ut * ut + vt * vt));
+    } else if (st == STYPE_DISK_) {
+      shape = j1(sqrt(up * up + vp * vp) * s.eX * 2.0 * M_PI);
+    } else if (st == STYPE_RING_) {
+      shape = j0(sqrt(up * up + vp * vp) * s.eX * 2.0 * M_PI);
+    }
+    ph.x *= shape;
+    ph.y *= shape;
+  }
+  return ph;
+}
+
+__device__ __forceinline__ void add_stokes(double2 *C, double2 ph, double I, double Q, double U,
+                                           double V) {
+  // C0 += ph (I+Q); C1 += ph (U + iV); C2 += ph (U - iV); C3 += ph (I-Q)   (predict.c:466-476)
+  const double2 II = make_double2(ph.x * I, ph.y * I), QQ = make_double2(ph.x * Q, ph.y * Q);
+  const double2 UU = make_double2(ph.x * U, ph.y * U), VV = make_double2(ph.x * V, ph.y * V);
+  C[0].x += II.x + QQ.x;  C[0].y += II.y + QQ.y;
+  C[1].x += UU.x - VV.y;  C[1].y += UU.y + VV.x;
+  C[2].x += UU.x + VV.y;  C[2].y += UU.y - VV.x;
+  C[3].x += II.x - QQ.x;  C[3].y += II.y - QQ.y;
+}
+
+// flux at frequency f with the three-term log-spectral index (residual.c:1177-1210)
+__device__ __forceinline__ double spec_flux(double s0, double tempfr) {
+  if (s0 > 0.0) return exp(log(s0) + tempfr);
+  return (s0 == 0.0) ? 0.0 : -exp(log(-s0) + tempfr);
+}
+
+#define COH_THREADS 128
+
+// MODE 0: coherencies per cluster at freq[0] -> planar coh ; MODE 1: multifreq sum -> xout
+template <int MODE>
+__global__ void __launch_bounds__(COH_THREADS)
+k_sky_predict(CohArgs a) {
+  __shared__ __align__(128) DevSource sbuf[2][COH_SEG_MAX];
+  __shared__ __align__(8) unsigned long long bar[2];
+  const long long r = (long long)blockIdx.x * COH_THREADS + threadIdx.x;
+  const bool active = r < a.R;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double u = 0.0, v = 0.0, w = 0.0;
+  if (active) {
+    u = a.u[r];
+    v = a.v[r];
+    w = a.w[r];
+  }
+  const int nchan = (MODE == 0) ? 1 : a.Nchan;
+  // prologue: stage segment 0
+  if (threadIdx.x == 0 && a.nseg > 0) {
+    const CohSegment sg = a.segs[0];
+    const unsigned bytes = (unsigned)sg.count * (unsigned)sizeof(DevSource);
+    mbar_expect_tx(&bar[0], bytes);
+    if (bytes) bulk_g2s(&sbuf[0][0], a.src + sg.first, bytes, &bar[0]);
+  }
+  for (int cf = 0; cf < nchan; cf++) {
+    // (channels re-walk the segment list; the staging pipeline simply continues)
+    double2 X[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) X[c] = make_double2(0.0, 0.0);
+    const double freq = a.freqs[cf];
+    double2 C[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) C[c] = make_double2(0.0, 0.0);
+    for (int sgi = 0; sgi < a.nseg; sgi++) {
+      const int it = cf * a.nseg + sgi;  // global staging iteration
+      const int b = it & 1;
+      // stage the next segment (of this or the next channel) into the other buffer
+      if (threadIdx.x == 0) {
+        int nxt = sgi + 1;
+        bool more = true;
+        if (nxt == a.nseg) {
+          nxt = 0;
+          more = (cf + 1 < nchan);
+        }
+        if (more) {
+          const CohSegment sn = a.segs[nxt];
+          const unsigned bytes = (unsigned)sn.count * (unsigned)sizeof(DevSource);
+          mbar_expect_tx(&bar[b ^ 1], bytes);
+          if (bytes) bulk_g2s(&sbuf[b ^ 1][0], a.src + sn.first, bytes, &bar[b ^ 1]);
+        }
+      }
+      const CohSegment sg = a.segs[sgi];
+      mbar_wait(&bar[b], (unsigned)((it >> 1) & 1));
+      if (active) {
+        for (int s = 0; s < sg.count; s++) {
+          const DevSource &S = sbuf[b][s];
+          const double2 ph = source_phase(S, u, v, w, freq, a.fdelta2);
+          double I = S.sI, Q = S.sQ, U = S.sU, V = S.sV;
+          if (MODE == 1 && S.spec_idx != 0.0) {
+            const double fr = log(freq / S.f0);
+            const double fr1 = fr * fr, fr2 = fr1 * fr;
+            const double tf = S.spec_idx * fr + S.spec_idx1 * fr1 + S.spec_idx2 * fr2;
+            I = spec_flux(S.sI0, tf);
+            Q = spec_flux(S.sQ0, tf);
+            U = spec_flux(S.sU0, tf);
+            V = spec_flux(S.sV0, tf);
+          }
+          add_stokes(C, ph, I, Q, U, V);
+        }
+        if (sg.last) {
+          if (MODE == 0) {
+            double2 *ck = a.coh + (long long)sg.cluster * 4 * a.R;
+#pragma unroll
+            for (int c = 0; c < 4; c++) st_stream(ck + (long long)c * a.R + r, C[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) X[c] = cadd(X[c], C[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; c++) C[c] = make_double2(0.0, 0.0);
+        }
+      }
+      __syncthreads();  // everyone is done with sbuf[b] before it is refilled two iterations on
+    }
+    if (MODE == 1 && active) {
+      double2 *xo = a.xout + ((long long)cf * a.R + r) * 4;
+#pragma unroll
+      for (int c = 0; c < 4; c++) xo[c] = cadd(xo[c], X[c]);
+    }
+  }
+  if (MODE == 0 && active && a.flag) {
+    // uv cut: unflagged rows outside [uvmin, uvmax] get flag 2 (predict.c:488-493)
+    if (a.flag[r] == 0) {
+      const double uvdist = sqrt(u * u + v * v) * a.freqs[0];
+      if (uvdist < a.uvmin || uvdist > a.uvmax) a.flag[r] = 2;
+    }
+  }
+}
+
+extern "C" {
+void db_launch_coherencies(const CohArgs *a, cudaStream_t st) {
+  unsigned grid = (unsigned)((a->R + COH_THREADS - 1) / COH_THREADS);
+  k_sky_predict<0><<<grid, COH_THREADS, 0, st>>>(*a);
+}
+void db_launch_predict_multifreq(const CohArgs *a, cudaStream_t st) {
+  unsigned grid = (unsigned)((a->R + COH_THREADS - 1) / COH_THREADS);
+  k_sky_predict<1><<<grid, COH_THREADS, 0, st>>>(*a);
+}
+}

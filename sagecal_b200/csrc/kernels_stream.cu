@@ -1,0 +1,537 @@
+// Streaming sm_100a kernels of the calibration E-step: every kernel makes one pass over planar
+// coherencies / visibilities in HBM with 128-bit coalesced loads (a warp = one station p against
+// 32 consecutive stations q, 512 contiguous bytes per polarisation product per timeslot).
+//
+//   k_predict_full   : V = sum_k J_kp C_k J_kq^H over all clusters, residual / cost
+//                      (replaces predict_threadfn_withgain_full, lmfit.c:611-688, plus
+//                       cost_func / robust_cost_func, robust_lbfgs.c:674-726)
+//   k_grad_full      : LBFGS gradient over all clusters from a stored residual
+//                      (replaces cpu_calc_deriv(_robust), robust_lbfgs.c:424-560,155-316, which
+//                       loop per PARAMETER over all rows; here one pass over rows)
+//   k_cluster_pass   : per-cluster E-step pass of the LM solver: model of one cluster, residual,
+//                      cost and J^T e in a single sweep (replaces predict_threadfn_withgain(0),
+//                      lmfit.c:64-124,233-296 + the J^T e dgemv of clmfit.c:315)
+//   k_coh_gram       : per-baseline time sums conj(C) (x) C from which J^T J is assembled without
+//                      ever forming the dense Jacobian (jacobian_threadfn, lmfit.c:392-474 +
+//                      dgemm, clmfit.c:307)
+#include "internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion (API layout <-> planar device layout)
+// ------------------------------------------------------------------------------------------------
+// src: rows [r0, r0+nr) of the API coherency array, [row][M][4] complex; dst planar [M][4][R]
+// block (32 clusters, 8 rows): 64 B contiguous reads per thread (2 KB per warp), 128 B row-runs out
+#define XP_ROWS 8
+__global__ void k_coh_to_planar(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                long long r0, int nr, int M, long long R) {
+  __shared__ double2 tile[4][XP_ROWS][33];
+  const int kx = blockIdx.x * 32 + threadIdx.x;
+  const int ry = blockIdx.y * XP_ROWS + threadIdx.y;
+  if (kx < M && ry < nr) {
+    const double2 *s = src + ((long long)ry * M + kx) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; c++) tile[c][threadIdx.y][threadIdx.x] = s[c];
+  }
+  __syncthreads();
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int rr = tid % XP_ROWS, kk = tid / XP_ROWS;
+  const int k = blockIdx.x * 32 + kk;
+  const int r = blockIdx.y * XP_ROWS + rr;
+  if (k < M && r < nr) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) dst[((long long)k * 4 + c) * R + r0 + r] = tile[c][rr][kk];
+  }
+}
+
+// planar [M][4][R] -> API layout rows [r0, r0+nr)
+__global__ void k_coh_from_planar(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                  long long r0, int nr, int M, long long R) {
+  __shared__ double2 tile[4][XP_ROWS][33];
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int rr = tid % XP_ROWS, kk = tid / XP_ROWS;
+  const int k = blockIdx.x * 32 + kk;
+  const int r = blockIdx.y * XP_ROWS + rr;
+  if (k < M && r < nr) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) tile[c][rr][kk] = src[((long long)k * 4 + c) * R + r0 + r];
+  }
+  __syncthreads();
+  const int kx = blockIdx.x * 32 + threadIdx.x;
+  const int ry = blockIdx.y * XP_ROWS + threadIdx.y;
+  if (kx < M && ry < nr) {
+    double2 *d = dst + ((long long)ry * M + kx) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; c++) d[c] = tile[c][threadIdx.y][threadIdx.x];
+  }
+}
+
+// API visibilities [row][4] complex <-> planar [4][R]
+__global__ void k_vis_to_planar(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                long long R) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over 4*R, c fastest in src
+  if (i < 4 * R) {
+    long long r = i >> 2;
+    int c = (int)(i & 3);
+    dst[(long long)c * R + r] = src[i];
+  }
+}
+__global__ void k_vis_from_planar(const double2 *__restrict__ src, double2 *__restrict__ dst,
+                                  long long R) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * R) {
+    long long r = i >> 2;
+    int c = (int)(i & 3);
+    dst[i] = src[(long long)c * R + r];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic grid reduction: per-CTA partial, the last CTA to arrive sums them in index order
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_reduce_sum(double v, double *partials, double *out,
+                                                unsigned int *counter) {
+  __shared__ double wsum[32];
+  __shared__ bool is_last;
+  v = warp_sum(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wsum[w] = v;
+  __syncthreads();
+  unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+  unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; i++) s += wsum[i];
+    partials[bid] = s;
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    // fixed-order tree: thread i sums partials i, i+T, ...; then block tree
+    double s = 0.0;
+    for (unsigned int i = threadIdx.x; i < nblocks; i += blockDim.x)
+      s += ((volatile double *)partials)[i];
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) wsum[w] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      int nw = (blockDim.x + 31) >> 5;
+      for (int i = 0; i < nw; i++) tot += wsum[i];
+      *out = tot;
+      *counter = 0;  // re-arm for the next launch
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// full predict over all clusters
+// ------------------------------------------------------------------------------------------------
+
+template <int TB>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_predict_full(PredictArgs a) {
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = td.pb * TILE_P + w;
+  const int q = td.qb * TILE_Q + lane;
+  const bool valid = (q > p) && (q < a.N);
+  const int t0 = blockIdx.y * TB;
+  double cost = 0.0;
+  if (valid) {
+    const long long b = baseline_index(p, q, a.N);
+    double2 acc[TB][4];
+    bool fl[TB];
+    long long row[TB];
+#pragma unroll
+    for (int i = 0; i < TB; i++) {
+      int t = t0 + i;
+      row[i] = (long long)(t < a.tilesz ? t : a.tilesz - 1) * a.Nbase + b;
+      fl[i] = (t < a.tilesz) ? (a.flag[row[i]] != 0) : true;
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[i][c] = make_double2(0.0, 0.0);
+    }
+    for (int k = 0; k < a.M; k++) {
+      const ClusterDesc cd = a.clus[k];
+      const double2 *ck = a.coh + (long long)k * 4 * a.R;
+      double2 Jp[4], Jq[4];
+      int cur = -1;
+#pragma unroll
+      for (int i = 0; i < TB; i++) {
+        double2 C[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) C[c] = ld_stream(ck + (long long)c * a.R + row[i]);
+        int px = row_chunk(row[i], a.R, cd.nchunk);
+        if (px != cur) {
+          const double *pblk = a.pp + a.chunk_poff[cd.chunk0 + px];
+          load_jones(pblk, p, Jp);
+          load_jones(pblk, q, Jq);
+          cur = px;
+        }
+        double2 T1[4], T2[4];
+        mat_ab(Jp, C, T1);
+        mat_abh(T1, Jq, T2);
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[i][c] = cadd(acc[i][c], T2[c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TB; i++) {
+      if (t0 + i < a.tilesz) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          double2 m = fl[i] ? make_double2(0.0, 0.0) : acc[i][c];
+          double2 xv = make_double2(0.0, 0.0);
+          if (a.out_mode == 1 || a.cost_mode) xv = ld_stream(a.x + (long long)c * a.R + row[i]);
+          double2 e = csub(xv, m);
+          if (a.out_mode == 1) st_stream(a.out + (long long)c * a.R + row[i], e);
+          if (a.out_mode == 2) st_stream(a.out + (long long)c * a.R + row[i], m);
+          if (a.cost_mode == 1) {
+            cost = fma(e.x, e.x, cost);
+            cost = fma(e.y, e.y, cost);
+          } else if (a.cost_mode == 2) {
+            cost += log(1.0 + e.x * e.x * a.inv_nu);
+            cost += log(1.0 + e.y * e.y * a.inv_nu);
+          }
+        }
+      }
+    }
+  }
+  if (a.cost_mode) grid_reduce_sum(cost, a.partials, a.cost, a.counter);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared epilogue: reduce per-thread station gradients of a tile and add them to g (8 doubles per
+// station).  Gp belongs to station p (shared by the whole warp), Gq to station q (one per lane,
+// shared by the 8 warps of the CTA).  warp-shuffle reduction for p, smem transpose for q.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_reduce_station_grad(const double2 *Gp, const double2 *Gq,
+                                                          double *gblk, int p, int q, int N,
+                                                          bool pvalid, double (*sq)[8][TILE_Q],
+                                                          double scale) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // station p: butterfly over the 32 lanes
+  double vp[8];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    vp[2 * c] = warp_sum(Gp[c].x);
+    vp[2 * c + 1] = warp_sum(Gp[c].y);
+  }
+  if (pvalid && lane < 8) {
+    double v = vp[0];
+#pragma unroll
+    for (int c = 1; c < 8; c++) v = (lane == c) ? vp[c] : v;
+    atomicAdd(gblk + 8 * (long long)p + lane, scale * v);
+  }
+  // station q: [warp][component][lane] in smem, warp c sums component c over the 8 warps
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    sq[w][2 * c][lane] = Gq[c].x;
+    sq[w][2 * c + 1][lane] = Gq[c].y;
+  }
+  __syncthreads();
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < TILE_P; ww++) s += sq[ww][w][lane];
+    if (q < N && s != 0.0) atomicAdd(gblk + 8 * (long long)q + w, scale * s);
+  }
+  __syncthreads();
+}
+
+// contraction of the time-summed outer product W[i][j][l][m] = sum_t R_ij conj(C_lm) with the Jones
+// matrices:   Gp = R Jq C^H -> Gp_il = sum_{j,m} Jq_jm W[i,j,l,m]
+//             Gq = R^H Jp C -> Gq_jm = sum_{i,l} Jp_il conj(W[i,j,l,m])
+// (the 8 reals of Gp/Gq are d(cost)/d(Re,Im of J_p,il / J_q,jm) up to the factor 2, see
+//  DESIGN.md "closed-form gradient"; cf. the per-parameter E_col products of lmfit.c:436-466)
+__device__ __forceinline__ void contract_W(const double2 *W, const double2 *Jp, const double2 *Jq,
+                                           double2 *Gp, double2 *Gq) {
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int m = 0; m < 2; m++) cfma(s, Jq[2 * j + m], W[((i * 2 + j) * 2 + l) * 2 + m]);
+      Gp[2 * i + l] = cadd(Gp[2 * i + l], s);
+    }
+#pragma unroll
+  for (int j = 0; j < 2; j++)
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+      double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int l = 0; l < 2; l++) cfmac(s, Jp[2 * i + l], W[((i * 2 + j) * 2 + l) * 2 + m]);
+      Gq[2 * j + m] = cadd(Gq[2 * j + m], s);
+    }
+}
+
+// W += R (x) conj(C)
+__device__ __forceinline__ void accum_W(double2 *W, const double2 *Rm, const double2 *C) {
+#pragma unroll
+  for (int ij = 0; ij < 4; ij++)
+#pragma unroll
+    for (int lm = 0; lm < 4; lm++) cfmac(W[ij * 4 + lm], Rm[ij], C[lm]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LBFGS gradient over all clusters
+// ------------------------------------------------------------------------------------------------
+
+template <int TB>
+__global__ void __launch_bounds__(TILE_THREADS)
+k_grad_full(GradArgs a) {
+  __shared__ double sq[TILE_P][8][TILE_Q];
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = td.pb * TILE_P + w;
+  const int q = td.qb * TILE_Q + lane;
+  const bool valid = (q > p) && (q < a.N);
+  const int t0 = blockIdx.y * TB;
+  const long long b = valid ? baseline_index(p, q, a.N) : 0;
+  double2 Rm[TB][4];
+  long long row[TB];
+  bool use[TB];
+#pragma unroll
+  for (int i = 0; i < TB; i++) {
+    int t = t0 + i;
+    row[i] = (long long)(t < a.tilesz ? t : a.tilesz - 1) * a.Nbase + b;
+    use[i] = valid && (t < a.tilesz) && (a.flag[row[i]] == 0);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      double2 e = make_double2(0.0, 0.0);
+      if (use[i]) {
+        e = ld_stream(a.res + (long long)c * a.R + row[i]);
+        if (a.robust) {
+          e.x = e.x / (a.nu + e.x * e.x);
+          e.y = e.y / (a.nu + e.y * e.y);
+        }
+      }
+      Rm[i][c] = e;
+    }
+  }
+  for (int k = 0; k < a.M; k++) {
+    const ClusterDesc cd = a.clus[k];
+    const double2 *ck = a.coh + (long long)k * 4 * a.R;
+    // gradient chunk of a timeslot: t / ceil(tilesz/nchunk)   (robust_lbfgs.c:464-470)
+    const int tpc = (a.tilesz + cd.nchunk - 1) / cd.nchunk;
+    int i0 = 0;
+    while (i0 < TB) {  // runs of timeslots that share a chunk (one run unless hybrid)
+      const int chunk = (t0 + i0 < a.tilesz ? t0 + i0 : a.tilesz - 1) / tpc;
+      double2 W[16];
+#pragma unroll
+      for (int z = 0; z < 16; z++) W[z] = make_double2(0.0, 0.0);
+      int i1 = i0;
+#pragma unroll
+      for (int i = 0; i < TB; i++) {
+        if (i >= i0 && i == i1) {
+          int t = t0 + i;
+          int ch = (t < a.tilesz ? t : a.tilesz - 1) / tpc;
+          if (ch == chunk) {
+            i1 = i + 1;
+            if (use[i]) {
+              double2 C[4];
+#pragma unroll
+              for (int c = 0; c < 4; c++) C[c] = ld_stream(ck + (long long)c * a.R + row[i]);
+              accum_W(W, Rm[i], C);
+            }
+          }
+        }
+      }
+      double *gblk = a.g + a.chunk_poff[cd.chunk0 + chunk];
+      double2 Jp[4], Jq[4], Gp[4], Gq[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        Jp[c] = Jq[c] = Gp[c] = Gq[c] = make_double2(0.0, 0.0);
+      }
+      if (valid) {
+        const double *pblk = a.pp + a.chunk_poff[cd.chunk0 + chunk];
+        load_jones(pblk, p, Jp);
+        load_jones(pblk, q, Jq);
+        contract_W(W, Jp, Jq, Gp, Gq);
+      }
+      tile_reduce_station_grad(Gp, Gq, gblk, p, q, a.N, p < a.N - 1, sq, a.scale);
+      i0 = i1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-cluster E-step pass (LM): one cluster, one hybrid chunk, timeslots [t_begin, t_end)
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_cluster_pass(ClusterPassArgs a) {
+  __shared__ double sq[TILE_P][8][TILE_Q];
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = td.pb * TILE_P + w;
+  const int q = td.qb * TILE_Q + lane;
+  const bool valid = (q > p) && (q < a.N);
+  const int ts = a.t_begin + blockIdx.y * a.tslice;
+  const int te = min(ts + a.tslice, a.t_end);
+  const bool want_grad = (a.jte != nullptr) && (a.mode <= 1);
+  double cost = 0.0;
+  double2 Jp[4], Jq[4], W[16];
+#pragma unroll
+  for (int z = 0; z < 16; z++) W[z] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) Jp[c] = Jq[c] = make_double2(0.0, 0.0);
+  if (valid) {
+    load_jones(a.pblk, p, Jp);
+    load_jones(a.pblk, q, Jq);
+    const long long b = baseline_index(p, q, a.N);
+#pragma unroll 2
+    for (int t = ts; t < te; t++) {
+      const long long row = (long long)t * a.Nbase + b;
+      double2 C[4], v[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) C[c] = ld_stream(a.coh_k + (long long)c * a.R + row);
+#pragma unroll
+      for (int c = 0; c < 4; c++) v[c] = ld_stream(a.in + (long long)c * a.R + row);
+      const bool fl = a.flag[row] != 0;
+      double2 T1[4], m[4];
+      mat_ab(Jp, C, T1);
+      mat_abh(T1, Jq, m);
+      if (fl) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) m[c] = make_double2(0.0, 0.0);
+      }
+      double2 e[4];
+      if (a.mode == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          double2 d = cadd(v[c], m[c]);
+          if (a.write_out) st_stream(a.out + (long long)c * a.R + row, d);
+          e[c] = csub(d, m[c]);
+        }
+      } else if (a.mode == 2) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) st_stream(a.out + (long long)c * a.R + row, cadd(v[c], m[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          e[c] = csub(v[c], m[c]);
+          if (a.write_out) st_stream(a.out + (long long)c * a.R + row, e[c]);
+        }
+      }
+      if (a.mode <= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          cost = fma(e[c].x, e[c].x, cost);
+          cost = fma(e[c].y, e[c].y, cost);
+        }
+        if (want_grad && !fl) accum_W(W, e, C);
+      }
+    }
+  }
+  if (want_grad) {
+    double2 Gp[4], Gq[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) Gp[c] = Gq[c] = make_double2(0.0, 0.0);
+    if (valid) contract_W(W, Jp, Jq, Gp, Gq);
+    tile_reduce_station_grad(Gp, Gq, a.jte, p, q, a.N, p < a.N - 1, sq, 1.0);
+  }
+  if (a.mode <= 1) grid_reduce_sum(cost, a.partials, a.cost, a.counter);
+}
+
+// ------------------------------------------------------------------------------------------------
+// time-summed Gram tensor of the coherencies of each baseline:
+//   T[b][16] = Hermitian 4x4  sum_t conj(c) c^T,  c = (C00,C01,C10,C11), unflagged rows only
+// stored as: 4 real diagonals, then the 6 complex upper off-diagonals (01,02,03,12,13,23)
+// grid (ntile, nclusters); the time range of one hybrid chunk / OS subset per launch
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TILE_THREADS)
+k_coh_gram(GramArgs a) {
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = td.pb * TILE_P + w;
+  const int q = td.qb * TILE_Q + lane;
+  if (!((q > p) && (q < a.N))) return;
+  const long long b = baseline_index(p, q, a.N);
+  const double2 *ck = a.coh + (long long)(a.k0 + blockIdx.y) * 4 * a.R;
+  double d[4] = {0.0, 0.0, 0.0, 0.0};
+  double2 o[6];
+#pragma unroll
+  for (int z = 0; z < 6; z++) o[z] = make_double2(0.0, 0.0);
+#pragma unroll 4
+  for (int t = a.t_begin; t < a.t_end; t += a.t_step) {
+    const long long row = (long long)t * a.Nbase + b;
+    double2 C[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) C[c] = ld_stream(ck + (long long)c * a.R + row);
+    if (a.flag[row] == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        d[c] = fma(C[c].x, C[c].x, d[c]);
+        d[c] = fma(C[c].y, C[c].y, d[c]);
+      }
+      cfmacl(o[0], C[0], C[1]);
+      cfmacl(o[1], C[0], C[2]);
+      cfmacl(o[2], C[0], C[3]);
+      cfmacl(o[3], C[1], C[2]);
+      cfmacl(o[4], C[1], C[3]);
+      cfmacl(o[5], C[2], C[3]);
+    }
+  }
+  double2 *Tb = reinterpret_cast<double2 *>(a.T + ((long long)blockIdx.y * a.Nbase + b) * 16);
+  Tb[0] = make_double2(d[0], d[1]);
+  Tb[1] = make_double2(d[2], d[3]);
+#pragma unroll
+  for (int z = 0; z < 6; z++) Tb[2 + z] = o[z];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+void db_launch_coh_to_planar(const double2 *src, double2 *dst, long long r0, int nr, int M,
+                             long long R, cudaStream_t st) {
+  dim3 block(32, XP_ROWS), grid((M + 31) / 32, (nr + XP_ROWS - 1) / XP_ROWS);
+  k_coh_to_planar<<<grid, block, 0, st>>>(src, dst, r0, nr, M, R);
+}
+void db_launch_coh_from_planar(const double2 *src, double2 *dst, long long r0, int nr, int M,
+                               long long R, cudaStream_t st) {
+  dim3 block(32, XP_ROWS), grid((M + 31) / 32, (nr + XP_ROWS - 1) / XP_ROWS);
+  k_coh_from_planar<<<grid, block, 0, st>>>(src, dst, r0, nr, M, R);
+}
+void db_launch_vis_to_planar(const double2 *src, double2 *dst, long long R, cudaStream_t st) {
+  long long n = 4 * R;
+  k_vis_to_planar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, R);
+}
+void db_launch_vis_from_planar(const double2 *src, double2 *dst, long long R, cudaStream_t st) {
+  long long n = 4 * R;
+  k_vis_from_planar<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, R);
+}
+
+#define PREDICT_TB 4
+int db_predict_nblocks(int ntile, int tilesz) { return ntile * ((tilesz + PREDICT_TB - 1) / PREDICT_TB); }
+void db_launch_predict_full(const PredictArgs *a, int ntile, cudaStream_t st) {
+  dim3 grid(ntile, (a->tilesz + PREDICT_TB - 1) / PREDICT_TB);
+  k_predict_full<PREDICT_TB><<<grid, TILE_THREADS, 0, st>>>(*a);
+}
+void db_launch_grad_full(const GradArgs *a, int ntile, cudaStream_t st) {
+  dim3 grid(ntile, (a->tilesz + PREDICT_TB - 1) / PREDICT_TB);
+  k_grad_full<PREDICT_TB><<<grid, TILE_THREADS, 0, st>>>(*a);
+}
+int db_cluster_pass_nblocks(int ntile, int nt, int tslice) { return ntile * ((nt + tslice - 1) / tslice); }
+void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st) {
+  int nt = a->t_end - a->t_begin;
+  dim3 grid(ntile, (nt + a->tslice - 1) / a->tslice);
+  k_cluster_pass<<<grid, TILE_THREADS, 0, st>>>(*a);
+}
+void db_launch_coh_gram(const GramArgs *a, int ntile, int nk, cudaStream_t st) {
+  dim3 grid(ntile, nk);
+  k_coh_gram<<<grid, TILE_THREADS, 0, st>>>(*a);
+}
+
+}  // extern "C"

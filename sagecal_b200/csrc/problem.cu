@@ -1,0 +1,281 @@
+// Device-resident problem ("one solve interval") and the thin dirac_b200_* layer over the kernels.
+// Replaces the per-call H2D copies / cudaMalloc churn of the reference GPU path
+// (clmfit_fl.c:193-225, lbfgs_cuda.c:93-131, mderiv.cu:1402-1460) with one resident copy.
+#include <string.h>
+#include <vector>
+
+#include "../../include/dirac_b200.h"
+#include "internal.cuh"
+#include "problem.h"
+
+static unsigned long long g_launches = 0;
+void db_count_launch(int n) { g_launches += (unsigned long long)n; }
+extern "C" unsigned long long dirac_b200_launch_count(void) { return g_launches; }
+
+static void require_gpu() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fprintf(stderr,
+            "dirac_b200: no CUDA device available (%s). This library has no CPU fallback.\n",
+            cudaGetErrorString(e));
+    exit(1);
+  }
+}
+
+template <typename T>
+static T *dev_alloc(size_t n) {
+  T *p = nullptr;
+  DB_CHECK(cudaMalloc((void **)&p, n * sizeof(T) + 16));
+  return p;
+}
+
+static void build_tiles(int N, std::vector<TileDesc> &tiles) {
+  int npb = (N - 1 + TILE_P - 1) / TILE_P;  // p in [0, N-2]
+  int nqb = (N + TILE_Q - 1) / TILE_Q;
+  for (int pb = 0; pb < npb; pb++)
+    for (int qb = 0; qb < nqb; qb++) {
+      int pmin = pb * TILE_P;
+      int qmax = qb * TILE_Q + TILE_Q - 1;
+      if (qmax > N - 1) qmax = N - 1;
+      if (qmax > pmin) {
+        TileDesc t;
+        t.pb = (short)pb;
+        t.qb = (short)qb;
+        tiles.push_back(t);
+      }
+    }
+}
+
+extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
+                                                 const baseline_t *barr, const clus_source_t *carr,
+                                                 int M, int Mt, const double *coh,
+                                                 const double *x) {
+  require_gpu();
+  if (Nbase != N * (N - 1) / 2) {
+    fprintf(stderr, "dirac_b200: Nbase=%d is not N(N-1)/2 for N=%d; only the canonical baseline "
+                    "set of generate_baselines is supported\n", Nbase, N);
+    exit(1);
+  }
+  if (N > 32767) {
+    fprintf(stderr, "dirac_b200: N=%d stations exceed the supported 32767\n", N);
+    exit(1);
+  }
+  dirac_b200_problem *pr = new dirac_b200_problem();
+  memset(&pr->d, 0, sizeof(DevProblem));
+  DevProblem &d = pr->d;
+  d.N = N; d.Nbase = Nbase; d.tilesz = tilesz; d.M = M; d.Mt = Mt;
+  d.R = (long long)Nbase * tilesz;
+  DB_CHECK(cudaGetDevice(&d.device));
+  DB_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+  const long long R = d.R;
+
+  // --- row order must be the canonical one (baseline_utils.c:445-461): checked, bit-exact ---
+  std::vector<unsigned char> hflag(R);
+  {
+    long long r = 0;
+    for (int t = 0; t < tilesz; t++)
+      for (int p = 0; p < N - 1; p++)
+        for (int q = p + 1; q < N; q++, r++) {
+          if (barr[r].sta1 != p || barr[r].sta2 != q) {
+            fprintf(stderr, "dirac_b200: barr[%lld]=(%d,%d) is not the canonical (%d,%d) of "
+                            "generate_baselines; unsupported row order\n",
+                    r, barr[r].sta1, barr[r].sta2, p, q);
+            exit(1);
+          }
+          hflag[r] = barr[r].flag;
+        }
+  }
+  d.flag = dev_alloc<unsigned char>(R);
+  DB_CHECK(cudaMemcpy(d.flag, hflag.data(), R, cudaMemcpyHostToDevice));
+
+  // --- cluster / chunk tables ---
+  d.h_clus = (ClusterDesc *)malloc(sizeof(ClusterDesc) * M);
+  int mt = 0;
+  for (int k = 0; k < M; k++) {
+    d.h_clus[k].nchunk = carr[k].nchunk;
+    d.h_clus[k].chunk0 = mt;
+    mt += carr[k].nchunk;
+  }
+  if (mt != Mt) {
+    fprintf(stderr, "dirac_b200: sum of nchunk (%d) != Mt (%d)\n", mt, Mt);
+    exit(1);
+  }
+  d.h_chunk_poff = (int *)malloc(sizeof(int) * Mt);
+  for (int k = 0; k < M; k++)
+    for (int c = 0; c < carr[k].nchunk; c++) d.h_chunk_poff[d.h_clus[k].chunk0 + c] = carr[k].p[c];
+  d.clus = dev_alloc<ClusterDesc>(M);
+  d.chunk_poff = dev_alloc<int>(Mt);
+  DB_CHECK(cudaMemcpy(d.clus, d.h_clus, sizeof(ClusterDesc) * M, cudaMemcpyHostToDevice));
+  DB_CHECK(cudaMemcpy(d.chunk_poff, d.h_chunk_poff, sizeof(int) * Mt, cudaMemcpyHostToDevice));
+
+  // --- tiles ---
+  std::vector<TileDesc> tiles;
+  build_tiles(N, tiles);
+  d.ntile = (int)tiles.size();
+  d.tiles = dev_alloc<TileDesc>(tiles.size());
+  DB_CHECK(cudaMemcpy(d.tiles, tiles.data(), sizeof(TileDesc) * tiles.size(),
+                      cudaMemcpyHostToDevice));
+
+  // --- Jones, data, coherencies ---
+  d.pp = dev_alloc<double>((size_t)8 * N * Mt);
+  d.x = dev_alloc<double2>((size_t)4 * R);
+  d.coh = dev_alloc<double2>((size_t)M * 4 * R);
+  pr->vis_stage = dev_alloc<double2>((size_t)4 * R);
+  if (x) dirac_b200_set_data(pr, x);
+  if (coh) {
+    // chunked upload through a device staging buffer, transposed to planar on the device
+    long long rows_per = (128ll << 20) / ((long long)M * 64);
+    if (rows_per < 1) rows_per = 1;
+    if (rows_per > R) rows_per = R;
+    double2 *stage = dev_alloc<double2>((size_t)rows_per * M * 4);
+    for (long long r0 = 0; r0 < R; r0 += rows_per) {
+      int nr = (int)((R - r0 < rows_per) ? (R - r0) : rows_per);
+      DB_CHECK(cudaMemcpyAsync(stage, coh + (size_t)r0 * M * 8, (size_t)nr * M * 64,
+                               cudaMemcpyHostToDevice, d.stream));
+      db_launch_coh_to_planar(stage, d.coh, r0, nr, M, R, d.stream);
+      db_count_launch(1);
+    }
+    DB_CHECK(cudaStreamSynchronize(d.stream));
+    DB_CHECK(cudaFree(stage));
+  }
+
+  // --- scratch ---
+  int nb1 = db_predict_nblocks(d.ntile, tilesz);
+  int nb2 = db_cluster_pass_nblocks(d.ntile, tilesz, 1);
+  pr->npartials = (nb1 > nb2 ? nb1 : nb2) + 64;
+  pr->partials = dev_alloc<double>(pr->npartials);
+  d.scal = dev_alloc<double>(64);
+  DB_CHECK(cudaMallocHost((void **)&d.h_scal, 64 * sizeof(double)));
+  d.counters = dev_alloc<unsigned int>(16);
+  DB_CHECK(cudaMemset(d.counters, 0, 16 * sizeof(unsigned int)));
+  pr->res = dev_alloc<double2>((size_t)4 * R);
+  pr->g = dev_alloc<double>((size_t)8 * N * Mt);
+  DB_CHECK(cudaGetLastError());
+  return pr;
+}
+
+extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
+  if (!pr) return;
+  DevProblem &d = pr->d;
+  cudaStreamSynchronize(d.stream);
+  db_lm_free(pr);
+  cudaFree(d.coh); cudaFree(d.x); cudaFree(d.flag); cudaFree(d.pp); cudaFree(d.clus);
+  cudaFree(d.chunk_poff); cudaFree(d.tiles); cudaFree(d.scal); cudaFree(d.counters);
+  cudaFree(pr->partials); cudaFree(pr->res); cudaFree(pr->g); cudaFree(pr->vis_stage);
+  cudaFreeHost(d.h_scal);
+  free(d.h_clus); free(d.h_chunk_poff);
+  cudaStreamDestroy(d.stream);
+  delete pr;
+}
+
+// host API-layout vector (8R doubles) -> planar device vector
+void db_upload_vis(dirac_b200_problem *pr, const double *h, double2 *dst) {
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemcpyAsync(pr->vis_stage, h, (size_t)d.R * 64, cudaMemcpyHostToDevice, d.stream));
+  db_launch_vis_to_planar(pr->vis_stage, dst, d.R, d.stream);
+  db_count_launch(1);
+}
+// planar device vector -> host API-layout vector
+void db_download_vis(dirac_b200_problem *pr, const double2 *src, double *h) {
+  DevProblem &d = pr->d;
+  db_launch_vis_from_planar(src, pr->vis_stage, d.R, d.stream);
+  db_count_launch(1);
+  DB_CHECK(cudaMemcpyAsync(h, pr->vis_stage, (size_t)d.R * 64, cudaMemcpyDeviceToHost, d.stream));
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+}
+
+extern "C" void dirac_b200_set_data(dirac_b200_problem *pr, const double *x) {
+  db_upload_vis(pr, x, pr->d.x);
+  DB_CHECK(cudaStreamSynchronize(pr->d.stream));
+}
+
+extern "C" void dirac_b200_get_coherencies(dirac_b200_problem *pr, double *coh) {
+  DevProblem &d = pr->d;
+  long long rows_per = (128ll << 20) / ((long long)d.M * 64);
+  if (rows_per < 1) rows_per = 1;
+  if (rows_per > d.R) rows_per = d.R;
+  double2 *stage = dev_alloc<double2>((size_t)rows_per * d.M * 4);
+  for (long long r0 = 0; r0 < d.R; r0 += rows_per) {
+    int nr = (int)((d.R - r0 < rows_per) ? (d.R - r0) : rows_per);
+    db_launch_coh_from_planar(d.coh, stage, r0, nr, d.M, d.R, d.stream);
+    db_count_launch(1);
+    DB_CHECK(cudaMemcpyAsync(coh + (size_t)r0 * d.M * 8, stage, (size_t)nr * d.M * 64,
+                             cudaMemcpyDeviceToHost, d.stream));
+  }
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+  DB_CHECK(cudaFree(stage));
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer primitives used by the solvers
+// ------------------------------------------------------------------------------------------------
+// model/residual/cost over all clusters at the Jones currently in d.pp; returns after queuing;
+// the cost lands in d.scal[slot] (device)
+void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, int out_mode,
+                    int cost_mode, double nu, int slot) {
+  DevProblem &d = pr->d;
+  PredictArgs a;
+  a.coh = d.coh; a.x = d.x; a.flag = d.flag; a.pp = pp_dev; a.clus = d.clus;
+  a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.out = out; a.partials = pr->partials;
+  a.cost = d.scal + slot; a.counter = d.counters; a.R = d.R; a.N = d.N; a.Nbase = d.Nbase;
+  a.tilesz = d.tilesz; a.M = d.M; a.out_mode = out_mode; a.cost_mode = cost_mode;
+  a.inv_nu = (nu > 0.0) ? 1.0 / nu : 0.0;
+  db_launch_predict_full(&a, d.ntile, d.stream);
+  db_count_launch(1);
+}
+
+double db_read_scalar(dirac_b200_problem *pr, int slot) {
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemcpyAsync(d.h_scal + slot, d.scal + slot, sizeof(double), cudaMemcpyDeviceToHost,
+                           d.stream));
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+  return d.h_scal[slot];
+}
+
+// gradient over all clusters from the residual in pr->res; g_dev (8*N*Mt) is overwritten
+void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, int robust,
+                 double nu) {
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemsetAsync(g_dev, 0, sizeof(double) * 8 * d.N * d.Mt, d.stream));
+  GradArgs a;
+  a.coh = d.coh; a.res = pr->res; a.flag = d.flag; a.pp = pp_dev; a.clus = d.clus;
+  a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.g = g_dev; a.R = d.R; a.N = d.N;
+  a.Nbase = d.Nbase; a.tilesz = d.tilesz; a.M = d.M; a.robust = robust; a.nu = nu;
+  // sign conventions of the reference: Gaussian g = -2 Re(conj(f-d) . df) (robust_lbfgs.c:554),
+  // robust g = +2 (f-d) df/(nu+(f-d)^2) (robust_lbfgs.c:286-299); here e = d-f
+  a.scale = robust ? -2.0 : 2.0;
+  db_launch_grad_full(&a, d.ntile, d.stream);
+  db_count_launch(1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// thin C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" double dirac_b200_predict(dirac_b200_problem *pr, const double *pp, double *out,
+                                     int out_mode, int cost_mode, double nu) {
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * 8 * d.N * d.Mt, cudaMemcpyHostToDevice,
+                           d.stream));
+  if (!out) out_mode = 0;
+  db_predict_dev(pr, d.pp, pr->res, out_mode, cost_mode, nu, 0);
+  double c = 0.0;
+  if (cost_mode) c = db_read_scalar(pr, 0);
+  if (out_mode) db_download_vis(pr, pr->res, out);
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+  DB_CHECK(cudaGetLastError());
+  return c;
+}
+
+extern "C" void dirac_b200_grad(dirac_b200_problem *pr, const double *pp, double *g, int robust,
+                                double nu) {
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * 8 * d.N * d.Mt, cudaMemcpyHostToDevice,
+                           d.stream));
+  db_predict_dev(pr, d.pp, pr->res, 1, 0, 0.0, 0);  // residual e = x - V
+  db_grad_dev(pr, d.pp, pr->g, robust, nu);
+  DB_CHECK(cudaMemcpyAsync(g, pr->g, sizeof(double) * 8 * d.N * d.Mt, cudaMemcpyDeviceToHost,
+                           d.stream));
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+  DB_CHECK(cudaGetLastError());
+}

@@ -1,0 +1,49 @@
+// Internal: the opaque dirac_b200_problem and the device-pointer primitives shared by the solvers.
+#pragma once
+#include <cusolverDn.h>
+#include <cublas_v2.h>
+
+#include "internal.cuh"
+
+struct LMWork {
+  bool ready;
+  int n8;                 // 8N
+  double *T;              // [Mt][Nbase][16] Gram tensors per (cluster, chunk), built on first use
+  unsigned char *T_valid; // host, [Mt]
+  double *Tsub;           // [Nbase][16] scratch (OS subsets, tests)
+  double *JTJ0, *JTJ;     // [8N][8N]
+  double *JTe, *JTe_new;  // [8N]
+  double *Hst;            // [N][4]
+  double *Dp;             // [8N]
+  double *pnew;           // [8N]
+  double *h_vec;          // pinned host scratch, 4*8N + 4N + 16
+  int *devinfo;
+  double *cswork;
+  int lwork;
+  double *tau;            // QR
+  double *svdS, *svdU, *svdVT;
+  cusolverDnHandle_t cs;
+  cublasHandle_t cb;
+  double2 *dbuf;          // [4][R] hidden data of the cluster being solved
+};
+
+struct dirac_b200_problem {
+  DevProblem d;
+  double *partials;
+  int npartials;
+  double2 *res;           // [4][R] residual of the full model
+  double2 *vis_stage;     // [R][4] API-layout staging
+  double *g;              // [8*N*Mt]
+  LMWork lm;
+};
+
+void db_count_launch(int n);
+void db_upload_vis(dirac_b200_problem *pr, const double *h, double2 *dst);
+void db_download_vis(dirac_b200_problem *pr, const double2 *src, double *h);
+void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, int out_mode,
+                    int cost_mode, double nu, int slot);
+double db_read_scalar(dirac_b200_problem *pr, int slot);
+void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, int robust,
+                 double nu);
+void db_lm_init(dirac_b200_problem *pr);
+void db_lm_free(dirac_b200_problem *pr);

@@ -1,0 +1,253 @@
+// Drop-in entry points of the Dirac C API for the calibration hot path.
+//
+// sagefit_visibilities restates the SAGE/EM orchestration of lmfit.c:778-1053 on a device-resident
+// problem: the residual of the full model stays in HBM for the whole call, each cluster visit is
+//   [hidden data + first normal equations] -> LM iterations -> [residual with the new Jones]
+// and the host only sees scalars and the 8N-vectors the LM decisions need.
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/dirac_b200.h"
+#include "problem.h"
+
+void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
+                 const double *opts, int linsolv, int os, int randomize, double *info);
+void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
+                  int linsolv, int os, int randomize, double nulow, double nuhigh,
+                  double *robust_nu, double *info);
+void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, int robust,
+                  double nu);
+
+static bool is_robust_mode(int solver_mode) {
+  return solver_mode == SM_OSLM_OSRLM_RLBFGS || solver_mode == SM_RLM_RLBFGS ||
+         solver_mode == SM_RTR_OSRLM_RLBFGS || solver_mode == SM_NSD_RLBFGS;
+}
+
+extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                    int tilesz, baseline_t *barr, clus_source_t *carr,
+                                    double *coh, int M, int Mt, double freq0, double fdelta,
+                                    double *pp, double uvmin, int Nt, int max_emiter, int max_iter,
+                                    int max_lbfgs, int lbfgs_m, int gpu_threads, int linsolv,
+                                    int solver_mode, double nulow, double nuhigh, int randomize,
+                                    double *mean_nu, double *res_0, double *res_1) {
+  (void)u; (void)v; (void)w; (void)freq0; (void)fdelta; (void)uvmin; (void)Nt; (void)gpu_threads;
+  if (solver_mode == SM_RTR_OSLM_LBFGS || solver_mode == SM_RTR_OSRLM_RLBFGS ||
+      solver_mode == SM_NSD_RLBFGS) {
+    fprintf(stderr, "dirac_b200: solver_mode %d (RTR/NSD) is outside this library's scope; use "
+                    "0-3 (LM / OS-LM / robust LM + LBFGS)\n", solver_mode);
+    exit(1);
+  }
+  if (solver_mode < 0 || solver_mode > 6) {
+    fprintf(stderr, "%s: %d: undefined solver mode\n", __FILE__, __LINE__);  // lmfit.c:957-962
+    exit(1);
+  }
+  const int m = N * Mt * 8;
+  const long long n = (long long)Nbase * tilesz * 8;
+  dirac_b200_problem *pr = dirac_b200_create(N, Nbase, tilesz, barr, carr, M, Mt, coh, x);
+  DevProblem &d = pr->d;
+  // CPU-path LM thresholds (lmfit.c:801)
+  double opts[5] = {1e-3, 1e-15, 1e-15, 1e-20, -1e-6};
+  double info[10];
+  double robust_nu0 = nulow;
+  std::vector<double> nerr(M, 0.0), robust_nuM(M, 0.0);
+  const bool robust = is_robust_mode(solver_mode);
+
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
+  // residual of the current model: r = x - sum_k model_k, res_0 = ||r|| / n   (lmfit.c:866-869)
+  double2 *r = pr->res;
+  db_predict_dev(pr, d.pp, r, 1, 1, 0.0, 0);
+  *res_0 = sqrt(db_read_scalar(pr, 0)) / (double)n;
+
+  int weighted_iter = 0;
+  const int total_iter = M * max_iter;
+  const int iter_bar = (int)ceil((0.80 / (double)M) * ((double)total_iter));
+  for (int ci = 0; ci < max_emiter; ci++) {
+    for (int cj = 0; cj < M; cj++) {
+      int this_itermax;
+      if (weighted_iter) {
+        this_itermax = (int)((0.20 * nerr[cj]) * ((double)total_iter)) + iter_bar;
+      } else {
+        this_itermax = max_iter;
+      }
+      if (this_itermax > 0) {
+        double init_res = 0.0, final_res = 0.0;
+        for (int ck = 0; ck < carr[cj].nchunk; ck++) {
+          double *pblk = d.pp + carr[cj].p[ck];
+          const bool last = (ci == max_emiter - 1);
+          if (solver_mode == SM_OSLM_LBFGS) {
+            db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, last ? 0 : 1, randomize,
+                        info);
+          } else if (solver_mode == SM_LM_LBFGS) {
+            db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 0, randomize, info);
+          } else if (solver_mode == SM_RLM_RLBFGS) {
+            if (last) {
+              double nu = robust_nu0;
+              db_rlm_chunk(pr, cj, ck, pblk, r, this_itermax, linsolv, 0, randomize, nulow, nuhigh,
+                           &nu, info);
+              robust_nuM[cj] += nu;
+            } else {
+              db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info);
+            }
+          } else {  // SM_OSLM_OSRLM_RLBFGS
+            if (last) {
+              double nu = robust_nu0;
+              db_rlm_chunk(pr, cj, ck, pblk, r, this_itermax, linsolv, 1, randomize, nulow, nuhigh,
+                           &nu, info);
+              robust_nuM[cj] += nu;
+            } else {
+              db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info);
+            }
+          }
+          init_res += info[0];
+          final_res += info[1];
+        }
+        if (init_res > 0.0) {
+          nerr[cj] = (init_res - final_res) / init_res;
+          if (nerr[cj] < 0.0) nerr[cj] = 0.0;
+        } else {
+          nerr[cj] = 0.0;
+        }
+        if (robust && ci == max_emiter - 1) robust_nuM[cj] /= (double)carr[cj].nchunk;
+      }
+    }
+    double total_err = 0.0;
+    for (int cj = 0; cj < M; cj++) total_err += fabs(nerr[cj]);
+    if (total_err > 0.0)
+      for (int cj = 0; cj < M; cj++) nerr[cj] *= 1.0 / total_err;
+    if (randomize) weighted_iter = !weighted_iter;
+  }
+  if (robust) {
+    double s = 0.0;
+    for (int cj = 0; cj < M; cj++) s += fabs(robust_nuM[cj]);
+    robust_nu0 = s / (double)M;
+    if (robust_nu0 < nulow) robust_nu0 = nulow;
+    else if (robust_nu0 > nuhigh) robust_nu0 = nuhigh;
+  }
+  DB_CHECK(cudaMemcpyAsync(pp, d.pp, sizeof(double) * m, cudaMemcpyDeviceToHost, d.stream));
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+
+  if (max_lbfgs > 0) {
+    if (robust) {
+      if (lbfgs_m > 0) {
+        db_lbfgs_fit(pr, pp, m, max_lbfgs, lbfgs_m, 1, robust_nu0);
+      } else if (lbfgs_m < 0) {
+        fprintf(stderr, "dirac_b200: minibatch LBFGS (lbfgs_m<0) is not supported; running "
+                        "full-batch with memory %d\n", -lbfgs_m);
+        db_lbfgs_fit(pr, pp, m, max_lbfgs, -lbfgs_m, 1, robust_nu0);
+      }
+    } else {
+      db_lbfgs_fit(pr, pp, m, max_lbfgs, lbfgs_m, 0, 0.0);
+    }
+  }
+  // final residual, in place in x   (lmfit.c:1039-1044)
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
+  db_predict_dev(pr, d.pp, r, 1, 1, 0.0, 0);
+  *res_1 = sqrt(db_read_scalar(pr, 0)) / (double)n;
+  db_download_vis(pr, r, x);
+  *mean_nu = robust_nu0;
+  DB_CHECK(cudaGetLastError());
+  dirac_b200_destroy(pr);
+  return (*res_1 > *res_0) ? -1 : 0;
+}
+
+#define SAGEFIT_ALIAS(name)                                                                      \
+  extern "C" int name(double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz,  \
+                      baseline_t *barr, clus_source_t *carr, double *coh, int M, int Mt,         \
+                      double freq0, double fdelta, double *pp, double uvmin, int Nt,             \
+                      int max_emiter, int max_iter, int max_lbfgs, int lbfgs_m, int gpu_threads, \
+                      int linsolv, int solver_mode, double nulow, double nuhigh, int randomize,  \
+                      double *mean_nu, double *res_0, double *res_1) {                           \
+    return sagefit_visibilities(u, v, w, x, N, Nbase, tilesz, barr, carr, coh, M, Mt, freq0,     \
+                                fdelta, pp, uvmin, Nt, max_emiter, max_iter, max_lbfgs, lbfgs_m, \
+                                gpu_threads, linsolv, solver_mode, nulow, nuhigh, randomize,     \
+                                mean_nu, res_0, res_1);                                          \
+  }
+SAGEFIT_ALIAS(sagefit_visibilities_dual_pt_flt)
+SAGEFIT_ALIAS(sagefit_visibilities_dual_pt)
+SAGEFIT_ALIAS(sagefit_visibilities_dual_pt_one_gpu)
+
+extern "C" int bfgsfit_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                    int tilesz, baseline_t *barr, clus_source_t *carr,
+                                    double *coh, int M, int Mt, double freq0, double fdelta,
+                                    double *pp, double uvmin, int Nt, int max_lbfgs, int lbfgs_m,
+                                    int gpu_threads, int solver_mode, double mean_nu,
+                                    double *res_0, double *res_1) {
+  (void)u; (void)v; (void)w; (void)freq0; (void)fdelta; (void)uvmin; (void)Nt; (void)gpu_threads;
+  const int m = N * Mt * 8;
+  const long long n = (long long)Nbase * tilesz * 8;
+  dirac_b200_problem *pr = dirac_b200_create(N, Nbase, tilesz, barr, carr, M, Mt, coh, x);
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
+  db_predict_dev(pr, d.pp, nullptr, 0, 1, 0.0, 0);
+  *res_0 = sqrt(db_read_scalar(pr, 0)) / (double)n;
+  if (max_lbfgs > 0) {
+    int M_ = lbfgs_m > 0 ? lbfgs_m : -lbfgs_m;
+    if (is_robust_mode(solver_mode)) {
+      db_lbfgs_fit(pr, pp, m, max_lbfgs, M_, 1, mean_nu);
+    } else {
+      db_lbfgs_fit(pr, pp, m, max_lbfgs, M_, 0, 0.0);
+    }
+  }
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
+  db_predict_dev(pr, d.pp, pr->res, 1, 1, 0.0, 0);
+  *res_1 = sqrt(db_read_scalar(pr, 0)) / (double)n;
+  db_download_vis(pr, pr->res, x);
+  DB_CHECK(cudaGetLastError());
+  dirac_b200_destroy(pr);
+  return (*res_1 > *res_0) ? -1 : 0;
+}
+
+extern "C" int bfgsfit_visibilities_gpu(double *u, double *v, double *w, double *x, int N,
+                                        int Nbase, int tilesz, baseline_t *barr,
+                                        clus_source_t *carr, double *coh, int M, int Mt,
+                                        double freq0, double fdelta, double *pp, double uvmin,
+                                        int Nt, int max_lbfgs, int lbfgs_m, int gpu_threads,
+                                        int solver_mode, double mean_nu, double *res_0,
+                                        double *res_1) {
+  return bfgsfit_visibilities(u, v, w, x, N, Nbase, tilesz, barr, carr, coh, M, Mt, freq0, fdelta,
+                              pp, uvmin, Nt, max_lbfgs, lbfgs_m, gpu_threads, solver_mode, mean_nu,
+                              res_0, res_1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// index / flag helpers the driver calls directly (host, bit-exact integer work)
+// ------------------------------------------------------------------------------------------------
+// canonical row order (0,1),(0,2)...(N-2,N-1) per timeslot; flags untouched
+// (baselinegen_threadfn, baseline_utils.c:438-466)
+extern "C" int generate_baselines(int Nbase, int tilesz, int N, baseline_t *barr, int Nt) {
+  (void)Nt;
+  for (int t = 0; t < tilesz; t++) {
+    int sta1 = 0, sta2 = 1;
+    baseline_t *b = barr + (size_t)t * Nbase;
+    for (int cj = 0; cj < Nbase; cj++) {
+      b[cj].sta1 = sta1;
+      b[cj].sta2 = sta2;
+      if (sta2 < N - 1) {
+        sta2++;
+      } else if (sta1 < N - 2) {
+        sta1++;
+        sta2 = sta1 + 1;
+      } else {
+        sta1 = 0;
+        sta2 = 1;
+      }
+    }
+  }
+  return 0;
+}
+
+// flag[ci] > 0 -> barr.flag = 1 and the 8 data reals zeroed, else barr.flag = 0
+// (preflag_threadfn, baseline_utils.c:206-227)
+extern "C" int preset_flags_and_data(int Nbase, double *flag, baseline_t *barr, double *x, int Nt) {
+  (void)Nt;
+  for (int ci = 0; ci < Nbase; ci++) {
+    if (flag[ci] > 0.0) {
+      barr[ci].flag = 1;
+      for (int c = 0; c < 8; c++) x[8 * (size_t)ci + c] = 0.0;
+    } else {
+      barr[ci].flag = 0;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,130 @@
+"""GPU parity of the individual E-step passes against the compiled reference CPU code.
+Tolerances: fp64 arithmetic on both sides; differences come from FMA contraction and summation
+order only."""
+import numpy as np
+import pytest
+
+from util import small_problem, perturbed_jones, relerr
+from sagecal_b200 import lib as blib
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    dict(N=8, M=2, tilesz=10, seed=11),
+    dict(N=13, M=5, tilesz=7, seed=12, kmean=2.0),
+    dict(N=35, M=6, tilesz=9, seed=13, kmean=1.0),          # two q-blocks, partial tiles
+    dict(N=20, M=4, tilesz=10, seed=14, nchunk=[1, 2, 1, 5]),  # hybrid chunks
+    dict(N=9, M=3, tilesz=10, seed=15, nchunk=[3, 1, 4]),     # nchunk does not divide tilesz
+]
+
+
+@pytest.fixture(params=range(len(CASES)), ids=lambda i: "case%d" % i)
+def bound(request):
+    return small_problem(**CASES[request.param])
+
+
+def test_predict_full(api, ref, bound):
+    pr = bound.pr
+    pp = perturbed_jones(pr)
+    md = ref.me_data(pr.N, pr.Nbase, pr.tilesz, bound.barr, bound.sky, pr.coh)
+    want = ref.predict_full(pp, md, bound.n)
+    with blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, bound.barr, bound.sky, pr.coh, pr.x) as dp:
+        _, got = dp.predict(pp, out_mode=2)
+        c, res = dp.predict(pp, out_mode=1, cost_mode=1)
+    assert relerr(got, want) < 1e-13
+    assert relerr(res, pr.x - want) < 1e-13
+    assert abs(c - np.sum((pr.x - want) ** 2)) <= 1e-12 * c
+    # flagged rows carry no model (lmfit.c:78-81)
+    assert np.all(got.reshape(-1, 8)[pr.flag != 0] == 0.0)
+
+
+@pytest.mark.parametrize("robust", [False, True])
+def test_cost_and_grad(api, ref, bound, robust):
+    pr = bound.pr
+    pp = perturbed_jones(pr, seed=5)
+    nu = 3.5
+    md = ref.me_data(pr.N, pr.Nbase, pr.tilesz, bound.barr, bound.sky, pr.coh, robust_nu=nu)
+    cw = ref.cost(pp, pr.x, md, robust=robust)
+    gw = ref.grad(pp, pr.x, md, robust=robust)
+    with blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, bound.barr, bound.sky, pr.coh, pr.x) as dp:
+        c = dp.cost(pp, robust=robust, nu=nu)
+        g = dp.grad(pp, robust=robust, nu=nu)
+    assert abs(c - cw) <= 1e-12 * abs(cw)
+    assert relerr(g, gw) < 1e-11
+
+
+def test_normal_equations(api, ref, bound):
+    """J^T J, J^T e, ||e||^2 of every (cluster, chunk) against the reference's dense Jacobian"""
+    pr = bound.pr
+    pp = perturbed_jones(pr, seed=7)
+    rng = np.random.default_rng(1)
+    xd = pr.x + 0.01 * rng.normal(0, 1, pr.x.shape)
+    xd.reshape(-1, 8)[pr.flag == 1] = 0.0
+    with blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, bound.barr, bound.sky, pr.coh, pr.x) as dp:
+        off = 0
+        for k in range(pr.M):
+            nch = pr.nchunk[k]
+            tilechunk = (pr.tilesz + nch - 1) // nch
+            for ck in range(nch):
+                t0 = min(ck * tilechunk, pr.tilesz)
+                t1 = min(t0 + tilechunk, pr.tilesz)
+                pblk = pp[off:off + 8 * pr.N].copy()
+                off += 8 * pr.N
+                if t1 <= t0:
+                    continue
+                md = ref.me_data(pr.N, pr.Nbase, t1 - t0, bound.barr, bound.sky, pr.coh, clus=k,
+                                 tileoff=t0)
+                nn = 8 * (t1 - t0) * pr.Nbase
+                xs = xd[8 * t0 * pr.Nbase: 8 * t1 * pr.Nbase]
+                J = ref.lm_jac(pblk, md, nn)
+                e = xs - ref.lm_func(pblk, md, nn)
+                c, JTJ, JTe = dp.normal_eq(k, ck, pblk, xd)
+                assert abs(c - e @ e) <= 1e-12 * (e @ e)
+                assert relerr(JTe, J.T @ e) < 1e-11
+                assert relerr(JTJ, J.T @ J) < 1e-11
+                assert np.array_equal(JTJ, JTJ.T)
+
+
+def test_coherencies_device(api, ref):
+    b = small_problem(N=12, M=4, tilesz=6, seed=21, kmean=2.0, gaussian_frac=0.5)
+    pr = b.pr
+    barr1 = b.fresh_barr()
+    want = ref.precalculate_coherencies(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, barr1, b.sky, pr.freq0,
+                                        pr.fdelta, uvmin=30.0, uvmax=1e5)
+    barr2 = b.fresh_barr()
+    got = api.precalculate_coherencies(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, barr2, b.sky, pr.freq0,
+                                       pr.fdelta, uvmin=30.0, uvmax=1e5)
+    from sagecal_b200.dirac_api import barr_to_numpy
+    assert np.array_equal(barr_to_numpy(barr1, pr.Nbase1)[2], barr_to_numpy(barr2, pr.Nbase1)[2])
+    assert relerr(got, want) < 1e-11
+    # resident variant
+    barr3 = b.fresh_barr()
+    with blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, barr3, b.sky, None, pr.x) as dp:
+        dp.precalculate(pr.u, pr.v, pr.w, pr.freq0, pr.fdelta, uvmin=30.0, uvmax=1e5, barr=barr3)
+        got2 = dp.get_coherencies()
+    assert relerr(got2, want) < 1e-11
+    assert np.array_equal(barr_to_numpy(barr1, pr.Nbase1)[2], barr_to_numpy(barr3, pr.Nbase1)[2])
+
+
+@pytest.mark.parametrize("add", [0, 1])
+def test_predict_multifreq(api, ref, add):
+    b = small_problem(N=10, M=3, tilesz=5, seed=22, kmean=2.0, gaussian_frac=0.3)
+    pr = b.pr
+    for cl in pr.clusters:  # give half of the sources a spectral index
+        K = len(cl["ll"])
+        cl["spec_idx"] = np.where(np.arange(K) % 2 == 0, -0.7, 0.0)
+        cl["spec_idx1"] = np.full(K, 0.05)
+        cl["spec_idx2"] = np.full(K, -0.01)
+        cl["f0"] = np.full(K, 140e6)
+    from sagecal_b200.dirac_api import SkyModel
+    sky = SkyModel(pr.clusters, pr.N)
+    freqs = np.array([145e6, 150e6, 155e6])
+    rng = np.random.default_rng(2)
+    x0 = rng.normal(0, 1, 8 * pr.Nbase1 * len(freqs))
+    xa = x0.copy()
+    xb = x0.copy()
+    ref.predict_visibilities_multifreq(pr.u, pr.v, pr.w, xa, pr.N, pr.Nbase, pr.tilesz, b.barr, sky,
+                                       freqs, pr.fdelta * 3, add_to_data=add)
+    api.predict_visibilities_multifreq(pr.u, pr.v, pr.w, xb, pr.N, pr.Nbase, pr.tilesz, b.barr, sky,
+                                       freqs, pr.fdelta * 3, add_to_data=add)
+    assert relerr(xb, xa) < 1e-11

@@ -175,8 +175,9 @@ extern "C" int precalculate_coherencies(double *u, double *v, double *w, double 
   return 0;
 }
 
-// Dirac_radio.h:659 (residual.c:1257-1340): x[chan][row][8] (+)= sum over clusters; SIMUL_ONLY (0)
-// clears x first.  No Jones, no flags.
+// Dirac_radio.h:659 (residual.c:1257-1340): x[chan][row][8] += sum over clusters; add_to_data ==
+// SIMUL_ONLY (1, Dirac_radio.h:78) clears x first, every other value accumulates onto the input
+// (the thread function only ever adds, residual.c:1238-1245).  No Jones, no flags.
 extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, double *x, int N,
                                               int Nbase, int tilesz, baseline_t *barr,
                                               clus_source_t *carr, int M, double *freqs, int Nchan,
@@ -198,7 +199,7 @@ extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, d
   double2 *dx = nullptr;
   const size_t nx = (size_t)Nchan * R * 4;
   DB_CHECK(cudaMalloc((void **)&dx, sizeof(double2) * nx));
-  if (add_to_data == 0) {
+  if (add_to_data == 1) {  // SIMUL_ONLY
     DB_CHECK(cudaMemsetAsync(dx, 0, sizeof(double2) * nx, st));
   } else {
     DB_CHECK(cudaMemcpyAsync(dx, x, sizeof(double2) * nx, cudaMemcpyHostToDevice, st));

@@ -205,7 +205,7 @@ class DiracAPI:
         return coh
 
     def predict_visibilities_multifreq(self, u, v, w, x, N, Nbase, tilesz, barr, sky: SkyModel,
-                                       freqs, fdelta, tdelta=10.0, dec0=1.0, Nt=4, add_to_data=0):
+                                       freqs, fdelta, tdelta=10.0, dec0=1.0, Nt=4, add_to_data=1):
         freqs = np.ascontiguousarray(freqs, dtype=np.float64)
         return self.lib.predict_visibilities_multifreq(
             dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M,

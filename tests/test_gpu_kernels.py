@@ -106,7 +106,7 @@ def test_coherencies_device(api, ref):
     assert np.array_equal(barr_to_numpy(barr1, pr.Nbase1)[2], barr_to_numpy(barr3, pr.Nbase1)[2])
 
 
-@pytest.mark.parametrize("add", [0, 1])
+@pytest.mark.parametrize("add", [1, 2, 0])  # SIMUL_ONLY=1 clears, others accumulate
 def test_predict_multifreq(api, ref, add):
     b = small_problem(N=10, M=3, tilesz=5, seed=22, kmean=2.0, gaussian_frac=0.3)
     pr = b.pr

@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — baseline-visibilities/s through predict+Jacobian (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (own arm, hand-written sm_100a kernels)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path, bounded sample)
+
+One "step" = one complete direction-dependent solve of the workload on device-resident inputs:
+`max_emiter` SAGE sweeps over all M clusters (per cluster: hidden data, J^T e, J^T J, damped solve,
+trial cost, Jones update) followed by `max_lbfgs` LBFGS iterations over all clusters (cost +
+gradient passes).  Units per step = rows x clusters x (SAGE sweeps + LBFGS gradient evaluations
+actually performed): every baseline-visibility of every direction goes through predict + Jacobian
+once per sweep.  `value` = units / time on resident data, `e2e` = the same solve through the
+drop-in C entry point `sagefit_visibilities` with pinned HOST buffers (upload of coherencies and
+data, download of residual and Jones inside the timed region).
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "baseline_visibilities_per_sec_predict_jacobian"
+UNIT = "baseline-visibilities/s"
+
+SOLVE = dict(max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, linsolv=0, solver_mode=1,
+             nulow=2.0, nuhigh=30.0, randomize=0)
+#: bounded CPU sample of the same workload (dense Jacobian + dgemm make the full shape infeasible:
+#: 7.2 GB and ~0.9 PFLOP per cluster-iteration at N=62,T=120)
+CPU_SAMPLE = dict(N=62, M=4, tilesz=4)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", help="C2 (62 st, 64 clusters, 120 slots) | C1 | "
+                    "custom N,M,T e.g. 62,16,30")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_shape(name):
+    from sagecal_b200 import synth
+    if name in synth.CONFIGS:
+        c = synth.CONFIGS[name]
+        return dict(N=c["N"], M=c["M"], tilesz=c["tilesz"], radius=c["radius"], seed=c["seed"],
+                    kmean=c["kmean"])
+    N, M, T = (int(v) for v in name.split(","))
+    return dict(N=N, M=M, tilesz=T, radius=40e3, seed=20260921 + 2, kmean=2.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("k_cluster_pass_dram_bytes_per_launch")
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+# reference (CPU) arm — the only place besides tests/ and smoke() that may execute oracle/
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, seed):
+    """times the reference's own sagefit_visibilities (oracle/_ref) on a bounded sample of the
+    workload with every host thread; returns (units/s, seconds per step, description)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdirac
+    from sagecal_b200 import synth
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+    if not refdirac.available():
+        return None, None, "oracle/_ref/libdirac_ref.so not built"
+    ref = refdirac.load()
+    cores = os.cpu_count() or 1
+    try:
+        ref.lib.openblas_set_num_threads(cores)
+    except AttributeError:
+        pass
+    pr = synth.make_problem(radius=40e3, seed=seed, kmean=2.0, **CPU_SAMPLE)
+    barr = make_barr(pr.sta1, pr.sta2, pr.flag)
+    sky = SkyModel(pr.clusters, pr.N)
+    sweeps = SOLVE["max_emiter"] + SOLVE["max_lbfgs"] + 1
+    units = pr.Nbase1 * pr.M * sweeps
+    ts = []
+    for it in range(warmup + steps):
+        x = pr.x.copy()
+        pp = pr.pp0.copy()
+        t0 = time.perf_counter()
+        ref.sagefit_visibilities(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz, barr, sky, pr.coh,
+                                 pp, Nt=cores, **SOLVE)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            ts.append(t1 - t0)
+    sec = float(np.mean(ts))
+    desc = ("reference sagefit_visibilities (oracle/_ref, gcc -O2, OpenBLAS %d threads, Nt=%d) on "
+            "N=%d M=%d tilesz=%d, %d steps" % (cores, cores, pr.N, pr.M, pr.tilesz, steps))
+    return units / sec, sec, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = workload_shape(args.workload)
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    v, sec, desc = cpu_reference_run(steps, warm, shape["seed"])
+    cores = os.cpu_count() or 1
+    if v is None:
+        print(json.dumps({"impl": "reference", "unavailable": desc}))
+        return
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s (N=%d, M=%d, tilesz=%d) sampled as N=%d M=%d tilesz=%d"
+                   % (args.workload, shape["N"], shape["M"], shape["tilesz"], CPU_SAMPLE["N"],
+                      CPU_SAMPLE["M"], CPU_SAMPLE["tilesz"]), "solve": SOLVE},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------
+def build_workload(api, shape, rank, world):
+    """synthetic MS of the workload shape; coherencies by the numpy generator (independent of the
+    product), data = true-Jones model + noise"""
+    from sagecal_b200 import synth
+    pr = synth.make_problem(**shape)
+    return pr
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from sagecal_b200 import lib as blib
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api = blib.load()
+    stream = torch.cuda.Stream()
+    api.set_stream(stream.cuda_stream)
+
+    shape = workload_shape(args.workload)
+    # weak scaling over independent solve intervals: every rank solves its own interval (its own
+    # time tile of the observation) — tiles are independent in the reference driver
+    # (fullbatch_mode.cpp:308); see DESIGN.md "multi-GPU"
+    shape = dict(shape)
+    shape["seed"] = shape["seed"] + 1000 * rank
+    pr = build_workload(api, shape, rank, world)
+    barr = make_barr(pr.sta1, pr.sta2, pr.flag)
+    sky = SkyModel(pr.clusters, pr.N)
+    R, M = pr.Nbase1, pr.M
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    coh_t, coh_h = pinned(pr.coh.view(np.float64))
+    coh_h = coh_h.view(np.complex128)
+    x_t, x_h = pinned(pr.x)
+    pp_t, pp_h = pinned(pr.pp0)
+
+    K, W = args.steps, max(args.warmup, 3)
+    clocks = ClockSampler(local)
+
+    # ---------------- resident-data throughput (`value`) ----------------
+    with torch.cuda.stream(stream):
+        dp = blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, barr, sky, coh_h, x_h)
+        res = None
+        for _ in range(W):
+            pp = pr.pp0.copy()
+            res = dp.sagefit(pp, None, **SOLVE)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g0 = api.kernel_count(1)
+        l0 = api.launch_count()
+        api.profile_enable(True)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(K):
+            pp = pr.pp0.copy()
+            res = dp.sagefit(pp, None, **SOLVE)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = clocks.stop()
+        ms_total = e0.elapsed_time(e1)
+        launches = api.launch_count() - l0
+        ngrad = (api.kernel_count(1) - g0) / K
+        prof = {k: api.profile_read(k) for k in range(6)}
+        api.profile_enable(False)
+    sweeps = SOLVE["max_emiter"] + ngrad
+    units_step = R * M * sweeps
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / K
+    value = world * units_step / (ms_step * 1e-3)
+
+    # ---------------- end to end through the drop-in C entry point (`e2e`) ----------------
+    e2e = None
+    if not args.no_e2e:
+        dp.close()
+        h2d = coh_h.nbytes + x_h.nbytes + pp_h.nbytes + R  # coherencies, data, Jones, flags
+        d2h = x_h.nbytes + pp_h.nbytes
+        with torch.cuda.stream(stream):
+            def one():
+                x_h[:] = pr.x
+                pp_h[:] = pr.pp0
+                return api.sagefit_visibilities(pr.u, pr.v, pr.w, x_h, pr.N, pr.Nbase, pr.tilesz,
+                                                barr, sky, coh_h, pp_h, **SOLVE)
+            one()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            for _ in range(K):
+                one()
+            f1.record(stream)
+            torch.cuda.synchronize()
+        te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te.item()) / K
+        e2e = {"value": world * units_step / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant own kernel ----------------
+    peak, peak_src = measured_peaks()
+    names = ["k_predict_full", "k_grad_full", "k_cluster_pass", "k_coh_gram", "assemble",
+             "damped_solve(cusolver)"]
+    shares = {}
+    for k in range(6):
+        n, ms, by = prof[k]
+        shares[names[k]] = {"launches_per_step": n / K, "ms_per_step": ms / K,
+                            "share_of_step": (ms / K) / ms_step if ms_step else None,
+                            "GBps": (by / (ms * 1e-3)) / 1e9 if ms > 0 and by > 0 else None}
+    own = {k: v for k, v in shares.items() if not k.startswith("damped")}
+    dom = max(own, key=lambda k: own[k]["ms_per_step"])
+    n, ms, by = prof[names.index(dom)]
+    achieved = (by / (ms * 1e-3)) / 1e9 if ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "launches_in_timed_region": n, "avg_launch_us": 1e3 * ms / n if n else None,
+                "kernels": shares}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, sec, desc = cpu_reference_run(1, 0, shape["seed"])
+        if v is not None:
+            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                   "sample": desc, "seconds_per_step": sec}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                   "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: N=%d stations, %d baselines, M=%d clusters, tilesz=%d, "
+                               "rows=%d per GPU" % (args.workload, pr.N, pr.Nbase, M, pr.tilesz, R),
+                   "solve": SOLVE, "sweeps_per_step": sweeps,
+                   "units_per_step": "rows*clusters*(em_sweeps+lbfgs_grad_evals)",
+                   "l2": "inputs (%.0f MB coherencies) larger than the 126 MB L2, no flush needed"
+                         % (coh_h.nbytes / 1e6),
+                   "parallelism": "one independent solve interval per GPU" if world > 1 else "1 GPU",
+                   "final_res": [res[2], res[3]] if res else None},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -168,8 +168,27 @@ void dirac_b200_grad(dirac_b200_problem *pr, const double *pp, double *g, int ro
 double dirac_b200_normal_eq(dirac_b200_problem *pr, int clus, int chunk, const double *pblk,
                             const double *xd, double *JTJ, double *JTe);
 
+/* sagefit_visibilities (lmfit.c:778-1053) on an already resident problem: no upload, Jones pp
+ * in/out on the host, final residual to x_out (API layout) unless x_out == NULL.  This is what the
+ * drop-in sagefit_visibilities calls between dirac_b200_create and dirac_b200_destroy. */
+int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_out, int max_emiter,
+                       int max_iter, int max_lbfgs, int lbfgs_m, int linsolv, int solver_mode,
+                       double nulow, double nuhigh, int randomize, double *mean_nu, double *res_0,
+                       double *res_1);
+
+/* run on a caller-supplied CUDA stream (cudaStream_t) instead of a private one; NULL restores the
+ * default.  Affects problems created afterwards and the reference entry points. */
+void dirac_b200_set_stream(void *stream);
+
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 unsigned long long dirac_b200_launch_count(void);
+/* per-launch CUDA-event timing of the library's kernels on their launching stream.
+ * kind: 0 k_predict_full, 1 k_grad_full, 2 k_cluster_pass, 3 k_coh_gram, 4 assemble, 5 damped solve
+ * (cuSOLVER).  enable(1) clears the records; read returns the launch count and sums the elapsed
+ * milliseconds and the algorithmic bytes of the recorded launches of that kind. */
+unsigned long long dirac_b200_kernel_count(int kind); /* launches of `kind` since load */
+void dirac_b200_profile_enable(int on);
+int dirac_b200_profile_read(int kind, double *ms, double *bytes);
 
 #ifdef __cplusplus
 }

@@ -122,7 +122,9 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   a.mode = mode; a.write_out = write_out;
   if (jte_dev && mode <= 1)
     DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
+  db_prof_begin(2, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0)), d.stream);
   db_launch_cluster_pass(&a, d.ntile, d.stream);
+  db_prof_end(d.stream);
   db_count_launch(1);
 }
 
@@ -132,7 +134,9 @@ static void gram(dirac_b200_problem *pr, int k, int t0, int t1, int step, double
   GramArgs a;
   a.coh = d.coh; a.flag = d.flag; a.tiles = d.tiles; a.T = Tdst; a.R = d.R; a.N = d.N;
   a.Nbase = d.Nbase; a.k0 = k; a.t_begin = t0; a.t_end = t1; a.t_step = step;
+  db_prof_begin(3, (double)((t1 - t0 + step - 1) / step) * d.Nbase * 65.0 + 128.0 * d.Nbase, d.stream);
   db_launch_coh_gram(&a, d.ntile, 1, d.stream);
+  db_prof_end(d.stream);
   db_count_launch(1);
 }
 
@@ -144,7 +148,9 @@ static void assemble(dirac_b200_problem *pr, const double *T, const double *pblk
   AssembleArgs a;
   a.T = T; a.pblk = pblk_dev; a.JTJ = JTJ; a.Hst = w.Hst; a.tiles = d.tiles; a.N = d.N;
   a.Nbase = d.Nbase;
+  db_prof_begin(4, 128.0 * d.Nbase + 8.0 * 64.0 * d.N * d.N, d.stream);
   db_launch_assemble(&a, d.ntile, d.stream);
+  db_prof_end(d.stream);
   db_count_launch(2);
 }
 
@@ -174,6 +180,7 @@ static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double e
   DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice, d.stream));
   int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
   hinfo[0] = hinfo[1] = 0;
+  db_prof_begin(5, 0.0, d.stream);
   if (linsolv == 0) {
     CS_CHECK(cusolverDnDpotrf(w.cs, CUBLAS_FILL_MODE_LOWER, n, w.JTJ, n, w.cswork, w.lwork,
                               w.devinfo));
@@ -211,12 +218,14 @@ static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double e
     for (int i = 0; i < n; i++) hb[i] = (hS[i] > eps1) ? hb[i] / hS[i] : 0.0;
     DB_CHECK(cudaMemcpyAsync(w.pnew, hb, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream));
     CB_CHECK(cublasDgemv(w.cb, CUBLAS_OP_T, n, n, &one, w.svdVT, n, w.pnew, 1, &zero, w.Dp, 1));
+    db_prof_end(d.stream);
     DB_CHECK(cudaStreamSynchronize(d.stream));
     free(hS);
     free(hb);
     db_count_launch(2);
     return 1;
   }
+  db_prof_end(d.stream);
   // the step itself comes back with the status
   DB_CHECK(cudaMemcpyAsync(w.h_vec + 2 * n, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost,
                            d.stream));

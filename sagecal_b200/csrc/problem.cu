@@ -12,6 +12,63 @@ static unsigned long long g_launches = 0;
 void db_count_launch(int n) { g_launches += (unsigned long long)n; }
 extern "C" unsigned long long dirac_b200_launch_count(void) { return g_launches; }
 
+// ---- optional per-launch CUDA-event timing (bench.py's roofline leg) -----------------------------
+struct ProfRec { cudaEvent_t a, b; int kind; double bytes; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_evpool;
+static int g_prof_on = 0;
+static cudaEvent_t prof_event() {
+  if (!g_evpool.empty()) { cudaEvent_t e = g_evpool.back(); g_evpool.pop_back(); return e; }
+  cudaEvent_t e;
+  DB_CHECK(cudaEventCreate(&e));
+  return e;
+}
+static unsigned long long g_kind_count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+extern "C" unsigned long long dirac_b200_kernel_count(int kind) {
+  return (kind >= 0 && kind < 8) ? g_kind_count[kind] : 0ull;
+}
+void db_prof_begin(int kind, double bytes, cudaStream_t st) {
+  if (kind >= 0 && kind < 8) g_kind_count[kind]++;
+  if (!g_prof_on) return;
+  ProfRec r; r.a = prof_event(); r.b = prof_event(); r.kind = kind; r.bytes = bytes;
+  DB_CHECK(cudaEventRecord(r.a, st));
+  g_prof.push_back(r);
+}
+void db_prof_end(cudaStream_t st) {
+  if (!g_prof_on) return;
+  DB_CHECK(cudaEventRecord(g_prof.back().b, st));
+}
+extern "C" void dirac_b200_profile_enable(int on) {
+  for (auto &r : g_prof) { g_evpool.push_back(r.a); g_evpool.push_back(r.b); }
+  g_prof.clear();
+  g_prof_on = on;
+}
+extern "C" int dirac_b200_profile_read(int kind, double *ms, double *bytes) {
+  DB_CHECK(cudaDeviceSynchronize());
+  int cnt = 0; double t = 0.0, by = 0.0;
+  for (auto &r : g_prof) if (r.kind == kind) {
+    float f = 0.f; DB_CHECK(cudaEventElapsedTime(&f, r.a, r.b)); t += f; by += r.bytes; cnt++;
+  }
+  if (ms) *ms = t;
+  if (bytes) *bytes = by;
+  return cnt;
+}
+
+// ---- stream the library works on: its own, unless the host supplies one ---------------------------
+static cudaStream_t g_user_stream = nullptr;
+static int g_have_user_stream = 0;
+extern "C" void dirac_b200_set_stream(void *stream) {
+  g_user_stream = (cudaStream_t)stream;
+  g_have_user_stream = (stream != nullptr);
+}
+cudaStream_t db_new_stream(int *owned) {
+  if (g_have_user_stream) { *owned = 0; return g_user_stream; }
+  cudaStream_t st;
+  DB_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  *owned = 1;
+  return st;
+}
+
 static void require_gpu() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -67,7 +124,7 @@ extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
   d.N = N; d.Nbase = Nbase; d.tilesz = tilesz; d.M = M; d.Mt = Mt;
   d.R = (long long)Nbase * tilesz;
   DB_CHECK(cudaGetDevice(&d.device));
-  DB_CHECK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+  d.stream = db_new_stream(&pr->own_stream);
   const long long R = d.R;
 
   // --- row order must be the canonical one (baseline_utils.c:445-461): checked, bit-exact ---
@@ -165,7 +222,7 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   cudaFree(pr->partials); cudaFree(pr->res); cudaFree(pr->g); cudaFree(pr->vis_stage);
   cudaFreeHost(d.h_scal);
   free(d.h_clus); free(d.h_chunk_poff);
-  cudaStreamDestroy(d.stream);
+  if (pr->own_stream) cudaStreamDestroy(d.stream);
   delete pr;
 }
 
@@ -221,7 +278,9 @@ void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, 
   a.cost = d.scal + slot; a.counter = d.counters; a.R = d.R; a.N = d.N; a.Nbase = d.Nbase;
   a.tilesz = d.tilesz; a.M = d.M; a.out_mode = out_mode; a.cost_mode = cost_mode;
   a.inv_nu = (nu > 0.0) ? 1.0 / nu : 0.0;
+  db_prof_begin(0, (double)d.R * (64.0 * d.M + 65.0 + (out_mode ? 64.0 : 0.0)), d.stream);
   db_launch_predict_full(&a, d.ntile, d.stream);
+  db_prof_end(d.stream);
   db_count_launch(1);
 }
 
@@ -245,7 +304,9 @@ void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, in
   // sign conventions of the reference: Gaussian g = -2 Re(conj(f-d) . df) (robust_lbfgs.c:554),
   // robust g = +2 (f-d) df/(nu+(f-d)^2) (robust_lbfgs.c:286-299); here e = d-f
   a.scale = robust ? -2.0 : 2.0;
+  db_prof_begin(1, (double)d.R * (64.0 * d.M + 65.0) + 64.0 * d.N * d.Mt, d.stream);
   db_launch_grad_full(&a, d.ntile, d.stream);
+  db_prof_end(d.stream);
   db_count_launch(1);
 }
 

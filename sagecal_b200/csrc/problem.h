@@ -35,9 +35,13 @@ struct dirac_b200_problem {
   double2 *vis_stage;     // [R][4] API-layout staging
   double *g;              // [8*N*Mt]
   LMWork lm;
+  int own_stream;
 };
 
 void db_count_launch(int n);
+void db_prof_begin(int kind, double bytes, cudaStream_t st);
+void db_prof_end(cudaStream_t st);
+cudaStream_t db_new_stream(int *owned);
 void db_upload_vis(dirac_b200_problem *pr, const double *h, double2 *dst);
 void db_download_vis(dirac_b200_problem *pr, const double2 *src, double *h);
 void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, int out_mode,

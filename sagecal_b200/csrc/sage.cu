@@ -24,14 +24,12 @@ static bool is_robust_mode(int solver_mode) {
          solver_mode == SM_RTR_OSRLM_RLBFGS || solver_mode == SM_NSD_RLBFGS;
 }
 
-extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase,
-                                    int tilesz, baseline_t *barr, clus_source_t *carr,
-                                    double *coh, int M, int Mt, double freq0, double fdelta,
-                                    double *pp, double uvmin, int Nt, int max_emiter, int max_iter,
-                                    int max_lbfgs, int lbfgs_m, int gpu_threads, int linsolv,
-                                    int solver_mode, double nulow, double nuhigh, int randomize,
-                                    double *mean_nu, double *res_0, double *res_1) {
-  (void)u; (void)v; (void)w; (void)freq0; (void)fdelta; (void)uvmin; (void)Nt; (void)gpu_threads;
+// SAGE/EM on an already resident problem.  pp: host, in/out.  If x_out != NULL the final residual is
+// written there (API layout).  Mirrors lmfit.c:778-1053.
+extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_out,
+                                  int max_emiter, int max_iter, int max_lbfgs, int lbfgs_m,
+                                  int linsolv, int solver_mode, double nulow, double nuhigh,
+                                  int randomize, double *mean_nu, double *res_0, double *res_1) {
   if (solver_mode == SM_RTR_OSLM_LBFGS || solver_mode == SM_RTR_OSRLM_RLBFGS ||
       solver_mode == SM_NSD_RLBFGS) {
     fprintf(stderr, "dirac_b200: solver_mode %d (RTR/NSD) is outside this library's scope; use "
@@ -42,10 +40,11 @@ extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, 
     fprintf(stderr, "%s: %d: undefined solver mode\n", __FILE__, __LINE__);  // lmfit.c:957-962
     exit(1);
   }
-  const int m = N * Mt * 8;
-  const long long n = (long long)Nbase * tilesz * 8;
-  dirac_b200_problem *pr = dirac_b200_create(N, Nbase, tilesz, barr, carr, M, Mt, coh, x);
   DevProblem &d = pr->d;
+  const int N = d.N, M = d.M, Mt = d.Mt;
+  const int m = N * Mt * 8;
+  const long long n = (long long)d.Nbase * d.tilesz * 8;
+  const ClusterDesc *hc = d.h_clus;
   // CPU-path LM thresholds (lmfit.c:801)
   double opts[5] = {1e-3, 1e-15, 1e-15, 1e-20, -1e-6};
   double info[10];
@@ -72,8 +71,8 @@ extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, 
       }
       if (this_itermax > 0) {
         double init_res = 0.0, final_res = 0.0;
-        for (int ck = 0; ck < carr[cj].nchunk; ck++) {
-          double *pblk = d.pp + carr[cj].p[ck];
+        for (int ck = 0; ck < hc[cj].nchunk; ck++) {
+          double *pblk = d.pp + d.h_chunk_poff[hc[cj].chunk0 + ck];
           const bool last = (ci == max_emiter - 1);
           if (solver_mode == SM_OSLM_LBFGS) {
             db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, last ? 0 : 1, randomize,
@@ -108,7 +107,7 @@ extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, 
         } else {
           nerr[cj] = 0.0;
         }
-        if (robust && ci == max_emiter - 1) robust_nuM[cj] /= (double)carr[cj].nchunk;
+        if (robust && ci == max_emiter - 1) robust_nuM[cj] /= (double)hc[cj].nchunk;
       }
     }
     double total_err = 0.0;
@@ -144,11 +143,25 @@ extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, 
   DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
   db_predict_dev(pr, d.pp, r, 1, 1, 0.0, 0);
   *res_1 = sqrt(db_read_scalar(pr, 0)) / (double)n;
-  db_download_vis(pr, r, x);
+  if (x_out) db_download_vis(pr, r, x_out);
   *mean_nu = robust_nu0;
   DB_CHECK(cudaGetLastError());
-  dirac_b200_destroy(pr);
   return (*res_1 > *res_0) ? -1 : 0;
+}
+
+extern "C" int sagefit_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                    int tilesz, baseline_t *barr, clus_source_t *carr,
+                                    double *coh, int M, int Mt, double freq0, double fdelta,
+                                    double *pp, double uvmin, int Nt, int max_emiter, int max_iter,
+                                    int max_lbfgs, int lbfgs_m, int gpu_threads, int linsolv,
+                                    int solver_mode, double nulow, double nuhigh, int randomize,
+                                    double *mean_nu, double *res_0, double *res_1) {
+  (void)u; (void)v; (void)w; (void)freq0; (void)fdelta; (void)uvmin; (void)Nt; (void)gpu_threads;
+  dirac_b200_problem *pr = dirac_b200_create(N, Nbase, tilesz, barr, carr, M, Mt, coh, x);
+  int rv = dirac_b200_sagefit(pr, pp, x, max_emiter, max_iter, max_lbfgs, lbfgs_m, linsolv,
+                              solver_mode, nulow, nuhigh, randomize, mean_nu, res_0, res_1);
+  dirac_b200_destroy(pr);
+  return rv;
 }
 
 #define SAGEFIT_ALIAS(name)                                                                      \

@@ -19,7 +19,9 @@ EXPORTED = [
     "precalculate_coherencies", "predict_visibilities_multifreq", "generate_baselines",
     "preset_flags_and_data", "dirac_b200_create", "dirac_b200_destroy", "dirac_b200_set_data",
     "dirac_b200_precalculate", "dirac_b200_get_coherencies", "dirac_b200_predict",
-    "dirac_b200_grad", "dirac_b200_normal_eq", "dirac_b200_launch_count",
+    "dirac_b200_grad", "dirac_b200_normal_eq", "dirac_b200_launch_count", "dirac_b200_sagefit",
+    "dirac_b200_set_stream", "dirac_b200_profile_enable", "dirac_b200_profile_read",
+    "dirac_b200_kernel_count",
 ]
 
 
@@ -52,9 +54,33 @@ class DiracB200(DiracAPI):
         L.dirac_b200_normal_eq.restype = d
         L.dirac_b200_normal_eq.argtypes = [vp, i, i, dp, dp, dp, dp]
         L.dirac_b200_launch_count.restype = C.c_ulonglong
+        L.dirac_b200_sagefit.restype = i
+        L.dirac_b200_sagefit.argtypes = [vp, dp, dp, i, i, i, i, i, i, d, d, i, dp, dp, dp]
+        L.dirac_b200_set_stream.argtypes = [vp]
+        L.dirac_b200_kernel_count.restype = C.c_ulonglong
+        L.dirac_b200_kernel_count.argtypes = [i]
+        L.dirac_b200_profile_enable.argtypes = [i]
+        L.dirac_b200_profile_read.restype = i
+        L.dirac_b200_profile_read.argtypes = [i, dp, dp]
 
     def launch_count(self) -> int:
         return int(self.lib.dirac_b200_launch_count())
+
+    def kernel_count(self, kind) -> int:
+        return int(self.lib.dirac_b200_kernel_count(kind))
+
+    def set_stream(self, cuda_stream_ptr):
+        self.lib.dirac_b200_set_stream(C.c_void_p(cuda_stream_ptr))
+
+    def profile_enable(self, on=True):
+        self.lib.dirac_b200_profile_enable(1 if on else 0)
+
+    def profile_read(self, kind):
+        """(launches, total ms, total algorithmic bytes) of the recorded launches of `kind`"""
+        ms = C.c_double(0.0)
+        by = C.c_double(0.0)
+        n = self.lib.dirac_b200_profile_read(kind, C.byref(ms), C.byref(by))
+        return n, ms.value, by.value
 
 
 class DeviceProblem:
@@ -108,6 +134,18 @@ class DeviceProblem:
         g = np.zeros(self.m)
         self.api.lib.dirac_b200_grad(self.h, dptr(pp), dptr(g), 1 if robust else 0, nu)
         return g
+
+    def sagefit(self, pp, x_out=None, max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, linsolv=0,
+                solver_mode=1, nulow=2.0, nuhigh=30.0, randomize=0):
+        """dirac_b200_sagefit on the resident problem; pp updated in place.
+        returns (retval, mean_nu, res_0, res_1)"""
+        nu, r0, r1 = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+        rv = self.api.lib.dirac_b200_sagefit(self.h, dptr(pp),
+                                             dptr(x_out) if x_out is not None else None,
+                                             max_emiter, max_iter, max_lbfgs, lbfgs_m, linsolv,
+                                             solver_mode, nulow, nuhigh, randomize, C.byref(nu),
+                                             C.byref(r0), C.byref(r1))
+        return rv, nu.value, r0.value, r1.value
 
     def normal_eq(self, clus, chunk, pblk, xd):
         n8 = 8 * self.N

@@ -7,9 +7,9 @@ src/lib/Dirac/Dirac_common.h:173-195 (clus_source_t, baseline_t), Dirac.h:1651,1
 (precalculate_coherencies, predict_visibilities_multifreq).
 
 `DiracAPI(path)` binds any shared library that implements this ABI.  The product library is
-`sagecal_b200/libdirac_b200.so` (see `sagecal_b200.lib`); tests additionally bind the
-compiled reference (`oracle/_ref/libdirac_ref.so`) through the very same class, which is what
-makes the parity tests read like "call both, compare".
+`sagecal_b200/libdirac_b200.so` (see `sagecal_b200.lib`); the test suite additionally binds the
+compiled reference through the very same class, which is what makes the parity tests read like
+"call both, compare".  Nothing in this package loads that library.
 """
 from __future__ import annotations
 

@@ -168,6 +168,12 @@ void dirac_b200_grad(dirac_b200_problem *pr, const double *pp, double *g, int ro
 double dirac_b200_normal_eq(dirac_b200_problem *pr, int clus, int chunk, const double *pblk,
                             const double *xd, double *JTJ, double *JTe);
 
+/* the same system with the sqrt-weights of the robust LM applied to the rows of J and to e
+ * (robustlm.c:2298-2316); wt has 8 weights per row of the full interval, API layout. */
+double dirac_b200_normal_eq_weighted(dirac_b200_problem *pr, int clus, int chunk,
+                                     const double *pblk, const double *xd, const double *wt,
+                                     double *JTJ, double *JTe);
+
 /* sagefit_visibilities (lmfit.c:778-1053) on an already resident problem: no upload, Jones pp
  * in/out on the host, final residual to x_out (API layout) unless x_out == NULL.  This is what the
  * drop-in sagefit_visibilities calls between dirac_b200_create and dirac_b200_destroy. */

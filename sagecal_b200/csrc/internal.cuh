@@ -217,6 +217,24 @@ struct ClusterPassArgs {
              // 2: ADD   out = in + m          (no cost / jte)
              // 3: SUB   out = in - m          (no cost / jte)
   int write_out;
+  const double2 *wt;         // [4][R] sqrt-weights (re,im) of the robust LM, or null.  With
+                             // weights: cost = ||wt.e||^2 and J^T e -> J^T (wt^2 . e); the vector
+                             // written for mode 1 stays the UNWEIGHTED e
+};
+
+// weighted normal matrix of the robust LM (J <- wt.J, robustlm.c:2298-2307), one polarisation
+// product c = (i,j) of the visibility per pass of the CTA over its rows
+struct WeightedJtjArgs {
+  const double2 *coh_k;      // [4][R]
+  const double2 *wt;         // [4][R] sqrt-weights
+  const unsigned char *flag;
+  const double *pblk;
+  const TileDesc *tiles;
+  double *JTJ;               // [8N][8N], zeroed by the caller; off-diagonal blocks accumulate here
+  double *HP, *HQ;           // [N][2][10] station sums of the p-role / q-role diagonal terms, zeroed
+  long long R;
+  int N, Nbase;
+  int t_begin, t_end, tslice;
 };
 
 struct GramArgs {

@@ -137,7 +137,15 @@ __global__ void k_copy_add_diag(const double *__restrict__ A0, double *__restric
   }
 }
 
+__global__ void k_extract_diag(const double *__restrict__ A, double *__restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = A[(long long)i * n + i];
+}
+
 extern "C" {
+void db_launch_extract_diag(const double *A, double *dst, int n, cudaStream_t st) {
+  k_extract_diag<<<(n + 127) / 128, 128, 0, st>>>(A, dst, n);
+}
 void db_launch_assemble(const AssembleArgs *a, int ntile, cudaStream_t st) {
   k_assemble_offdiag<<<ntile, TILE_THREADS, 0, st>>>(*a);
   k_assemble_diag<<<(a->N + 63) / 64, 64, 0, st>>>(a->Hst, a->JTJ, a->N);

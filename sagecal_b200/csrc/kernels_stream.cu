@@ -423,10 +423,22 @@ k_cluster_pass(ClusterPassArgs a) {
         }
       }
       if (a.mode <= 1) {
+        if (a.wt) {
+          // robust LM: e <- wt.e for the cost, J^T (wt.(wt.e)) for the gradient
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          cost = fma(e[c].x, e[c].x, cost);
-          cost = fma(e[c].y, e[c].y, cost);
+          for (int c = 0; c < 4; c++) {
+            const double2 wv = ld_stream(a.wt + (long long)c * a.R + row);
+            const double ex = wv.x * e[c].x, ey = wv.y * e[c].y;
+            cost = fma(ex, ex, cost);
+            cost = fma(ey, ey, cost);
+            e[c] = make_double2(wv.x * ex, wv.y * ey);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            cost = fma(e[c].x, e[c].x, cost);
+            cost = fma(e[c].y, e[c].y, cost);
+          }
         }
         if (want_grad && !fl) accum_W(W, e, C);
       }

@@ -1,10 +1,12 @@
 // Per-cluster Levenberg-Marquardt on the device-resident problem.
 //
-// Control flow mirrors clevmar_der_single_nocuda (clmfit.c:219-529) and
-// oslevmar_der_single_nocuda (clmfit.c:1281-1640) decision for decision; what differs is how the
-// quantities are produced:
+// Control flow mirrors clevmar_der_single_nocuda (clmfit.c:219-529), oslevmar_der_single_nocuda
+// (clmfit.c:1281-1640), rlevmar_der_single_nocuda (robustlm.c:2008-2600) and
+// osrlevmar_der_single_nocuda (robustlm.c:2607-3250) decision for decision; what differs is how
+// the quantities are produced:
 //   e, ||e||^2, J^T e   one streaming pass over (hidden data, coh_k)          k_cluster_pass
 //   J^T J               assembled from the per-baseline Gram tensors           k_coh_gram/k_assemble
+//                       (weighted, robust LM: one streaming pass)              k_weighted_jtj
 //   (J^T J + mu I) dp   cuSOLVER potrf/potrs | geqrf+ormqr+trsm | gesvd        (library, not HBM bound)
 // The dense n x 8N Jacobian of the reference (7.2 GB per cluster at N=62, T=120) never exists.
 #include <float.h>
@@ -31,6 +33,18 @@
     }                                                                                      \
   } while (0)
 
+extern "C" {
+void db_launch_weighted_jtj(const WeightedJtjArgs *a, int ntile, cudaStream_t st);
+void db_launch_sum_abs(const double2 *v, long long R, long long r0, long long r1, double *partials,
+                       double *out, unsigned int *counter, cudaStream_t st);
+void db_launch_update_weights(const double2 *e, double2 *wt, long long R, long long r0,
+                              long long r1, double nu0, double *partials, double *out,
+                              unsigned int *counter, cudaStream_t st);
+void db_launch_scale_vis(double2 *v, long long R, long long r0, long long r1, double alpha,
+                         int set_const, cudaStream_t st);
+void db_launch_extract_diag(const double *A, double *dst, int n, cudaStream_t st);
+}
+
 template <typename T>
 static T *dalloc(size_t n) {
   T *p = nullptr;
@@ -54,10 +68,13 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.Hst = dalloc<double>((size_t)4 * d.N);
   w.Dp = dalloc<double>(n8);
   w.pnew = dalloc<double>(n8);
+  w.plast = dalloc<double>(n8);
   w.devinfo = dalloc<int>(4);
   w.tau = dalloc<double>(n8);
   w.svdS = w.svdU = w.svdVT = nullptr;
-  DB_CHECK(cudaMallocHost((void **)&w.h_vec, sizeof(double) * (4 * n8 + 4 * d.N + 16)));
+  w.wbuf = w.ebuf = nullptr;
+  w.HP = w.HQ = nullptr;
+  DB_CHECK(cudaMallocHost((void **)&w.h_vec, sizeof(double) * (5 * n8 + 4 * d.N + 32)));
   CS_CHECK(cusolverDnCreate(&w.cs));
   CS_CHECK(cusolverDnSetStream(w.cs, d.stream));
   CB_CHECK(cublasCreate(&w.cb));
@@ -77,13 +94,24 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.ready = true;
 }
 
+static void robust_init(dirac_b200_problem *pr) {
+  LMWork &w = pr->lm;
+  if (w.wbuf) return;
+  DevProblem &d = pr->d;
+  w.wbuf = dalloc<double2>((size_t)4 * d.R);
+  w.ebuf = dalloc<double2>((size_t)4 * d.R);
+  w.HP = dalloc<double>((size_t)d.N * 20);
+  w.HQ = dalloc<double>((size_t)d.N * 20);
+}
+
 void db_lm_free(dirac_b200_problem *pr) {
   LMWork &w = pr->lm;
   if (!w.ready) return;
   cudaFree(w.T); cudaFree(w.Tsub); cudaFree(w.JTJ0); cudaFree(w.JTJ); cudaFree(w.JTe);
-  cudaFree(w.JTe_new); cudaFree(w.Hst); cudaFree(w.Dp); cudaFree(w.pnew); cudaFree(w.devinfo);
-  cudaFree(w.tau); cudaFree(w.cswork); cudaFree(w.dbuf);
+  cudaFree(w.JTe_new); cudaFree(w.Hst); cudaFree(w.Dp); cudaFree(w.pnew); cudaFree(w.plast);
+  cudaFree(w.devinfo); cudaFree(w.tau); cudaFree(w.cswork); cudaFree(w.dbuf);
   if (w.svdS) { cudaFree(w.svdS); cudaFree(w.svdU); cudaFree(w.svdVT); }
+  if (w.wbuf) { cudaFree(w.wbuf); cudaFree(w.ebuf); cudaFree(w.HP); cudaFree(w.HQ); }
   cudaFreeHost(w.h_vec);
   free(w.T_valid);
   cusolverDnDestroy(w.cs);
@@ -107,7 +135,7 @@ static int pick_tslice(const DevProblem &d, int nt) {
 // one streaming pass of cluster k over timeslots [t0,t1): see ClusterPassArgs for the modes
 void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
                      double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
-                     int t1) {
+                     int t1, const double2 *wt) {
   DevProblem &d = pr->d;
   if (t1 <= t0) {
     if (mode <= 1) DB_CHECK(cudaMemsetAsync(d.scal + cost_slot, 0, sizeof(double), d.stream));
@@ -119,10 +147,11 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   a.in = in; a.flag = d.flag; a.pblk = pblk_dev; a.tiles = d.tiles; a.out = out; a.jte = jte_dev;
   a.partials = pr->partials; a.cost = d.scal + cost_slot; a.counter = d.counters; a.R = d.R;
   a.N = d.N; a.Nbase = d.Nbase; a.t_begin = t0; a.t_end = t1; a.tslice = pick_tslice(d, t1 - t0);
-  a.mode = mode; a.write_out = write_out;
+  a.mode = mode; a.write_out = write_out; a.wt = wt;
   if (jte_dev && mode <= 1)
     DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
-  db_prof_begin(2, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0)), d.stream);
+  db_prof_begin(2, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
+                                                 (wt ? 64.0 : 0.0)), d.stream);
   db_launch_cluster_pass(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
   db_count_launch(1);
@@ -134,7 +163,8 @@ static void gram(dirac_b200_problem *pr, int k, int t0, int t1, int step, double
   GramArgs a;
   a.coh = d.coh; a.flag = d.flag; a.tiles = d.tiles; a.T = Tdst; a.R = d.R; a.N = d.N;
   a.Nbase = d.Nbase; a.k0 = k; a.t_begin = t0; a.t_end = t1; a.t_step = step;
-  db_prof_begin(3, (double)((t1 - t0 + step - 1) / step) * d.Nbase * 65.0 + 128.0 * d.Nbase, d.stream);
+  db_prof_begin(3, (double)((t1 - t0 + step - 1) / step) * d.Nbase * 65.0 + 128.0 * d.Nbase,
+                d.stream);
   db_launch_coh_gram(&a, d.ntile, 1, d.stream);
   db_prof_end(d.stream);
   db_count_launch(1);
@@ -150,6 +180,27 @@ static void assemble(dirac_b200_problem *pr, const double *T, const double *pblk
   a.Nbase = d.Nbase;
   db_prof_begin(4, 128.0 * d.Nbase + 8.0 * 64.0 * d.N * d.N, d.stream);
   db_launch_assemble(&a, d.ntile, d.stream);
+  db_prof_end(d.stream);
+  db_count_launch(2);
+}
+
+// weighted J^T J of cluster k over timeslots [t0,t1) by streaming (robust LM)
+static void weighted_jtj(dirac_b200_problem *pr, int k, int t0, int t1, const double *pblk_dev,
+                         const double2 *wt, double *JTJ) {
+  DevProblem &d = pr->d;
+  LMWork &w = pr->lm;
+  const int n = w.n8;
+  DB_CHECK(cudaMemsetAsync(JTJ, 0, sizeof(double) * (size_t)n * n, d.stream));
+  DB_CHECK(cudaMemsetAsync(w.HP, 0, sizeof(double) * 20 * d.N, d.stream));
+  DB_CHECK(cudaMemsetAsync(w.HQ, 0, sizeof(double) * 20 * d.N, d.stream));
+  if (t1 <= t0) return;
+  WeightedJtjArgs a;
+  a.coh_k = d.coh + (size_t)k * 4 * d.R;
+  a.wt = wt; a.flag = d.flag; a.pblk = pblk_dev; a.tiles = d.tiles; a.JTJ = JTJ; a.HP = w.HP;
+  a.HQ = w.HQ; a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.t_begin = t0; a.t_end = t1;
+  a.tslice = pick_tslice(d, t1 - t0);
+  db_prof_begin(6, (double)(t1 - t0) * d.Nbase * 129.0 + 8.0 * 64.0 * d.N * d.N, d.stream);
+  db_launch_weighted_jtj(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
   db_count_launch(2);
 }
@@ -219,6 +270,8 @@ static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double e
     DB_CHECK(cudaMemcpyAsync(w.pnew, hb, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream));
     CB_CHECK(cublasDgemv(w.cb, CUBLAS_OP_T, n, n, &one, w.svdVT, n, w.pnew, 1, &zero, w.Dp, 1));
     db_prof_end(d.stream);
+    DB_CHECK(cudaMemcpyAsync(w.h_vec + 2 * n, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                             d.stream));
     DB_CHECK(cudaStreamSynchronize(d.stream));
     free(hS);
     free(hb);
@@ -240,57 +293,66 @@ static double nrm2sq(const double *v, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// LM on chunk ck of cluster k.  `r` holds the residual of the full model over the whole interval;
-// on return the chunk's rows of `r` are the residual with the updated Jones.  pblk_dev points at
-// the 8N parameters inside the device copy of pp (updated in place).
-//   os != 0 : ordered-subsets variant (clmfit.c:1074): J^T J and J^T e of ONE of Nsubsets time
-//             subsets per iteration.
-// info[0] = ||e||^2 at entry, info[1] = ||e||^2 at exit (lmfit.c:963-964 uses exactly these).
+// the LM iteration loop shared by the four reference variants.  On entry the hidden data of the
+// chunk is in w.dbuf and pblk_dev holds p.  If `have_first` the caller already produced
+// ||e||^2 (in *first_cost) and J^T e (in w.JTe) at p with the same weights (the fused first pass).
+// wt == null: plain LM, J^T J from the cached Gram tensor; wt != null: robust LM round.
+// `nu_damp` is the integer damping multiplier that the robust driver carries across its IRLS rounds
+// (robustlm.c keeps `nu` alive over the nw loop).  `evaluated_trial` reports whether w.plast holds
+// the last evaluated trial point (the reference's `ed` after a rejected step, clmfit.c:478).
 // ------------------------------------------------------------------------------------------------
-void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
-                 const double *opts, int linsolv, int os, int randomize, double *info) {
+struct LmOut {
+  double init_eL2, eL2, jacTe_inf, Dp_L2, mu;
+  int k, stop;
+};
+
+static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, double *pblk_dev,
+                    const double2 *wt, int itmax, const double *opts, int linsolv, int os,
+                    int os_shift, int randomize, bool have_first, double first_cost, int *nu_damp,
+                    bool *evaluated_trial, LmOut *out) {
   DevProblem &d = pr->d;
-  db_lm_init(pr);
   LMWork &w = pr->lm;
   const int n = w.n8;
-  int t0, t1;
-  chunk_range(d, k, ck, &t0, &t1);
   const int ntiles = t1 - t0;
-  const double tau = opts ? opts[0] : 1e-3;
-  const double eps1 = opts ? opts[1] : 1e-17;
-  const double eps2 = opts ? opts[2] : 1e-17;
-  const double eps2_sq = eps2 * eps2;
-  const double eps3 = opts ? opts[3] : 1e-17;
-
+  const double tau = opts[0], eps1 = opts[1], eps2 = opts[2], eps2_sq = opts[2] * opts[2],
+               eps3 = opts[3];
   double *hp = w.h_vec;            // current p
   double *hjte = w.h_vec + n;      // J^T e
   double *hDp = w.h_vec + 2 * n;   // step
   double *hpnew = w.h_vec + 3 * n; // trial p
   double *hH = w.h_vec + 4 * n;    // station sums [N][4]
 
-  // hidden data d = r + f(p_old); e = d - f(p_old); ||e||^2; J^T e  (lmfit.c:890-891 fused with
-  // the first func/jacf evaluation, clmfit.c:241-252)
-  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 1, t0, t1);
+  double p_eL2;
   DB_CHECK(cudaMemcpyAsync(hp, pblk_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-  if (!os)
-    DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-  double p_eL2 = db_read_scalar(pr, 1);  // synchronises
+  if (have_first) {
+    p_eL2 = first_cost;
+    if (!os)
+      DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+    DB_CHECK(cudaStreamSynchronize(d.stream));
+  } else {
+    // e = wt.(d - f(p)), ||e||^2, J^T e     (clmfit.c:241-252 / robustlm.c:2235-2251)
+    db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe, 1, t0, t1, wt);
+    if (!os)
+      DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+    p_eL2 = db_read_scalar(pr, 1);
+  }
   const double init_p_eL2 = p_eL2;
   int stop = 0;
   if (!isfinite(p_eL2)) stop = 7;
-  int nu = 2, nu2;
+  int nu = *nu_damp, nu2;
   double mu = 0.0, Dp_L2 = DBL_MAX, jacTe_inf = 0.0;
+  *evaluated_trial = false;
 
   // ordered subsets (clmfit.c:1313-1356)
   int Nsubsets = 10;
   if (ntiles < Nsubsets) Nsubsets = ntiles;
   const int max_os_iter = os ? (int)ceil(0.1 * (double)Nsubsets) : 1;
-  const int Ntper = os && Nsubsets > 0 ? (ntiles + Nsubsets - 1) / Nsubsets : ntiles;
+  const int Ntper = (os && Nsubsets > 0) ? (ntiles + Nsubsets - 1) / Nsubsets : ntiles;
 
-  // Gram tensor of this chunk (time-invariant part of J^T J), built once per solve interval
+  // Gram tensor of this chunk (time-invariant part of the unweighted J^T J), built once
   const int tix = d.h_clus[k].chunk0 + ck;
   double *Tfull = w.T + (size_t)tix * d.Nbase * 16;
-  if (!os && !w.T_valid[tix] && ntiles > 0) {
+  if (!wt && !os && !w.T_valid[tix] && ntiles > 0) {
     gram(pr, k, t0, t1, 1, Tfull);
     w.T_valid[tix] = 1;
   }
@@ -302,29 +364,54 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
       break;
     }
     for (int ositer = 0; ositer < max_os_iter; ositer++) {
-      const double *Tuse = Tfull;
+      int s0 = t0, s1 = t1;
       if (os) {
         int l;
         if (randomize) {
-          l = rand() % Nsubsets;  // FIXME: the reference draws a permutation (clmfit.c:1372)
+          l = rand() % Nsubsets;  // the reference draws a random permutation (clmfit.c:1372)
         } else {
-          l = (kiter + ositer) % Nsubsets;
+          l = (os_shift + kiter + ositer) % Nsubsets;
         }
-        int s0 = t0 + l * Ntper;
-        int s1 = s0 + Ntper;
+        s0 = t0 + l * Ntper;
+        s1 = (l * Ntper + Ntper < ntiles) ? s0 + Ntper : t1;
         if (s0 > t1) s0 = t1;
-        if (s1 > t1 || l == Nsubsets - 1) s1 = t1;
-        // J^T J and J^T e restricted to the subset; e is the current residual d - f(p)
-        gram(pr, k, s0, s1, 1, w.Tsub);
-        db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, w.JTe, 2, s0, s1);
+        // J^T e restricted to the subset; e is the current (weighted) residual d - f(p)
+        db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, w.JTe, 2, s0, s1, wt);
         DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost,
                                  d.stream));
-        Tuse = w.Tsub;
       }
-      assemble(pr, Tuse, pblk_dev, w.JTJ0);
-      DB_CHECK(cudaMemcpyAsync(hH, w.Hst, sizeof(double) * 4 * d.N, cudaMemcpyDeviceToHost,
-                               d.stream));
-      DB_CHECK(cudaStreamSynchronize(d.stream));
+      double mx = 0.0;
+      if (wt) {
+        weighted_jtj(pr, k, s0, s1, pblk_dev, wt, w.JTJ0);
+        // mu0 needs max_i (J^T J)_ii: gather the diagonal and bring it back
+        if (kiter == 0) {
+          double *hdiag = w.h_vec + 4 * n + 4 * d.N + 8;
+          db_launch_extract_diag(w.JTJ0, w.JTe_new, n, d.stream);  // JTe_new is free scratch here
+          db_count_launch(1);
+          DB_CHECK(cudaMemcpyAsync(hdiag, w.JTe_new, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                                   d.stream));
+          DB_CHECK(cudaStreamSynchronize(d.stream));
+          for (int i = 0; i < n; i++)
+            if (fabs(hdiag[i]) > fabs(mx)) mx = hdiag[i];
+        } else {
+          DB_CHECK(cudaStreamSynchronize(d.stream));
+        }
+      } else {
+        const double *Tuse = Tfull;
+        if (os) {
+          gram(pr, k, s0, s1, 1, w.Tsub);
+          Tuse = w.Tsub;
+        }
+        assemble(pr, Tuse, pblk_dev, w.JTJ0);
+        DB_CHECK(cudaMemcpyAsync(hH, w.Hst, sizeof(double) * 4 * d.N, cudaMemcpyDeviceToHost,
+                                 d.stream));
+        DB_CHECK(cudaStreamSynchronize(d.stream));
+        // the diagonal is (h00 x4, h11 x4) per station
+        for (int s = 0; s < d.N; s++) {
+          if (fabs(hH[4 * s]) > fabs(mx)) mx = hH[4 * s];
+          if (fabs(hH[4 * s + 1]) > fabs(mx)) mx = hH[4 * s + 1];
+        }
+      }
       jacTe_inf = 0.0;
       for (int i = 0; i < n; i++) {
         double a = fabs(hjte[i]);
@@ -336,23 +423,10 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
         stop = 1;
         break;
       }
-      if (kiter == 0 && ositer == 0) {
-        // mu0 = tau * max_i (J^T J)_ii ; the diagonal is (h00 x4, h11 x4) per station
-        double mx = 0.0;
-        for (int s = 0; s < d.N; s++) {
-          if (fabs(hH[4 * s]) > fabs(mx)) mx = hH[4 * s];
-          if (fabs(hH[4 * s + 1]) > fabs(mx)) mx = hH[4 * s + 1];
-        }
-        mu = tau * mx;
-      }
+      if (kiter == 0) mu = tau * mx;  // clmfit.c:342-352 (inside the OS loop in the OS variants)
       // adaptive damping loop (clmfit.c:356-540)
       while (1) {
         int issolved = damped_solve(pr, mu, linsolv, eps1);
-        if (linsolv == 2) {
-          DB_CHECK(cudaMemcpyAsync(hDp, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost,
-                                   d.stream));
-          DB_CHECK(cudaStreamSynchronize(d.stream));
-        }
         if (issolved) {
           for (int i = 0; i < n; i++) hpnew[i] = hp[i] + hDp[i];
           Dp_L2 = nrm2sq(hDp, n);
@@ -368,7 +442,10 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
                                    d.stream));
           // trial residual norm and, speculatively, J^T e at the trial point
           db_cluster_pass(pr, k, w.pnew, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe_new, 1, t0,
-                          t1);
+                          t1, wt);
+          DB_CHECK(cudaMemcpyAsync(w.plast, w.pnew, sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                                   d.stream));
+          *evaluated_trial = true;
           const double pDp_eL2 = db_read_scalar(pr, 1);
           if (!isfinite(pDp_eL2)) {
             stop = 7;
@@ -407,18 +484,140 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
     }
   }
   if (kiter >= itmax) stop = 3;
+  *nu_damp = nu;
+  out->init_eL2 = init_p_eL2;
+  out->eL2 = p_eL2;
+  out->jacTe_inf = jacTe_inf;
+  out->Dp_L2 = Dp_L2;
+  out->mu = mu;
+  out->k = kiter;
+  out->stop = stop;
+}
+
+static void fill_info(double *info, const LmOut &o) {
+  if (!info) return;
+  info[0] = o.init_eL2; info[1] = o.eL2; info[2] = o.jacTe_inf; info[3] = o.Dp_L2; info[4] = o.mu;
+  info[5] = (double)o.k; info[6] = (double)o.stop;
+  info[7] = info[8] = info[9] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LM on chunk ck of cluster k (clevmar / oslevmar).  `r` holds the residual of the full model over
+// the whole interval; on return the chunk's rows of `r` are the residual with the updated Jones.
+// pblk_dev points at the 8N parameters inside the device copy of pp (updated in place).
+// info[0] = ||e||^2 at entry, info[1] = ||e||^2 at exit (lmfit.c:963-964 uses exactly these).
+// ------------------------------------------------------------------------------------------------
+void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
+                 const double *opts, int linsolv, int os, int randomize, double *info) {
+  static const double defopts[4] = {1e-3, 1e-17, 1e-17, 1e-17};
+  DevProblem &d = pr->d;
+  db_lm_init(pr);
+  LMWork &w = pr->lm;
+  int t0, t1;
+  chunk_range(d, k, ck, &t0, &t1);
+  // hidden data d = r + f(p_old); e = d - f(p_old); ||e||^2; J^T e  (lmfit.c:890-891 fused with
+  // the first func/jacf evaluation, clmfit.c:241-252)
+  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 1, t0, t1, nullptr);
+  const double c0 = db_read_scalar(pr, 1);
+  int nu = 2;
+  bool ev;
+  LmOut o;
+  lm_core(pr, k, ck, t0, t1, pblk_dev, nullptr, itmax, opts ? opts : defopts, linsolv, os, 0,
+          randomize, true, c0, &nu, &ev, &o);
   // residual of the chunk with the final Jones: r = d - f(p)   (lmfit.c:980-981)
-  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1);
-  if (info) {
-    info[0] = init_p_eL2;
-    info[1] = p_eL2;
-    info[2] = jacTe_inf;
-    info[3] = Dp_L2;
-    info[4] = mu;
-    info[5] = (double)kiter;
-    info[6] = (double)stop;
-    info[7] = info[8] = info[9] = 0.0;
+  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr);
+  fill_info(info, o);
+}
+
+// digamma (updatenu.c:36-49)
+static double digamma_(double x) {
+  double result = 0.0, xx, xx2, xx4;
+  for (; x < 7.0; ++x) result -= 1.0 / x;
+  x -= 0.5;
+  xx = 1.0 / x;
+  xx2 = xx * xx;
+  xx4 = xx2 * xx2;
+  result += log(x) + (1. / 24.) * xx2 - (7.0 / 960.0) * xx4 + (31.0 / 8064.0) * xx4 * xx2 -
+            (127.0 / 30720.0) * xx4 * xx4;
+  return result;
+}
+
+// nu of the 30-point grid on [nulow, nuhigh) with the smallest |psi((nu+1)/2) - ln((nu+1)/2) -
+// psi(nu/2) + ln(nu/2) - sumq + 1|   (q_update_threadfn + idamin, updatenu.c:86-104,237-262)
+static double pick_nu(double sumq, double nulow, double nuhigh) {
+  const int Nd = 30;
+  const double deltanu = (nuhigh - nulow) / (double)Nd;
+  int best = 0;
+  double bestv = 0.0;
+  for (int ci = 0; ci < Nd; ci++) {
+    const double thisnu = nulow + (double)ci * deltanu;
+    double q = digamma_(thisnu * 0.5 + 0.5) - log((thisnu + 1.0) * 0.5);
+    q += -digamma_(thisnu * 0.5) + log(thisnu * 0.5);
+    q += -sumq + 1.0;
+    if (ci == 0 || fabs(q) < bestv) {
+      bestv = fabs(q);
+      best = ci;
+    }
   }
+  return nulow + (double)best * deltanu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// robust LM on chunk ck of cluster k (rlevmar / osrlevmar): three IRLS rounds of weighted LM;
+// between rounds w_i = sqrt((nu+1)/(nu+e_i^2)) from the unweighted residual, nu re-estimated,
+// weights rescaled to the previous mean (robustlm.c:2533-2566).
+// ------------------------------------------------------------------------------------------------
+void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
+                  int linsolv, int os, int randomize, double nulow, double nuhigh,
+                  double *robust_nu, double *info) {
+  static const double defopts[4] = {1e-3, 1e-17, 1e-17, 1e-17};  // opts == NULL (lmfit.c:917)
+  const int wt_itmax = 3;
+  DevProblem &d = pr->d;
+  db_lm_init(pr);
+  robust_init(pr);
+  LMWork &w = pr->lm;
+  const int n8 = w.n8;
+  int t0, t1;
+  chunk_range(d, k, ck, &t0, &t1);
+  const long long r0 = (long long)t0 * d.Nbase, r1 = (long long)t1 * d.Nbase;
+  const double ndata = 8.0 * (double)(r1 - r0);
+  // hidden data d = r + f(p_old)
+  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 2, 1, nullptr, 1, t0, t1, nullptr);
+  if (r1 > r0) db_launch_scale_vis(w.wbuf, d.R, r0, r1, 1.0, 1, d.stream);  // wt = 1
+  db_count_launch(1);
+  double nu_t = *robust_nu;
+  int nu = 2;
+  LmOut o;
+  memset(&o, 0, sizeof(o));
+  for (int nw = 0; nw < wt_itmax; nw++) {
+    bool evaluated = false;
+    lm_core(pr, k, ck, t0, t1, pblk_dev, w.wbuf, itmax, defopts, linsolv, os, nw, randomize, false,
+            0.0, &nu, &evaluated, &o);
+    if (nw < wt_itmax - 1 && r1 > r0) {
+      // residual the new weights are computed from: at nw == 0 the reference's `ed` is the
+      // (unit-weight) residual of the LAST evaluated point, which is a rejected trial if the loop
+      // stopped right after one (clmfit.c:478); later rounds recompute it at p (robustlm.c:2538)
+      const double *pe = (nw == 0 && evaluated) ? w.plast : pblk_dev;
+      db_cluster_pass(pr, k, pe, w.dbuf, w.ebuf, 1, 1, nullptr, 2, t0, t1, nullptr);
+      db_launch_sum_abs(w.wbuf, d.R, r0, r1, pr->partials, d.scal + 3, d.counters, d.stream);
+      db_launch_update_weights(w.ebuf, w.wbuf, d.R, r0, r1, nu_t, pr->partials, d.scal + 4,
+                               d.counters, d.stream);
+      db_count_launch(2);
+      DB_CHECK(cudaMemcpyAsync(d.h_scal + 3, d.scal + 3, 2 * sizeof(double),
+                               cudaMemcpyDeviceToHost, d.stream));
+      DB_CHECK(cudaStreamSynchronize(d.stream));
+      const double lambda = d.h_scal[3];
+      const double sumq = d.h_scal[4] / ndata;
+      nu_t = pick_nu(sumq, nulow, nuhigh);
+      db_launch_scale_vis(w.wbuf, d.R, r0, r1, lambda / ndata, 0, d.stream);
+      db_count_launch(1);
+    }
+  }
+  *robust_nu = nu_t;
+  // residual of the chunk with the final Jones: r = d - f(p)
+  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr);
+  (void)n8;
+  fill_info(info, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,9 +634,33 @@ extern "C" double dirac_b200_normal_eq(dirac_b200_problem *pr, int clus, int chu
   chunk_range(d, clus, chunk, &t0, &t1);
   db_upload_vis(pr, xd, w.dbuf);
   DB_CHECK(cudaMemcpyAsync(w.pnew, pblk, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream));
-  db_cluster_pass(pr, clus, w.pnew, w.dbuf, nullptr, 1, 0, w.JTe, 1, t0, t1);
+  db_cluster_pass(pr, clus, w.pnew, w.dbuf, nullptr, 1, 0, w.JTe, 1, t0, t1, nullptr);
   gram(pr, clus, t0, t1, 1, w.Tsub);
   assemble(pr, w.Tsub, w.pnew, w.JTJ0);
+  double c = db_read_scalar(pr, 1);
+  if (JTe) DB_CHECK(cudaMemcpy(JTe, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (JTJ)
+    DB_CHECK(cudaMemcpy(JTJ, w.JTJ0, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
+  DB_CHECK(cudaGetLastError());
+  return c;
+}
+
+// same with sqrt-weights wt (8 per row, API layout, full interval): the robust LM's weighted system
+extern "C" double dirac_b200_normal_eq_weighted(dirac_b200_problem *pr, int clus, int chunk,
+                                                const double *pblk, const double *xd,
+                                                const double *wt, double *JTJ, double *JTe) {
+  DevProblem &d = pr->d;
+  db_lm_init(pr);
+  robust_init(pr);
+  LMWork &w = pr->lm;
+  const int n = w.n8;
+  int t0, t1;
+  chunk_range(d, clus, chunk, &t0, &t1);
+  db_upload_vis(pr, xd, w.dbuf);
+  db_upload_vis(pr, wt, w.wbuf);
+  DB_CHECK(cudaMemcpyAsync(w.pnew, pblk, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream));
+  db_cluster_pass(pr, clus, w.pnew, w.dbuf, nullptr, 1, 0, w.JTe, 1, t0, t1, w.wbuf);
+  weighted_jtj(pr, clus, t0, t1, w.pnew, w.wbuf, w.JTJ0);
   double c = db_read_scalar(pr, 1);
   if (JTe) DB_CHECK(cudaMemcpy(JTe, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost));
   if (JTJ)

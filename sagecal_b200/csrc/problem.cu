@@ -200,7 +200,7 @@ extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
   // --- scratch ---
   int nb1 = db_predict_nblocks(d.ntile, tilesz);
   int nb2 = db_cluster_pass_nblocks(d.ntile, tilesz, 1);
-  pr->npartials = (nb1 > nb2 ? nb1 : nb2) + 64;
+  pr->npartials = (nb1 > nb2 ? nb1 : nb2) + 1024;  // also covers the fixed-grid reductions
   pr->partials = dev_alloc<double>(pr->npartials);
   d.scal = dev_alloc<double>(64);
   DB_CHECK(cudaMallocHost((void **)&d.h_scal, 64 * sizeof(double)));

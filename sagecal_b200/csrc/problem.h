@@ -25,6 +25,11 @@ struct LMWork {
   cusolverDnHandle_t cs;
   cublasHandle_t cb;
   double2 *dbuf;          // [4][R] hidden data of the cluster being solved
+  // robust LM (allocated on first use)
+  double2 *wbuf;          // [4][R] sqrt-weights
+  double2 *ebuf;          // [4][R] unweighted residual for the weight update
+  double *HP, *HQ;        // [N][2][10] station sums of the weighted normal matrix
+  double *plast;          // [8N] device copy of the last evaluated trial point
 };
 
 struct dirac_b200_problem {

@@ -21,7 +21,7 @@ EXPORTED = [
     "dirac_b200_precalculate", "dirac_b200_get_coherencies", "dirac_b200_predict",
     "dirac_b200_grad", "dirac_b200_normal_eq", "dirac_b200_launch_count", "dirac_b200_sagefit",
     "dirac_b200_set_stream", "dirac_b200_profile_enable", "dirac_b200_profile_read",
-    "dirac_b200_kernel_count",
+    "dirac_b200_kernel_count", "dirac_b200_normal_eq_weighted",
 ]
 
 
@@ -53,6 +53,8 @@ class DiracB200(DiracAPI):
         L.dirac_b200_grad.argtypes = [vp, dp, dp, i, d]
         L.dirac_b200_normal_eq.restype = d
         L.dirac_b200_normal_eq.argtypes = [vp, i, i, dp, dp, dp, dp]
+        L.dirac_b200_normal_eq_weighted.restype = d
+        L.dirac_b200_normal_eq_weighted.argtypes = [vp, i, i, dp, dp, dp, dp, dp]
         L.dirac_b200_launch_count.restype = C.c_ulonglong
         L.dirac_b200_sagefit.restype = i
         L.dirac_b200_sagefit.argtypes = [vp, dp, dp, i, i, i, i, i, i, d, d, i, dp, dp, dp]
@@ -154,6 +156,15 @@ class DeviceProblem:
         pblk = np.ascontiguousarray(pblk, dtype=np.float64)
         c = self.api.lib.dirac_b200_normal_eq(self.h, clus, chunk, dptr(pblk), dptr(xd),
                                               dptr(JTJ.reshape(-1)), dptr(JTe))
+        return c, JTJ, JTe
+
+    def normal_eq_weighted(self, clus, chunk, pblk, xd, wt):
+        n8 = 8 * self.N
+        JTJ = np.zeros((n8, n8))
+        JTe = np.zeros(n8)
+        pblk = np.ascontiguousarray(pblk, dtype=np.float64)
+        c = self.api.lib.dirac_b200_normal_eq_weighted(self.h, clus, chunk, dptr(pblk), dptr(xd),
+                                                       dptr(wt), dptr(JTJ.reshape(-1)), dptr(JTe))
         return c, JTJ, JTe
 
 

@@ -85,6 +85,37 @@ def test_normal_equations(api, ref, bound):
                 assert np.array_equal(JTJ, JTJ.T)
 
 
+def test_weighted_normal_equations(api, ref, bound):
+    """robust LM system: J <- wt.J, e <- wt.e (robustlm.c:2298-2316) against the dense reference J"""
+    pr = bound.pr
+    pp = perturbed_jones(pr, seed=8)
+    rng = np.random.default_rng(4)
+    wt = rng.uniform(0.2, 1.3, pr.x.shape)
+    with blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, bound.barr, bound.sky, pr.coh, pr.x) as dp:
+        off = 0
+        for k in range(pr.M):
+            nch = pr.nchunk[k]
+            tilechunk = (pr.tilesz + nch - 1) // nch
+            for ck in range(nch):
+                t0 = min(ck * tilechunk, pr.tilesz)
+                t1 = min(t0 + tilechunk, pr.tilesz)
+                pblk = pp[off:off + 8 * pr.N].copy()
+                off += 8 * pr.N
+                if t1 <= t0:
+                    continue
+                md = ref.me_data(pr.N, pr.Nbase, t1 - t0, bound.barr, bound.sky, pr.coh, clus=k,
+                                 tileoff=t0)
+                nn = 8 * (t1 - t0) * pr.Nbase
+                sl = slice(8 * t0 * pr.Nbase, 8 * t1 * pr.Nbase)
+                J = ref.lm_jac(pblk, md, nn) * wt[sl][:, None]
+                e = wt[sl] * (pr.x[sl] - ref.lm_func(pblk, md, nn))
+                c, JTJ, JTe = dp.normal_eq_weighted(k, ck, pblk, pr.x, wt)
+                assert abs(c - e @ e) <= 1e-12 * (e @ e)
+                assert relerr(JTe, J.T @ e) < 1e-11
+                assert relerr(JTJ, J.T @ J) < 1e-11
+                assert relerr(JTJ, JTJ.T) < 1e-13
+
+
 def test_coherencies_device(api, ref):
     b = small_problem(N=12, M=4, tilesz=6, seed=21, kmean=2.0, gaussian_frac=0.5)
     pr = b.pr

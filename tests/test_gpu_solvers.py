@@ -33,6 +33,12 @@ SAGE_CASES = [
     ("lm-hybrid", dict(N=12, M=4, tilesz=10, seed=32, nchunk=[1, 2, 1, 5]),
      dict(solver_mode=1, max_iter=3)),
     ("oslm", dict(N=10, M=3, tilesz=20, seed=33, kmean=1.0), dict(solver_mode=0, max_iter=4)),
+    ("rlm", dict(N=8, M=2, tilesz=10, seed=34, outliers=0.02), dict(solver_mode=2, max_iter=3)),
+    ("osrlm", dict(N=8, M=2, tilesz=20, seed=35, outliers=0.02), dict(solver_mode=3, max_iter=3)),
+    # tile counts per chunk are multiples of the OS subset count: the reference's OS-LM pairs J rows
+    # and residual rows of different tiles otherwise (clmfit.c:1313-1356, DESIGN.md "flagged quirks")
+    ("rlm-multi", dict(N=13, M=4, tilesz=20, seed=37, kmean=1.0, outliers=0.02, nchunk=[1, 2, 1, 4]),
+     dict(solver_mode=2, max_iter=2)),
     ("lm-nolbfgs", dict(N=35, M=3, tilesz=6, seed=34), dict(solver_mode=1, max_iter=2,
                                                            max_lbfgs=0)),
 ]
@@ -45,6 +51,7 @@ def test_sagefit_matches_reference(api, ref, name, prob, args):
     kw.update(args)
     (rr, xr, ppr), (rg, xg, ppg) = run_both(api, ref, b, **kw)
     assert rr[0] == rg[0]
+    assert abs(rr[1] - rg[1]) < 1e-9                    # mean nu
     assert abs(rr[2] - rg[2]) <= 1e-10 * rr[2]          # res_0
     assert relerr(ppg, ppr) < JONES_TOL, (name, relerr(ppg, ppr))
     assert relerr(xg, xr) < 1e-5 * max(1.0, np.max(np.abs(b.pr.x)) / np.max(np.abs(xr)))

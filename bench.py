@@ -147,7 +147,9 @@ def cpu_reference_run(steps, warmup, seed):
     if not refdirac.available():
         return None, None, "oracle/_ref/libdirac_ref.so not built"
     ref = refdirac.load()
-    cores = os.cpu_count() or 1
+    # the reference spawns Nt pthreads per predict/Jacobian call AND lets OpenBLAS thread its dgemm;
+    # beyond ~32 threads each the sample only gets slower (oversubscription), so cap there
+    cores = min(os.cpu_count() or 1, 32)
     try:
         ref.lib.openblas_set_num_threads(cores)
     except AttributeError:
@@ -181,7 +183,7 @@ def run_reference_arm(args):
     steps = max(1, min(args.steps, 3))
     warm = 1 if args.warmup > 0 else 0
     v, sec, desc = cpu_reference_run(steps, warm, shape["seed"])
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)
     if v is None:
         print(json.dumps({"impl": "reference", "unavailable": desc}))
         return
@@ -284,7 +286,7 @@ def main():
         ms_total = e0.elapsed_time(e1)
         launches = api.launch_count() - l0
         ngrad = (api.kernel_count(1) - g0) / K
-        prof = {k: api.profile_read(k) for k in range(6)}
+        prof = {k: api.profile_read(k) for k in range(8)}
         api.profile_enable(False)
     sweeps = SOLVE["max_emiter"] + ngrad
     units_step = R * M * sweeps
@@ -332,9 +334,9 @@ def main():
     # ---------------- roofline of the dominant own kernel ----------------
     peak, peak_src = measured_peaks()
     names = ["k_predict_full", "k_grad_full", "k_cluster_pass", "k_coh_gram", "assemble",
-             "damped_solve(cusolver)"]
+             "damped_solve(cusolver)", "k_weighted_jtj", "k_line_setup"]
     shares = {}
-    for k in range(6):
+    for k in range(8):
         n, ms, by = prof[k]
         shares[names[k]] = {"launches_per_step": n / K, "ms_per_step": ms / K,
                             "share_of_step": (ms / K) / ms_step if ms_step else None,
@@ -352,10 +354,10 @@ def main():
     if not args.no_cpu_baseline:
         v, sec, desc = cpu_reference_run(1, 0, shape["seed"])
         if v is not None:
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+            cpu = {"value": v, "unit": UNIT, "cores": min(os.cpu_count() or 1, 32), "kind": "reference",
                    "sample": desc, "seconds_per_step": sec}
         else:
-            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+            cpu = {"value": None, "unit": UNIT, "cores": min(os.cpu_count() or 1, 32), "kind": "reference",
                    "sample": desc}
 
     line = {

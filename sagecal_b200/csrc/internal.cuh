@@ -237,6 +237,21 @@ struct WeightedJtjArgs {
   int t_begin, t_end, tslice;
 };
 
+// line model of the LBFGS line search: e(alpha) = E0 - alpha E1 - alpha^2 E2 (kernels_line.cu)
+struct LineSetupArgs {
+  const double2 *coh;        // [M][4][R]
+  const double2 *x;          // [4][R] data
+  const unsigned char *flag;
+  const double *xk;          // Jones at the line origin (device, 8*N*Mt)
+  const double *pk;          // search direction (device, 8*N*Mt)
+  const ClusterDesc *clus;
+  const int *chunk_poff;
+  const TileDesc *tiles;
+  double2 *E0, *E1, *E2;     // [4][R] each
+  long long R;
+  int N, Nbase, tilesz, M;
+};
+
 struct GramArgs {
   const double2 *coh;        // [M][4][R], cluster of blockIdx.y is k0 + blockIdx.y
   const unsigned char *flag;

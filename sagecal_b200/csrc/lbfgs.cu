@@ -3,11 +3,16 @@
 // The iteration logic restates lbfgs_fit_fullbatch (lbfgs.c:479-640), mult_hessian (:33-111),
 // linesearch (:298-430), linesearch_zoom (:211-290) and cubic_interp (:116-205): same constants,
 // same order of cost evaluations, same acceptance tests, because every comparison steers the
-// iterates and parity with the CPU reference is judged on the solved Jones.  The parameter vector
-// is small (8*N*Mt doubles); it lives on the host like in the reference, while every cost/gradient
-// evaluation is one or two streaming passes over the resident coherencies:
-//   cost  = k_predict_full (sum e^2 | sum log(1+e^2/nu))        replaces cost_func / robust_cost_func
-//   grad  = k_predict_full (residual) + k_grad_full             replaces func_grad(_robust)
+// iterates and parity with the CPU reference is judged on the solved Jones.
+//
+// What differs is the cost of a cost evaluation.  Every evaluation of the reference's line search
+// is at x_k + alpha p_k (the reference moves a scratch vector xp along p_k by axpy; we track the
+// same alpha with the same sequence of additions).  One pass over the coherencies per LBFGS
+// iteration (k_line_setup) leaves the line model e(alpha) = E0 - alpha E1 - alpha^2 E2 in HBM/L2;
+// each of the 10-30 cost evaluations of the iteration is then a 192 B/row reduction (k_line_eval)
+// instead of a full predict over all clusters, and the residual at the accepted step feeds the
+// gradient pass (k_grad_full) directly.  Per iteration: 2 passes over the coherencies instead of
+// ~30 (cost_func / robust_cost_func, robust_lbfgs.c:674-726; func_grad(_robust), :569-669,322-416).
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -15,27 +20,75 @@
 
 #include "problem.h"
 
+extern "C" {
+void db_launch_line_setup(const LineSetupArgs *a, int ntile, cudaStream_t st);
+void db_launch_line_eval(const double2 *E0, const double2 *E1, const double2 *E2, long long n4,
+                         double alpha, int mode, double inv_nu, double *partials, double *out,
+                         unsigned int *counter, cudaStream_t st);
+void db_launch_line_residual(const double2 *E0, const double2 *E1, const double2 *E2, double2 *res,
+                             long long n4, double alpha, cudaStream_t st);
+}
+
 struct LbfgsCtx {
   dirac_b200_problem *pr;
   int robust;
   double nu;
+  int m;
   long long ncost, ngrad;
 };
 
-static double cost_eval(LbfgsCtx *c, const double *p, int m) {
-  DevProblem &d = c->pr->d;
-  DB_CHECK(cudaMemcpyAsync(d.pp, p, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
-  db_predict_dev(c->pr, d.pp, nullptr, 0, c->robust ? 2 : 1, c->nu, 0);
-  c->ncost++;
-  return db_read_scalar(c->pr, 0);
+static void line_alloc(dirac_b200_problem *pr) {
+  if (pr->E0) return;
+  DevProblem &d = pr->d;
+  const size_t n = (size_t)4 * d.R;
+  DB_CHECK(cudaMalloc((void **)&pr->E0, sizeof(double2) * n));
+  DB_CHECK(cudaMalloc((void **)&pr->E1, sizeof(double2) * n));
+  DB_CHECK(cudaMalloc((void **)&pr->E2, sizeof(double2) * n));
+  DB_CHECK(cudaMalloc((void **)&pr->pk_dev, sizeof(double) * 8 * d.N * d.Mt));
 }
 
-static void grad_eval(LbfgsCtx *c, const double *p, double *g, int m) {
-  DevProblem &d = c->pr->d;
-  DB_CHECK(cudaMemcpyAsync(d.pp, p, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
-  db_predict_dev(c->pr, d.pp, c->pr->res, 1, 0, 0.0, 0);
-  db_grad_dev(c->pr, d.pp, c->pr->g, c->robust, c->nu);
-  DB_CHECK(cudaMemcpyAsync(g, c->pr->g, sizeof(double) * m, cudaMemcpyDeviceToHost, d.stream));
+// line model along pk from xk (both host vectors)
+static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
+  dirac_b200_problem *pr = c->pr;
+  DevProblem &d = pr->d;
+  line_alloc(pr);
+  DB_CHECK(cudaMemcpyAsync(d.pp, xk, sizeof(double) * c->m, cudaMemcpyHostToDevice, d.stream));
+  DB_CHECK(cudaMemcpyAsync(pr->pk_dev, pk, sizeof(double) * c->m, cudaMemcpyHostToDevice,
+                           d.stream));
+  LineSetupArgs a;
+  a.coh = d.coh; a.x = d.x; a.flag = d.flag; a.xk = d.pp; a.pk = pr->pk_dev; a.clus = d.clus;
+  a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.E0 = pr->E0; a.E1 = pr->E1; a.E2 = pr->E2;
+  a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.tilesz = d.tilesz; a.M = d.M;
+  db_prof_begin(7, (double)d.R * (64.0 * d.M + 65.0 + 192.0), d.stream);
+  db_launch_line_setup(&a, d.ntile, d.stream);
+  db_prof_end(d.stream);
+  db_count_launch(1);
+}
+
+// phi(alpha) = cost(xk + alpha pk)
+static double line_cost(LbfgsCtx *c, double alpha) {
+  dirac_b200_problem *pr = c->pr;
+  DevProblem &d = pr->d;
+  db_launch_line_eval(pr->E0, pr->E1, pr->E2, 4 * d.R, alpha, c->robust ? 2 : 1,
+                      c->robust ? 1.0 / c->nu : 0.0, pr->partials, d.scal, d.counters, d.stream);
+  db_count_launch(1);
+  c->ncost++;
+  return db_read_scalar(pr, 0);
+}
+
+// gradient at p (host); if from_line, the residual is taken from the line model at alpha
+static void grad_eval(LbfgsCtx *c, const double *p, double *g, bool from_line, double alpha) {
+  dirac_b200_problem *pr = c->pr;
+  DevProblem &d = pr->d;
+  DB_CHECK(cudaMemcpyAsync(d.pp, p, sizeof(double) * c->m, cudaMemcpyHostToDevice, d.stream));
+  if (from_line) {
+    db_launch_line_residual(pr->E0, pr->E1, pr->E2, pr->res, 4 * d.R, alpha, d.stream);
+    db_count_launch(1);
+  } else {
+    db_predict_dev(pr, d.pp, pr->res, 1, 0, 0.0, 0);
+  }
+  db_grad_dev(pr, d.pp, pr->g, c->robust, c->nu);
+  DB_CHECK(cudaMemcpyAsync(g, pr->g, sizeof(double) * c->m, cudaMemcpyDeviceToHost, d.stream));
   DB_CHECK(cudaStreamSynchronize(d.stream));
   c->ngrad++;
 }
@@ -79,23 +132,23 @@ static void mult_hessian(int m, double *pk, const double *gk, const double *s, c
   }
 }
 
-static double cubic_interp(LbfgsCtx *c, const double *xk, const double *pk, double a, double b,
-                           double *xp, int m, double step) {
+// In the three functions below `xa` is the position of the reference's scratch vector xp along
+// the line (xp = xk + xa*pk); every my_daxpy(m,pk,t,xp) of the reference is `xa += t` here.
+static double cubic_interp(LbfgsCtx *c, double a, double b, double *xa, double step) {
   double f0, f1, f0d, f1d, p01, p02, z0, fz0, aa, cc;
-  memcpy(xp, xk, sizeof(double) * m);
-  vaxpy(xp, pk, a, m);
-  f0 = cost_eval(c, xp, m);
-  vaxpy(xp, pk, step, m);
-  p01 = cost_eval(c, xp, m);
-  vaxpy(xp, pk, -2.0 * step, m);
-  p02 = cost_eval(c, xp, m);
+  *xa = a;
+  f0 = line_cost(c, *xa);
+  *xa += step;
+  p01 = line_cost(c, *xa);
+  *xa += -2.0 * step;
+  p02 = line_cost(c, *xa);
   f0d = (p01 - p02) / (2.0 * step);
-  vaxpy(xp, pk, -a + step + b, m);
-  f1 = cost_eval(c, xp, m);
-  vaxpy(xp, pk, step, m);
-  p01 = cost_eval(c, xp, m);
-  vaxpy(xp, pk, -2.0 * step, m);
-  p02 = cost_eval(c, xp, m);
+  *xa += -a + step + b;
+  f1 = line_cost(c, *xa);
+  *xa += step;
+  p01 = line_cost(c, *xa);
+  *xa += -2.0 * step;
+  p02 = line_cost(c, *xa);
   f1d = (p01 - p02) / (2.0 * step);
 
   aa = 3.0 * (f0 - f1) / (b - a) + (f1d - f0d);
@@ -108,8 +161,8 @@ static double cubic_interp(LbfgsCtx *c, const double *xk, const double *pk, doub
     if (z0 > aa || z0 < cc) {
       fz0 = f0 + f1;
     } else {
-      vaxpy(xp, pk, -b + step + a + z0 * (b - a), m);
-      fz0 = cost_eval(c, xp, m);
+      *xa += -b + step + a + z0 * (b - a);
+      fz0 = line_cost(c, *xa);
     }
     if (f0 < f1 && f0 < fz0) return a;
     if (f1 < fz0) return b;
@@ -118,28 +171,27 @@ static double cubic_interp(LbfgsCtx *c, const double *xk, const double *pk, doub
   return (f0 < f1) ? a : b;
 }
 
-static double linesearch_zoom(LbfgsCtx *c, const double *xk, const double *pk, double a, double b,
-                              double *xp, double phi_0, double gphi_0, double sigma, double rho,
-                              double t1, double t2, double t3, int m, double step) {
+static double linesearch_zoom(LbfgsCtx *c, double a, double b, double *xa, double phi_0,
+                              double gphi_0, double sigma, double rho, double t1, double t2,
+                              double t3, double step) {
   double alphaj = 0.0, phi_j, phi_aj, gphi_j, p01, p02, aj = a, bj = b, alphak = 1.0;
   int ci = 0, found_step = 0;
   (void)t1;
   while (ci < 10) {
     p01 = aj + t2 * (bj - aj);
     p02 = bj - t3 * (bj - aj);
-    alphaj = cubic_interp(c, xk, pk, p01, p02, xp, m, step);
-    memcpy(xp, xk, sizeof(double) * m);
-    vaxpy(xp, pk, alphaj, m);
-    phi_j = cost_eval(c, xp, m);
-    vaxpy(xp, pk, -alphaj + aj, m);
-    phi_aj = cost_eval(c, xp, m);
+    alphaj = cubic_interp(c, p01, p02, xa, step);
+    *xa = alphaj;
+    phi_j = line_cost(c, *xa);
+    *xa += -alphaj + aj;
+    phi_aj = line_cost(c, *xa);
     if ((phi_j > phi_0 + rho * alphaj * gphi_0) || phi_j >= phi_aj) {
       bj = alphaj;
     } else {
-      vaxpy(xp, pk, -aj + alphaj + step, m);
-      p01 = cost_eval(c, xp, m);
-      vaxpy(xp, pk, -2.0 * step, m);
-      p02 = cost_eval(c, xp, m);
+      *xa += -aj + alphaj + step;
+      p01 = line_cost(c, *xa);
+      *xa += -2.0 * step;
+      p02 = line_cost(c, *xa);
       gphi_j = (p01 - p02) / (2.0 * step);
       if ((aj - alphaj) * gphi_j <= step) {
         alphak = alphaj;
@@ -160,20 +212,18 @@ static double linesearch_zoom(LbfgsCtx *c, const double *xk, const double *pk, d
   return alphak;
 }
 
-static double linesearch(LbfgsCtx *c, const double *xk, const double *pk, double alpha1,
-                         double sigma, double rho, double t1, double t2, double t3, int m,
-                         double step) {
-  std::vector<double> xpv(m);
-  double *xp = xpv.data();
+static double linesearch(LbfgsCtx *c, double alpha1, double sigma, double rho, double t1,
+                         double t2, double t3, double step) {
+  double xa;
   double alphai, alphai1, phi_0, phi_alphai, phi_alphai1, p01, p02, gphi_0, gphi_i, alphak, mu, tol;
   alphak = 1.0;
-  phi_0 = cost_eval(c, xk, m);
+  phi_0 = line_cost(c, 0.0);
   tol = (0.01 * phi_0 < 1e-6) ? 0.01 * phi_0 : 1e-6;
-  memcpy(xp, xk, sizeof(double) * m);
-  vaxpy(xp, pk, step, m);
-  p01 = cost_eval(c, xp, m);
-  vaxpy(xp, pk, -2.0 * step, m);
-  p02 = cost_eval(c, xp, m);
+  xa = 0.0;
+  xa += step;
+  p01 = line_cost(c, xa);
+  xa += -2.0 * step;
+  p02 = line_cost(c, xa);
   gphi_0 = (p01 - p02) / (2.0 * step);
   mu = (tol - phi_0) / (rho * gphi_0);
   if (!isnormal(mu)) return mu;
@@ -182,30 +232,27 @@ static double linesearch(LbfgsCtx *c, const double *xk, const double *pk, double
   alphai1 = 0.0;
   phi_alphai1 = phi_0;
   while (ci < 10) {
-    memcpy(xp, xk, sizeof(double) * m);
-    vaxpy(xp, pk, alphai, m);
-    phi_alphai = cost_eval(c, xp, m);
+    xa = alphai;
+    phi_alphai = line_cost(c, xa);
     if (phi_alphai < tol) {
       alphak = alphai;
       break;
     }
     if ((phi_alphai > phi_0 + alphai * gphi_0) || (ci > 1 && phi_alphai >= phi_alphai1)) {
-      alphak = linesearch_zoom(c, xk, pk, alphai1, alphai, xp, phi_0, gphi_0, sigma, rho, t1, t2,
-                               t3, m, step);
+      alphak = linesearch_zoom(c, alphai1, alphai, &xa, phi_0, gphi_0, sigma, rho, t1, t2, t3, step);
       break;
     }
-    vaxpy(xp, pk, step, m);
-    p01 = cost_eval(c, xp, m);
-    vaxpy(xp, pk, -2.0 * step, m);
-    p02 = cost_eval(c, xp, m);
+    xa += step;
+    p01 = line_cost(c, xa);
+    xa += -2.0 * step;
+    p02 = line_cost(c, xa);
     gphi_i = (p01 - p02) / (2.0 * step);
     if (fabs(gphi_i) <= -sigma * gphi_0) {
       alphak = alphai;
       break;
     }
     if (gphi_i >= 0) {
-      alphak = linesearch_zoom(c, xk, pk, alphai, alphai1, xp, phi_0, gphi_0, sigma, rho, t1, t2,
-                               t3, m, step);
+      alphak = linesearch_zoom(c, alphai, alphai1, &xa, phi_0, gphi_0, sigma, rho, t1, t2, t3, step);
       break;
     }
     if (mu <= (2.0 * alphai - alphai1)) {
@@ -215,7 +262,7 @@ static double linesearch(LbfgsCtx *c, const double *xk, const double *pk, double
       p01 = 2.0 * alphai - alphai1;
       double hi = alphai + t1 * (alphai - alphai1);
       p02 = (mu < hi) ? mu : hi;
-      alphai = cubic_interp(c, xk, pk, p01, p02, xp, m, step);
+      alphai = cubic_interp(c, p01, p02, &xa, step);
     }
     phi_alphai1 = phi_alphai;
     ci++;
@@ -230,13 +277,14 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
   ctx.pr = pr;
   ctx.robust = robust;
   ctx.nu = nu;
+  ctx.m = m;
   ctx.ncost = ctx.ngrad = 0;
   if (M < 1) M = 1;
   std::vector<double> gk(m), xk1(m), xk(m), pk(m), s((size_t)m * M), y((size_t)m * M), rho(M);
   double step, alphak;
   int ck, ci, cm;
   memcpy(xk.data(), p, sizeof(double) * m);
-  grad_eval(&ctx, xk.data(), gk.data(), m);
+  grad_eval(&ctx, xk.data(), gk.data(), false, 0.0);
   double gradnrm = vnrm2(gk.data(), m);
   const double STOP = 1e-17;  // CLM_STOP_THRESH, Dirac_common.h:43
   if (gradnrm < STOP) {
@@ -253,7 +301,8 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
   while (ck < itmax && isnormal(gradnrm) && gradnrm > STOP) {
     mult_hessian(m, pk.data(), gk.data(), s.data(), y.data(), rho.data(), ck < M ? ck : M, ci);
     for (int i = 0; i < m; i++) pk[i] = -pk[i];
-    alphak = linesearch(&ctx, xk.data(), pk.data(), 10.0, 0.1, 0.01, 9, 0.1, 0.5, m, step);
+    line_setup(&ctx, xk.data(), pk.data());
+    alphak = linesearch(&ctx, 10.0, 0.1, 0.01, 9, 0.1, 0.5, step);
     if (!isnormal(alphak) || fabs(alphak) < 1e-12) break;  // CLM_EPSILON
     memcpy(xk1.data(), xk.data(), sizeof(double) * m);
     vaxpy(xk1.data(), pk.data(), alphak, m);
@@ -263,7 +312,7 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
       sk[i] = xk1[i] - xk[i];
       yk[i] = -gk[i];
     }
-    grad_eval(&ctx, xk1.data(), gk.data(), m);
+    grad_eval(&ctx, xk1.data(), gk.data(), true, alphak);
     gradnrm = vnrm2(gk.data(), m);
     vaxpy(yk, gk.data(), 1.0, m);
     rho[ci] = 1.0 / vdot(yk, sk, m);

@@ -220,6 +220,7 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   cudaFree(d.coh); cudaFree(d.x); cudaFree(d.flag); cudaFree(d.pp); cudaFree(d.clus);
   cudaFree(d.chunk_poff); cudaFree(d.tiles); cudaFree(d.scal); cudaFree(d.counters);
   cudaFree(pr->partials); cudaFree(pr->res); cudaFree(pr->g); cudaFree(pr->vis_stage);
+  if (pr->E0) { cudaFree(pr->E0); cudaFree(pr->E1); cudaFree(pr->E2); cudaFree(pr->pk_dev); }
   cudaFreeHost(d.h_scal);
   free(d.h_clus); free(d.h_chunk_poff);
   if (pr->own_stream) cudaStreamDestroy(d.stream);

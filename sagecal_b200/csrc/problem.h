@@ -41,6 +41,9 @@ struct dirac_b200_problem {
   double *g;              // [8*N*Mt]
   LMWork lm;
   int own_stream;
+  // LBFGS line model (allocated on first use)
+  double2 *E0, *E1, *E2;  // [4][R] each
+  double *pk_dev;         // [8*N*Mt] search direction
 };
 
 void db_count_launch(int n);

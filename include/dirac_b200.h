@@ -182,6 +182,24 @@ int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_out, int ma
                        double nulow, double nuhigh, int randomize, double *mean_nu, double *res_0,
                        double *res_1);
 
+/* ---- cluster sharding over the GPUs of one box (one process per GPU) --------------------------
+ * The reference splits clusters over GPUs with host pthreads and merges on the host
+ * (src/lib/Radio/predict_withbeam_cuda.c:713-794, src/lib/Dirac/lmfit_cuda.c:1801-1950).  Here a
+ * rank holds the coherencies of its own contiguous block of clusters only; carr_local[k].p[] are
+ * offsets into the GLOBAL Jones vector of npar_global doubles, which is replicated like the data.
+ * The host supplies the collective: `allreduce(dev, count, stream, user)` must sum `count` doubles
+ * at device address `dev` over all ranks, enqueued on `stream` (an NCCL all-reduce).  Every rank
+ * calls dirac_b200_sagefit with identical arguments and gets identical pp / residual back.
+ * beta: hidden-data weight of the residual during a sweep (SAGE); <= 0 selects 1/world, the
+ * generalisation of the reference's 0.5 for two concurrent clusters (lmfit_cuda.c:1832-1842). */
+dirac_b200_problem *dirac_b200_create_shard(int N, int Nbase, int tilesz, const baseline_t *barr,
+                                            const clus_source_t *carr_local, int M_local,
+                                            int Mt_local, long long npar_global, const double *coh,
+                                            const double *x);
+void dirac_b200_set_comm(dirac_b200_problem *pr, int rank, int world,
+                         void (*allreduce)(void *dev, long long count, void *stream, void *user),
+                         void *user, int m_global, int k_global0, double beta);
+
 /* run on a caller-supplied CUDA stream (cudaStream_t) instead of a private one; NULL restores the
  * default.  Affects problems created afterwards and the reference entry points. */
 void dirac_b200_set_stream(void *stream);

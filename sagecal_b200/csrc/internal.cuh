@@ -43,6 +43,7 @@ struct ClusterDesc {
 struct DevProblem {
   int N, Nbase, tilesz, M, Mt;
   long long R;             // Nbase*tilesz rows
+  long long npar;          // length of the Jones vector pp (8*N*Mt, or the global length of a shard)
   int device;
   // resident data
   double2 *coh;            // [M][4][R]
@@ -217,6 +218,8 @@ struct ClusterPassArgs {
              // 2: ADD   out = in + m          (no cost / jte)
              // 3: SUB   out = in - m          (no cost / jte)
   int write_out;
+  double beta;               // SAGE hidden-data weight: INIT d = beta*in + m ; SUB out = d - m + (1-beta)*in2
+  const double2 *in2;        // mode 3 with beta != 1: the residual the hidden data was formed from
   const double2 *wt;         // [4][R] sqrt-weights (re,im) of the robust LM, or null.  With
                              // weights: cost = ||wt.e||^2 and J^T e -> J^T (wt^2 . e); the vector
                              // written for mode 1 stays the UNWEIGHTED e
@@ -250,6 +253,7 @@ struct LineSetupArgs {
   double2 *E0, *E1, *E2;     // [4][R] each
   long long R;
   int N, Nbase, tilesz, M;
+  int partial;               // 1: write the raw sums V0,V1,V2 of the local clusters (sharded run)
 };
 
 struct GramArgs {

@@ -114,7 +114,11 @@ k_line_setup(LineSetupArgs a) {
         const long long ix = (long long)c * a.R + row[i];
         const double2 xv = ld_stream(a.x + ix);
         const double2 z = make_double2(0.0, 0.0);
-        st_stream(a.E0 + ix, fl ? xv : csub(xv, V0[i][c]));
+        if (a.partial) {
+          st_stream(a.E0 + ix, fl ? z : V0[i][c]);
+        } else {
+          st_stream(a.E0 + ix, fl ? xv : csub(xv, V0[i][c]));
+        }
         st_stream(a.E1 + ix, fl ? z : V1[i][c]);
         st_stream(a.E2 + ix, fl ? z : V2[i][c]);
       }
@@ -158,6 +162,39 @@ k_line_residual(const double2 *__restrict__ E0, const double2 *__restrict__ E1,
   }
 }
 
+// sharded runs: out = x - pm (pm = all-reduced partial models); cost like k_predict_full
+__global__ void __launch_bounds__(256)
+k_residual_cost(const double2 *__restrict__ x, const double2 *__restrict__ pm,
+                double2 *__restrict__ out, long long n4, int out_mode, int cost_mode, double inv_nu,
+                double *partials, double *cost, unsigned int *counter) {
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double2 xv = x[i], m = pm[i];
+    const double2 e = make_double2(xv.x - m.x, xv.y - m.y);
+    if (out_mode == 1) out[i] = e;
+    if (out_mode == 2) out[i] = m;
+    if (cost_mode == 1) {
+      s = fma(e.x, e.x, s);
+      s = fma(e.y, e.y, s);
+    } else if (cost_mode == 2) {
+      s += log(1.0 + e.x * e.x * inv_nu);
+      s += log(1.0 + e.y * e.y * inv_nu);
+    }
+  }
+  if (cost_mode) grid_reduce_sum_l(s, partials, cost, counter);
+}
+
+// y = a*x + b*y elementwise over n4 double2
+__global__ void __launch_bounds__(256)
+k_axpby(const double2 *__restrict__ x, double2 *__restrict__ y, long long n4, double a, double b) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double2 xv = x[i], yv = y[i];
+    y[i] = make_double2(a * xv.x + b * yv.x, a * xv.y + b * yv.y);
+  }
+}
+
 extern "C" {
 #define LINE_TB 2
 void db_launch_line_setup(const LineSetupArgs *a, int ntile, cudaStream_t st) {
@@ -170,6 +207,16 @@ void db_launch_line_eval(const double2 *E0, const double2 *E1, const double2 *E2
                          unsigned int *counter, cudaStream_t st) {
   k_line_eval<<<LINE_GRID, 256, 0, st>>>(E0, E1, E2, n4, alpha, mode, inv_nu, partials, out,
                                          counter);
+}
+void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, long long n4,
+                             int out_mode, int cost_mode, double inv_nu, double *partials,
+                             double *cost, unsigned int *counter, cudaStream_t st) {
+  k_residual_cost<<<592, 256, 0, st>>>(x, pm, out, n4, out_mode, cost_mode, inv_nu, partials, cost,
+                                       counter);
+}
+void db_launch_axpby(const double2 *x, double2 *y, long long n4, double a, double b,
+                     cudaStream_t st) {
+  k_axpby<<<592, 256, 0, st>>>(x, y, n4, a, b);
 }
 void db_launch_line_residual(const double2 *E0, const double2 *E1, const double2 *E2, double2 *res,
                              long long n4, double alpha, cudaStream_t st) {

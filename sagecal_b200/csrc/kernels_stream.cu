@@ -408,18 +408,26 @@ k_cluster_pass(ClusterPassArgs a) {
       if (a.mode == 0) {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-          double2 d = cadd(v[c], m[c]);
+          double2 d = cadd(make_double2(a.beta * v[c].x, a.beta * v[c].y), m[c]);
           if (a.write_out) st_stream(a.out + (long long)c * a.R + row, d);
           e[c] = csub(d, m[c]);
         }
       } else if (a.mode == 2) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) st_stream(a.out + (long long)c * a.R + row, cadd(v[c], m[c]));
+        for (int c = 0; c < 4; c++)
+          st_stream(a.out + (long long)c * a.R + row,
+                    cadd(make_double2(a.beta * v[c].x, a.beta * v[c].y), m[c]));
       } else {
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           e[c] = csub(v[c], m[c]);
-          if (a.write_out) st_stream(a.out + (long long)c * a.R + row, e[c]);
+          double2 o = e[c];
+          if (a.mode == 3 && a.in2) {
+            const double2 r2 = a.in2[(long long)c * a.R + row];  // may alias out: plain load
+            o.x = fma(1.0 - a.beta, r2.x, o.x);
+            o.y = fma(1.0 - a.beta, r2.y, o.y);
+          }
+          if (a.write_out) st_stream(a.out + (long long)c * a.R + row, o);
         }
       }
       if (a.mode <= 1) {

@@ -44,7 +44,7 @@ static void line_alloc(dirac_b200_problem *pr) {
   DB_CHECK(cudaMalloc((void **)&pr->E0, sizeof(double2) * n));
   DB_CHECK(cudaMalloc((void **)&pr->E1, sizeof(double2) * n));
   DB_CHECK(cudaMalloc((void **)&pr->E2, sizeof(double2) * n));
-  DB_CHECK(cudaMalloc((void **)&pr->pk_dev, sizeof(double) * 8 * d.N * d.Mt));
+  DB_CHECK(cudaMalloc((void **)&pr->pk_dev, sizeof(double) * d.npar));
 }
 
 // line model along pk from xk (both host vectors)
@@ -59,10 +59,19 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
   a.coh = d.coh; a.x = d.x; a.flag = d.flag; a.xk = d.pp; a.pk = pr->pk_dev; a.clus = d.clus;
   a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.E0 = pr->E0; a.E1 = pr->E1; a.E2 = pr->E2;
   a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.tilesz = d.tilesz; a.M = d.M;
+  a.partial = (pr->world > 1) ? 1 : 0;
   db_prof_begin(7, (double)d.R * (64.0 * d.M + 65.0 + 192.0), d.stream);
   db_launch_line_setup(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
   db_count_launch(1);
+  if (pr->world > 1) {
+    // sum the model polynomials of all ranks, then E0 = x - V0
+    db_allreduce(pr, pr->E0, 8 * d.R);
+    db_allreduce(pr, pr->E1, 8 * d.R);
+    db_allreduce(pr, pr->E2, 8 * d.R);
+    db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);
+    db_count_launch(1);
+  }
 }
 
 // phi(alpha) = cost(xk + alpha pk)

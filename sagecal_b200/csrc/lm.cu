@@ -132,10 +132,14 @@ static int pick_tslice(const DevProblem &d, int nt) {
   return ts;
 }
 
+void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
+                     double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
+                     int t1, const double2 *wt, double beta = 1.0, const double2 *in2 = nullptr);
+
 // one streaming pass of cluster k over timeslots [t0,t1): see ClusterPassArgs for the modes
 void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
                      double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
-                     int t1, const double2 *wt) {
+                     int t1, const double2 *wt, double beta, const double2 *in2) {
   DevProblem &d = pr->d;
   if (t1 <= t0) {
     if (mode <= 1) DB_CHECK(cudaMemsetAsync(d.scal + cost_slot, 0, sizeof(double), d.stream));
@@ -147,7 +151,7 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   a.in = in; a.flag = d.flag; a.pblk = pblk_dev; a.tiles = d.tiles; a.out = out; a.jte = jte_dev;
   a.partials = pr->partials; a.cost = d.scal + cost_slot; a.counter = d.counters; a.R = d.R;
   a.N = d.N; a.Nbase = d.Nbase; a.t_begin = t0; a.t_end = t1; a.tslice = pick_tslice(d, t1 - t0);
-  a.mode = mode; a.write_out = write_out; a.wt = wt;
+  a.mode = mode; a.write_out = write_out; a.wt = wt; a.beta = beta; a.in2 = in2;
   if (jte_dev && mode <= 1)
     DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
   db_prof_begin(2, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
@@ -517,15 +521,19 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
   chunk_range(d, k, ck, &t0, &t1);
   // hidden data d = r + f(p_old); e = d - f(p_old); ||e||^2; J^T e  (lmfit.c:890-891 fused with
   // the first func/jacf evaluation, clmfit.c:241-252)
-  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 1, t0, t1, nullptr);
+  // (sharded runs weight the residual share of the hidden data with beta, SAGE: d = f + beta r)
+  const double beta = pr->world > 1 ? pr->beta : 1.0;
+  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 1, t0, t1, nullptr, beta);
   const double c0 = db_read_scalar(pr, 1);
   int nu = 2;
   bool ev;
   LmOut o;
   lm_core(pr, k, ck, t0, t1, pblk_dev, nullptr, itmax, opts ? opts : defopts, linsolv, os, 0,
           randomize, true, c0, &nu, &ev, &o);
-  // residual of the chunk with the final Jones: r = d - f(p)   (lmfit.c:980-981)
-  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr);
+  // residual of the chunk with the final Jones: r = d - f(p) (+ (1-beta) r when sharded)
+  // (lmfit.c:980-981)
+  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr, beta,
+                  beta != 1.0 ? r : nullptr);
   fill_info(info, o);
 }
 
@@ -581,8 +589,9 @@ void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, doubl
   chunk_range(d, k, ck, &t0, &t1);
   const long long r0 = (long long)t0 * d.Nbase, r1 = (long long)t1 * d.Nbase;
   const double ndata = 8.0 * (double)(r1 - r0);
-  // hidden data d = r + f(p_old)
-  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 2, 1, nullptr, 1, t0, t1, nullptr);
+  // hidden data d = beta r + f(p_old)
+  const double beta = pr->world > 1 ? pr->beta : 1.0;
+  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 2, 1, nullptr, 1, t0, t1, nullptr, beta);
   if (r1 > r0) db_launch_scale_vis(w.wbuf, d.R, r0, r1, 1.0, 1, d.stream);  // wt = 1
   db_count_launch(1);
   double nu_t = *robust_nu;
@@ -614,8 +623,9 @@ void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, doubl
     }
   }
   *robust_nu = nu_t;
-  // residual of the chunk with the final Jones: r = d - f(p)
-  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr);
+  // residual of the chunk with the final Jones: r = d - f(p) (+ (1-beta) r when sharded)
+  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr, beta,
+                  beta != 1.0 ? r : nullptr);
   (void)n8;
   fill_info(info, o);
 }

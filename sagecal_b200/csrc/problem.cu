@@ -104,10 +104,48 @@ static void build_tiles(int N, std::vector<TileDesc> &tiles) {
     }
 }
 
+static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const baseline_t *barr,
+                                       const clus_source_t *carr, int M, int Mt, const double *coh,
+                                       const double *x, long long npar);
+
 extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
                                                  const baseline_t *barr, const clus_source_t *carr,
                                                  int M, int Mt, const double *coh,
                                                  const double *x) {
+  return create_impl(N, Nbase, tilesz, barr, carr, M, Mt, coh, x, (long long)8 * N * Mt);
+}
+
+// One rank's shard of a cluster-sharded solve: carr/coh hold only the local clusters, whose
+// carr[k].p[] are offsets into the GLOBAL Jones vector of npar doubles.
+extern "C" dirac_b200_problem *dirac_b200_create_shard(int N, int Nbase, int tilesz,
+                                                       const baseline_t *barr,
+                                                       const clus_source_t *carr_local,
+                                                       int M_local, int Mt_local,
+                                                       long long npar_global, const double *coh,
+                                                       const double *x) {
+  return create_impl(N, Nbase, tilesz, barr, carr_local, M_local, Mt_local, coh, x, npar_global);
+}
+
+extern "C" void dirac_b200_set_comm(dirac_b200_problem *pr, int rank, int world,
+                                    void (*allreduce)(void *, long long, void *, void *),
+                                    void *user, int m_global, int k_global0, double beta) {
+  pr->rank = rank;
+  pr->world = world;
+  pr->allreduce = allreduce;
+  pr->comm_user = user;
+  pr->m_global = m_global;
+  pr->k_global0 = k_global0;
+  pr->beta = (beta > 0.0) ? beta : 1.0 / (double)(world > 0 ? world : 1);
+}
+
+// sum a device buffer of doubles over the ranks (no-op for a single rank)
+void db_allreduce(dirac_b200_problem *pr, void *dev, long long count) {
+  if (pr->world > 1) pr->allreduce(dev, count, (void *)pr->d.stream, pr->comm_user);
+}
+
+static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const baseline_t *barr,
+                                       const clus_source_t *carr, int M, int Mt, const double *coh,
+                                       const double *x, long long npar) {
   require_gpu();
   if (Nbase != N * (N - 1) / 2) {
     fprintf(stderr, "dirac_b200: Nbase=%d is not N(N-1)/2 for N=%d; only the canonical baseline "
@@ -123,6 +161,9 @@ extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
   DevProblem &d = pr->d;
   d.N = N; d.Nbase = Nbase; d.tilesz = tilesz; d.M = M; d.Mt = Mt;
   d.R = (long long)Nbase * tilesz;
+  d.npar = npar;
+  pr->rank = 0; pr->world = 1; pr->allreduce = nullptr; pr->comm_user = nullptr;
+  pr->m_global = M; pr->k_global0 = 0; pr->beta = 1.0;
   DB_CHECK(cudaGetDevice(&d.device));
   d.stream = db_new_stream(&pr->own_stream);
   const long long R = d.R;
@@ -175,7 +216,7 @@ extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
                       cudaMemcpyHostToDevice));
 
   // --- Jones, data, coherencies ---
-  d.pp = dev_alloc<double>((size_t)8 * N * Mt);
+  d.pp = dev_alloc<double>((size_t)d.npar);
   d.x = dev_alloc<double2>((size_t)4 * R);
   d.coh = dev_alloc<double2>((size_t)M * 4 * R);
   pr->vis_stage = dev_alloc<double2>((size_t)4 * R);
@@ -207,7 +248,7 @@ extern "C" dirac_b200_problem *dirac_b200_create(int N, int Nbase, int tilesz,
   d.counters = dev_alloc<unsigned int>(16);
   DB_CHECK(cudaMemset(d.counters, 0, 16 * sizeof(unsigned int)));
   pr->res = dev_alloc<double2>((size_t)4 * R);
-  pr->g = dev_alloc<double>((size_t)8 * N * Mt);
+  pr->g = dev_alloc<double>((size_t)d.npar);
   DB_CHECK(cudaGetLastError());
   return pr;
 }
@@ -220,6 +261,7 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   cudaFree(d.coh); cudaFree(d.x); cudaFree(d.flag); cudaFree(d.pp); cudaFree(d.clus);
   cudaFree(d.chunk_poff); cudaFree(d.tiles); cudaFree(d.scal); cudaFree(d.counters);
   cudaFree(pr->partials); cudaFree(pr->res); cudaFree(pr->g); cudaFree(pr->vis_stage);
+  if (pr->pm) cudaFree(pr->pm);
   if (pr->E0) { cudaFree(pr->E0); cudaFree(pr->E1); cudaFree(pr->E2); cudaFree(pr->pk_dev); }
   cudaFreeHost(d.h_scal);
   free(d.h_clus); free(d.h_chunk_poff);
@@ -279,6 +321,20 @@ void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, 
   a.cost = d.scal + slot; a.counter = d.counters; a.R = d.R; a.N = d.N; a.Nbase = d.Nbase;
   a.tilesz = d.tilesz; a.M = d.M; a.out_mode = out_mode; a.cost_mode = cost_mode;
   a.inv_nu = (nu > 0.0) ? 1.0 / nu : 0.0;
+  if (pr->world > 1) {
+    // cluster-sharded: partial model of the local clusters, summed over the ranks, then residual
+    // and cost from the sum (identical on every rank)
+    if (!pr->pm) pr->pm = dev_alloc<double2>((size_t)4 * d.R);
+    a.out = pr->pm; a.out_mode = 2; a.cost_mode = 0;
+    db_prof_begin(0, (double)d.R * (64.0 * d.M + 65.0 + 64.0), d.stream);
+    db_launch_predict_full(&a, d.ntile, d.stream);
+    db_prof_end(d.stream);
+    db_allreduce(pr, pr->pm, 8 * d.R);
+    db_launch_residual_cost(d.x, pr->pm, out, 4 * d.R, out ? out_mode : 0, cost_mode, a.inv_nu,
+                            pr->partials, d.scal + slot, d.counters, d.stream);
+    db_count_launch(2);
+    return;
+  }
   db_prof_begin(0, (double)d.R * (64.0 * d.M + 65.0 + (out_mode ? 64.0 : 0.0)), d.stream);
   db_launch_predict_full(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
@@ -297,7 +353,7 @@ double db_read_scalar(dirac_b200_problem *pr, int slot) {
 void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, int robust,
                  double nu) {
   DevProblem &d = pr->d;
-  DB_CHECK(cudaMemsetAsync(g_dev, 0, sizeof(double) * 8 * d.N * d.Mt, d.stream));
+  DB_CHECK(cudaMemsetAsync(g_dev, 0, sizeof(double) * d.npar, d.stream));
   GradArgs a;
   a.coh = d.coh; a.res = pr->res; a.flag = d.flag; a.pp = pp_dev; a.clus = d.clus;
   a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.g = g_dev; a.R = d.R; a.N = d.N;
@@ -309,6 +365,8 @@ void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, in
   db_launch_grad_full(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
   db_count_launch(1);
+  // sharded: every rank filled the blocks of its own clusters; the sum is the full gradient
+  db_allreduce(pr, g_dev, d.npar);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -317,7 +375,7 @@ void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, in
 extern "C" double dirac_b200_predict(dirac_b200_problem *pr, const double *pp, double *out,
                                      int out_mode, int cost_mode, double nu) {
   DevProblem &d = pr->d;
-  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * 8 * d.N * d.Mt, cudaMemcpyHostToDevice,
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * d.npar, cudaMemcpyHostToDevice,
                            d.stream));
   if (!out) out_mode = 0;
   db_predict_dev(pr, d.pp, pr->res, out_mode, cost_mode, nu, 0);
@@ -332,11 +390,11 @@ extern "C" double dirac_b200_predict(dirac_b200_problem *pr, const double *pp, d
 extern "C" void dirac_b200_grad(dirac_b200_problem *pr, const double *pp, double *g, int robust,
                                 double nu) {
   DevProblem &d = pr->d;
-  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * 8 * d.N * d.Mt, cudaMemcpyHostToDevice,
+  DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * d.npar, cudaMemcpyHostToDevice,
                            d.stream));
   db_predict_dev(pr, d.pp, pr->res, 1, 0, 0.0, 0);  // residual e = x - V
   db_grad_dev(pr, d.pp, pr->g, robust, nu);
-  DB_CHECK(cudaMemcpyAsync(g, pr->g, sizeof(double) * 8 * d.N * d.Mt, cudaMemcpyDeviceToHost,
+  DB_CHECK(cudaMemcpyAsync(g, pr->g, sizeof(double) * d.npar, cudaMemcpyDeviceToHost,
                            d.stream));
   DB_CHECK(cudaStreamSynchronize(d.stream));
   DB_CHECK(cudaGetLastError());

@@ -41,6 +41,15 @@ struct dirac_b200_problem {
   double *g;              // [8*N*Mt]
   LMWork lm;
   int own_stream;
+  // cluster sharding over ranks: sum of a device buffer of doubles over all ranks (NCCL all-reduce,
+  // supplied by the host); world == 1: never called
+  int rank, world;
+  void (*allreduce)(void *dev, long long count, void *stream, void *user);
+  void *comm_user;
+  int m_global;           // clusters over all ranks
+  int k_global0;          // global index of local cluster 0
+  double beta;            // hidden-data weight of the sharded SAGE sweep (1/world by default)
+  double2 *pm;            // [4][R] partial model / residual-delta staging
   // LBFGS line model (allocated on first use)
   double2 *E0, *E1, *E2;  // [4][R] each
   double *pk_dev;         // [8*N*Mt] search direction
@@ -58,4 +67,12 @@ double db_read_scalar(dirac_b200_problem *pr, int slot);
 void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, int robust,
                  double nu);
 void db_lm_init(dirac_b200_problem *pr);
+void db_allreduce(dirac_b200_problem *pr, void *dev, long long count);
+extern "C" {
+void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, long long n4,
+                             int out_mode, int cost_mode, double inv_nu, double *partials,
+                             double *cost, unsigned int *counter, cudaStream_t st);
+void db_launch_axpby(const double2 *x, double2 *y, long long n4, double a, double b,
+                     cudaStream_t st);
+}
 void db_lm_free(dirac_b200_problem *pr);

@@ -42,15 +42,33 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
   }
   DevProblem &d = pr->d;
   const int N = d.N, M = d.M, Mt = d.Mt;
-  const int m = N * Mt * 8;
+  const int m = (int)pr->d.npar;
   const long long n = (long long)d.Nbase * d.tilesz * 8;
   const ClusterDesc *hc = d.h_clus;
   // CPU-path LM thresholds (lmfit.c:801)
   double opts[5] = {1e-3, 1e-15, 1e-15, 1e-20, -1e-6};
   double info[10];
   double robust_nu0 = nulow;
-  std::vector<double> nerr(M, 0.0), robust_nuM(M, 0.0);
+  // cluster-sharded run: M local clusters, global cluster index k0 + cj; per-cluster
+  // bookkeeping vectors are global and summed over the ranks after every sweep
+  const bool sharded = pr->world > 1;
+  const int MG = sharded ? pr->m_global : M;
+  const int k0 = sharded ? pr->k_global0 : 0;
+  std::vector<double> nerr(MG, 0.0), robust_nuM(MG, 0.0), pp_start, hsum;
   const bool robust = is_robust_mode(solver_mode);
+  if (sharded) {
+    db_lm_init(pr);
+    if (!pr->pm) DB_CHECK(cudaMalloc((void **)&pr->pm, sizeof(double2) * 4 * d.R));
+    pp_start.resize(m);
+    hsum.resize(m > MG ? m : MG);
+  }
+  // sum a small host vector over the ranks through the device scratch pr->g
+  auto allreduce_host = [&](double *v, int cnt) {
+    DB_CHECK(cudaMemcpyAsync(pr->g, v, sizeof(double) * cnt, cudaMemcpyHostToDevice, d.stream));
+    db_allreduce(pr, pr->g, cnt);
+    DB_CHECK(cudaMemcpyAsync(v, pr->g, sizeof(double) * cnt, cudaMemcpyDeviceToHost, d.stream));
+    DB_CHECK(cudaStreamSynchronize(d.stream));
+  };
 
   DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
   // residual of the current model: r = x - sum_k model_k, res_0 = ||r|| / n   (lmfit.c:866-869)
@@ -59,13 +77,25 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
   *res_0 = sqrt(db_read_scalar(pr, 0)) / (double)n;
 
   int weighted_iter = 0;
-  const int total_iter = M * max_iter;
-  const int iter_bar = (int)ceil((0.80 / (double)M) * ((double)total_iter));
+  const int total_iter = MG * max_iter;
+  const int iter_bar = (int)ceil((0.80 / (double)MG) * ((double)total_iter));
   for (int ci = 0; ci < max_emiter; ci++) {
-    for (int cj = 0; cj < M; cj++) {
+    if (sharded) {
+      // remember the state every rank starts the sweep from
+      DB_CHECK(cudaMemcpyAsync(pr->pm, r, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice,
+                               d.stream));
+      DB_CHECK(cudaMemcpyAsync(pp_start.data(), d.pp, sizeof(double) * m, cudaMemcpyDeviceToHost,
+                               d.stream));
+      DB_CHECK(cudaStreamSynchronize(d.stream));
+      for (int g = 0; g < MG; g++)
+        if (g < k0 || g >= k0 + M) nerr[g] = 0.0;  // other ranks' entries come back by the sum
+    }
+    for (int cl = 0; cl < M; cl++) {
+      const int cj = cl;          // local cluster index (device tables)
+      const int cg = k0 + cl;     // global cluster index (bookkeeping)
       int this_itermax;
       if (weighted_iter) {
-        this_itermax = (int)((0.20 * nerr[cj]) * ((double)total_iter)) + iter_bar;
+        this_itermax = (int)((0.20 * nerr[cg]) * ((double)total_iter)) + iter_bar;
       } else {
         this_itermax = max_iter;
       }
@@ -84,7 +114,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
               double nu = robust_nu0;
               db_rlm_chunk(pr, cj, ck, pblk, r, this_itermax, linsolv, 0, randomize, nulow, nuhigh,
                            &nu, info);
-              robust_nuM[cj] += nu;
+              robust_nuM[cg] += nu;
             } else {
               db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info);
             }
@@ -93,7 +123,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
               double nu = robust_nu0;
               db_rlm_chunk(pr, cj, ck, pblk, r, this_itermax, linsolv, 1, randomize, nulow, nuhigh,
                            &nu, info);
-              robust_nuM[cj] += nu;
+              robust_nuM[cg] += nu;
             } else {
               db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info);
             }
@@ -102,24 +132,47 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
           final_res += info[1];
         }
         if (init_res > 0.0) {
-          nerr[cj] = (init_res - final_res) / init_res;
-          if (nerr[cj] < 0.0) nerr[cj] = 0.0;
+          nerr[cg] = (init_res - final_res) / init_res;
+          if (nerr[cg] < 0.0) nerr[cg] = 0.0;
         } else {
-          nerr[cj] = 0.0;
+          nerr[cg] = 0.0;
         }
-        if (robust && ci == max_emiter - 1) robust_nuM[cj] /= (double)hc[cj].nchunk;
+        if (robust && ci == max_emiter - 1) robust_nuM[cg] /= (double)hc[cj].nchunk;
       }
     }
+    if (sharded) {
+      // ONE all-reduce of the residual delta per sweep: r <- r_start + sum_ranks (r_local - r_start)
+      LMWork &w = pr->lm;
+      DB_CHECK(cudaMemcpyAsync(w.dbuf, r, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice,
+                               d.stream));
+      db_launch_axpby(pr->pm, w.dbuf, 4 * d.R, -1.0, 1.0, d.stream);   // dbuf = r - r_start
+      db_allreduce(pr, w.dbuf, 8 * d.R);
+      DB_CHECK(cudaMemcpyAsync(r, pr->pm, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice,
+                               d.stream));
+      db_launch_axpby(w.dbuf, r, 4 * d.R, 1.0, 1.0, d.stream);         // r = r_start + sum delta
+      // Jones: every rank changed only its own clusters' blocks
+      DB_CHECK(cudaMemcpyAsync(hsum.data(), d.pp, sizeof(double) * m, cudaMemcpyDeviceToHost,
+                               d.stream));
+      DB_CHECK(cudaStreamSynchronize(d.stream));
+      for (int i = 0; i < m; i++) hsum[i] -= pp_start[i];
+      allreduce_host(hsum.data(), m);
+      for (int i = 0; i < m; i++) hsum[i] += pp_start[i];
+      DB_CHECK(cudaMemcpyAsync(d.pp, hsum.data(), sizeof(double) * m, cudaMemcpyHostToDevice,
+                               d.stream));
+      DB_CHECK(cudaStreamSynchronize(d.stream));
+      allreduce_host(nerr.data(), MG);
+    }
     double total_err = 0.0;
-    for (int cj = 0; cj < M; cj++) total_err += fabs(nerr[cj]);
+    for (int cj = 0; cj < MG; cj++) total_err += fabs(nerr[cj]);
     if (total_err > 0.0)
-      for (int cj = 0; cj < M; cj++) nerr[cj] *= 1.0 / total_err;
+      for (int cj = 0; cj < MG; cj++) nerr[cj] *= 1.0 / total_err;
     if (randomize) weighted_iter = !weighted_iter;
   }
   if (robust) {
+    if (sharded) allreduce_host(robust_nuM.data(), MG);
     double s = 0.0;
-    for (int cj = 0; cj < M; cj++) s += fabs(robust_nuM[cj]);
-    robust_nu0 = s / (double)M;
+    for (int cj = 0; cj < MG; cj++) s += fabs(robust_nuM[cj]);
+    robust_nu0 = s / (double)MG;
     if (robust_nu0 < nulow) robust_nu0 = nulow;
     else if (robust_nu0 > nuhigh) robust_nu0 = nuhigh;
   }

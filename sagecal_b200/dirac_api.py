@@ -80,12 +80,14 @@ def cptr(a: np.ndarray):
 class SkyModel:
     """Owns the numpy buffers behind an array of clus_source_t."""
 
-    def __init__(self, clusters, N, keep_alive=None):
-        """clusters: list of dict(ll,mm,nn,sI,sQ,sU,sV[,stype,nchunk,f0,spec_idx...,gauss])."""
+    def __init__(self, clusters, N, keep_alive=None, p_base=0):
+        """clusters: list of dict(ll,mm,nn,sI,sQ,sU,sV[,stype,nchunk,f0,spec_idx...,gauss]).
+        p_base: offset of the first cluster's Jones block in the parameter vector (a shard of a
+        larger sky model keeps the global offsets)."""
         self.M = len(clusters)
         self.arr = (clus_source_t * self.M)()
         self._keep = []
-        off = 0
+        off = int(p_base)
         self.nchunk = []
         for k, cl in enumerate(clusters):
             K = len(cl["ll"])
@@ -133,7 +135,7 @@ class SkyModel:
                 self._keep.append(a)
                 setattr(cs, name, dptr(a))
         self.Mt = sum(self.nchunk)
-        self.nparam = off
+        self.nparam = off - int(p_base)
 
 
 def make_barr(sta1, sta2, flag):

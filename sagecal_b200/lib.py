@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-from .dirac_api import DiracAPI, SkyModel, baseline_t, clus_source_t, c_double_p, dptr, cptr
+from .dirac_api import DiracAPI, SkyModel, baseline_t, clus_source_t, c_double_p, dptr, cptr  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdirac_b200.so")
@@ -21,7 +21,8 @@ EXPORTED = [
     "dirac_b200_precalculate", "dirac_b200_get_coherencies", "dirac_b200_predict",
     "dirac_b200_grad", "dirac_b200_normal_eq", "dirac_b200_launch_count", "dirac_b200_sagefit",
     "dirac_b200_set_stream", "dirac_b200_profile_enable", "dirac_b200_profile_read",
-    "dirac_b200_kernel_count", "dirac_b200_normal_eq_weighted",
+    "dirac_b200_kernel_count", "dirac_b200_normal_eq_weighted", "dirac_b200_create_shard",
+    "dirac_b200_set_comm",
 ]
 
 

@@ -22,7 +22,8 @@ def product():
 def test_header_symbols_exported(product):
     hdr = open(os.path.join(ROOT, "include", "dirac_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b([a-z_0-9]+)\s*\(", hdr)) - {"defined", "extern"}
+    ctypes_ = {"void", "int", "double", "long", "char", "unsigned", "defined", "extern"}
+    declared = set(re.findall(r"\b([a-z_0-9]+)\s*\(", hdr)) - ctypes_
     declared = {d for d in declared if not d.startswith("__")}
     assert declared, "no declarations parsed"
     for sym in sorted(declared):

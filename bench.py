@@ -231,6 +231,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there otherwise
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api = blib.load()
     stream = torch.cuda.Stream()

@@ -108,19 +108,66 @@ __device__ __forceinline__ void cfmacl(double2 &acc, double2 a, double2 b) {  //
   acc.y = fma(-a.y, b.x, acc.y);
 }
 
+// The 2x2 products below are written as explicit FMA chains: 8 fp64 instructions per complex
+// output (2 DMUL + 6 DFMA, or 8 DFMA when accumulating) instead of the 10-12 that separate complex
+// multiplies and adds compile to.  The fp64 pipe (64 lanes/clk/SM) is the second bound of every
+// streaming kernel here, right behind HBM.
+// a0*b0 + a1*b1
+__device__ __forceinline__ double2 cdot2(double2 a0, double2 b0, double2 a1, double2 b1) {
+  double re = a0.x * b0.x;
+  re = fma(-a0.y, b0.y, re);
+  re = fma(a1.x, b1.x, re);
+  re = fma(-a1.y, b1.y, re);
+  double im = a0.x * b0.y;
+  im = fma(a0.y, b0.x, im);
+  im = fma(a1.x, b1.y, im);
+  im = fma(a1.y, b1.x, im);
+  return make_double2(re, im);
+}
+// a0*conj(b0) + a1*conj(b1)
+__device__ __forceinline__ double2 cdot2c(double2 a0, double2 b0, double2 a1, double2 b1) {
+  double re = a0.x * b0.x;
+  re = fma(a0.y, b0.y, re);
+  re = fma(a1.x, b1.x, re);
+  re = fma(a1.y, b1.y, re);
+  double im = a0.y * b0.x;
+  im = fma(-a0.x, b0.y, im);
+  im = fma(a1.y, b1.x, im);
+  im = fma(-a1.x, b1.y, im);
+  return make_double2(re, im);
+}
+// acc += a0*conj(b0) + a1*conj(b1)
+__device__ __forceinline__ void cdot2c_acc(double2 &acc, double2 a0, double2 b0, double2 a1,
+                                           double2 b1) {
+  acc.x = fma(a0.x, b0.x, acc.x);
+  acc.x = fma(a0.y, b0.y, acc.x);
+  acc.x = fma(a1.x, b1.x, acc.x);
+  acc.x = fma(a1.y, b1.y, acc.x);
+  acc.y = fma(a0.y, b0.x, acc.y);
+  acc.y = fma(-a0.x, b0.y, acc.y);
+  acc.y = fma(a1.y, b1.x, acc.y);
+  acc.y = fma(-a1.x, b1.y, acc.y);
+}
 // C = A*B          (lmfit.c:37-42 "amb")
 __device__ __forceinline__ void mat_ab(const double2 *a, const double2 *b, double2 *c) {
-  c[0] = cadd(cmul(a[0], b[0]), cmul(a[1], b[2]));
-  c[1] = cadd(cmul(a[0], b[1]), cmul(a[1], b[3]));
-  c[2] = cadd(cmul(a[2], b[0]), cmul(a[3], b[2]));
-  c[3] = cadd(cmul(a[2], b[1]), cmul(a[3], b[3]));
+  c[0] = cdot2(a[0], b[0], a[1], b[2]);
+  c[1] = cdot2(a[0], b[1], a[1], b[3]);
+  c[2] = cdot2(a[2], b[0], a[3], b[2]);
+  c[3] = cdot2(a[2], b[1], a[3], b[3]);
 }
 // C = A*B^H        (lmfit.c:50-58 "ambt")
 __device__ __forceinline__ void mat_abh(const double2 *a, const double2 *b, double2 *c) {
-  c[0] = cadd(cmulc(a[0], b[0]), cmulc(a[1], b[1]));
-  c[1] = cadd(cmulc(a[0], b[2]), cmulc(a[1], b[3]));
-  c[2] = cadd(cmulc(a[2], b[0]), cmulc(a[3], b[1]));
-  c[3] = cadd(cmulc(a[2], b[2]), cmulc(a[3], b[3]));
+  c[0] = cdot2c(a[0], b[0], a[1], b[1]);
+  c[1] = cdot2c(a[0], b[2], a[1], b[3]);
+  c[2] = cdot2c(a[2], b[0], a[3], b[1]);
+  c[3] = cdot2c(a[2], b[2], a[3], b[3]);
+}
+// C += A*B^H
+__device__ __forceinline__ void mat_abh_acc(const double2 *a, const double2 *b, double2 *c) {
+  cdot2c_acc(c[0], a[0], b[0], a[1], b[1]);
+  cdot2c_acc(c[1], a[0], b[2], a[1], b[3]);
+  cdot2c_acc(c[2], a[2], b[0], a[3], b[1]);
+  cdot2c_acc(c[3], a[2], b[2], a[3], b[3]);
 }
 // C = A^H*B
 __device__ __forceinline__ void mat_ahb(const double2 *a, const double2 *b, double2 *c) {
@@ -272,6 +319,19 @@ struct AssembleArgs {
   const double *pblk;    // 8N Jones
   double *JTJ;           // [8N][8N]
   double *Hst;           // [N][4] station sums (H00, H11, Re H01, Im H01), zeroed by the caller
+  const TileDesc *tiles;
+  int N, Nbase;
+};
+
+// all (eligible) clusters of a sweep at once: matrix y of the batch belongs to local cluster list[y]
+struct BatchAssembleArgs {
+  const double *T;       // Gram tensors [Mt][Nbase][16]
+  const double *pp;      // device Jones vector
+  const int *list;       // [nb] local cluster indices
+  const int *tix;        // [M] Gram slot of cluster k (first chunk)
+  const int *poff;       // [M] offset of cluster k's (first) block in pp
+  double *JTJ;           // [nb][8N][8N]
+  double *Hst;           // [nb][N][4], zeroed by the caller
   const TileDesc *tiles;
   int N, Nbase;
 };

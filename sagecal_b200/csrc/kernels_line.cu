@@ -88,21 +88,13 @@ k_line_setup(LineSetupArgs a) {
         load_jones(a.pk + off, q, Dq);
         cur = px;
       }
-      double2 A[4], B[4], T[4];
+      double2 A[4], B[4];
       mat_ab(Jp, C, A);
       mat_ab(Dp, C, B);
-      mat_abh(A, Jq, T);
-#pragma unroll
-      for (int c = 0; c < 4; c++) V0[i][c] = cadd(V0[i][c], T[c]);
-      mat_abh(B, Jq, T);
-#pragma unroll
-      for (int c = 0; c < 4; c++) V1[i][c] = cadd(V1[i][c], T[c]);
-      mat_abh(A, Dq, T);
-#pragma unroll
-      for (int c = 0; c < 4; c++) V1[i][c] = cadd(V1[i][c], T[c]);
-      mat_abh(B, Dq, T);
-#pragma unroll
-      for (int c = 0; c < 4; c++) V2[i][c] = cadd(V2[i][c], T[c]);
+      mat_abh_acc(A, Jq, V0[i]);
+      mat_abh_acc(B, Jq, V1[i]);
+      mat_abh_acc(A, Dq, V1[i]);
+      mat_abh_acc(B, Dq, V2[i]);
     }
   }
 #pragma unroll

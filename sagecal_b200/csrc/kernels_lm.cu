@@ -27,9 +27,7 @@ struct Gram {
 };
 
 
-__global__ void __launch_bounds__(TILE_THREADS)
-k_assemble_offdiag(AssembleArgs a) {
-  const TileDesc td = a.tiles[blockIdx.x];
+__device__ __forceinline__ void assemble_tile(const AssembleArgs &a, const TileDesc td) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = td.pb * TILE_P + w;
   const int q = td.qb * TILE_Q + lane;
@@ -107,10 +105,44 @@ k_assemble_offdiag(AssembleArgs a) {
   atomicAdd(a.Hst + 4 * q + 3, Hq[1].y);
 }
 
+__global__ void __launch_bounds__(TILE_THREADS)
+k_assemble_offdiag(AssembleArgs a) {
+  assemble_tile(a, a.tiles[blockIdx.x]);
+}
+
+// batched over clusters (blockIdx.y): all normal matrices of a SAGE sweep in one launch
+__global__ void __launch_bounds__(TILE_THREADS)
+k_assemble_offdiag_batched(BatchAssembleArgs b) {
+  const int k = b.list[blockIdx.y];
+  AssembleArgs a;
+  a.T = b.T + (long long)b.tix[k] * b.Nbase * 16;
+  a.pblk = b.pp + b.poff[k];
+  a.JTJ = b.JTJ + (long long)blockIdx.y * 64 * b.N * b.N;
+  a.Hst = b.Hst + (long long)blockIdx.y * 4 * b.N;
+  a.tiles = b.tiles;
+  a.N = b.N;
+  a.Nbase = b.Nbase;
+  assemble_tile(a, b.tiles[blockIdx.x]);
+}
+
+__device__ __forceinline__ void assemble_diag_station(const double *__restrict__ Hst,
+                                                      double *__restrict__ JTJ, int N, int s);
+
 // diagonal 8x8 blocks from the station sums; one thread per (station, 4x4 sub-block i)
 __global__ void k_assemble_diag(const double *__restrict__ Hst, double *__restrict__ JTJ, int N) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N) return;
+  assemble_diag_station(Hst, JTJ, N, s);
+}
+__global__ void k_assemble_diag_batched(const double *__restrict__ Hst, double *__restrict__ JTJ,
+                                        int N) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  assemble_diag_station(Hst + (long long)blockIdx.y * 4 * N, JTJ + (long long)blockIdx.y * 64 * N * N,
+                        N, s);
+}
+__device__ __forceinline__ void assemble_diag_station(const double *__restrict__ Hst,
+                                                      double *__restrict__ JTJ, int N, int s) {
   const double h00 = Hst[4 * s], h11 = Hst[4 * s + 1], hr = Hst[4 * s + 2], hi = Hst[4 * s + 3];
   const int ld = 8 * N;
   for (int i = 0; i < 2; i++) {
@@ -122,6 +154,44 @@ __global__ void k_assemble_diag(const double *__restrict__ Hst, double *__restri
         if ((r >> 2) == i && (c >> 2) == i) v = blk[r & 3][c & 3];
         if ((r >> 2) == i) JTJ[(long long)(8 * s + r) * ld + 8 * s + c] = v;
       }
+  }
+}
+
+// per matrix of the batch: mu0 = tau * max_i (J^T J)_ii (clmfit.c:342-352) -> mu[y]; the diagonal is
+// (h00 x4, h11 x4) per station, so the maximum runs over the station sums
+__global__ void __launch_bounds__(128)
+k_batch_mu0(const double *__restrict__ Hst, double *__restrict__ mu, int N, double tau) {
+  __shared__ double sv[4];
+  const double *H = Hst + (long long)blockIdx.x * 4 * N;
+  double mx = 0.0;
+  for (int s = threadIdx.x; s < N; s += blockDim.x) {
+    const double a = H[4 * s], b = H[4 * s + 1];
+    if (fabs(a) > fabs(mx)) mx = a;
+    if (fabs(b) > fabs(mx)) mx = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_xor_sync(0xffffffffu, mx, o);
+    if (fabs(other) > fabs(mx)) mx = other;
+  }
+  if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 4; i++)
+      if (fabs(sv[i]) > fabs(mx)) mx = sv[i];
+    mu[blockIdx.x] = tau * mx;
+  }
+}
+
+// A[y] = A0[y] + mu[y] I over a batch of n x n matrices
+__global__ void k_batch_add_diag(const double *__restrict__ A0, double *__restrict__ A,
+                                 const double *__restrict__ mu, int n) {
+  const long long nn = (long long)n * n;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nn) {
+    double v = A0[(long long)blockIdx.y * nn + i];
+    if (i / n == i % n) v += mu[blockIdx.y];
+    A[(long long)blockIdx.y * nn + i] = v;
   }
 }
 
@@ -142,13 +212,59 @@ __global__ void k_extract_diag(const double *__restrict__ A, double *__restrict_
   if (i < n) dst[i] = A[(long long)i * n + i];
 }
 
+// pnew = p + dp ; sc[0] = |dp|^2 ; sc[1] = dp . J^T e   (clmfit.c:440-449,487-497), one CTA
+__global__ void __launch_bounds__(512)
+k_lm_step(const double *__restrict__ p, const double *__restrict__ Dp,
+          const double *__restrict__ jte, double *__restrict__ pnew, double *__restrict__ sc, int n) {
+  __shared__ double s0[16], s1[16];
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double dp = Dp[i];
+    pnew[i] = p[i] + dp;
+    a = fma(dp, dp, a);
+    b = fma(dp, jte[i], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    s0[threadIdx.x >> 5] = a;
+    s1[threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) {
+      ta += s0[i];
+      tb += s1[i];
+    }
+    sc[0] = ta;
+    sc[1] = tb;
+  }
+}
+
 extern "C" {
+void db_launch_lm_step(const double *p, const double *Dp, const double *jte, double *pnew,
+                       double *sc, int n, cudaStream_t st) {
+  k_lm_step<<<1, 512, 0, st>>>(p, Dp, jte, pnew, sc, n);
+}
 void db_launch_extract_diag(const double *A, double *dst, int n, cudaStream_t st) {
   k_extract_diag<<<(n + 127) / 128, 128, 0, st>>>(A, dst, n);
 }
 void db_launch_assemble(const AssembleArgs *a, int ntile, cudaStream_t st) {
   k_assemble_offdiag<<<ntile, TILE_THREADS, 0, st>>>(*a);
   k_assemble_diag<<<(a->N + 63) / 64, 64, 0, st>>>(a->Hst, a->JTJ, a->N);
+}
+void db_launch_assemble_batched(const BatchAssembleArgs *b, int ntile, int nb, double tau,
+                                double *mu, double *Afac, cudaStream_t st) {
+  dim3 g1(ntile, nb);
+  k_assemble_offdiag_batched<<<g1, TILE_THREADS, 0, st>>>(*b);
+  dim3 g2((b->N + 63) / 64, nb);
+  k_assemble_diag_batched<<<g2, 64, 0, st>>>(b->Hst, b->JTJ, b->N);
+  k_batch_mu0<<<nb, 128, 0, st>>>(b->Hst, mu, b->N, tau);
+  const int n = 8 * b->N;
+  const long long nn = (long long)n * n;
+  dim3 g3((unsigned)((nn + 255) / 256), nb);
+  k_batch_add_diag<<<g3, 256, 0, st>>>(b->JTJ, Afac, mu, n);
 }
 void db_launch_copy_add_diag(const double *A0, double *A, int n, double mu, cudaStream_t st) {
   long long nn = (long long)n * n;

@@ -171,11 +171,9 @@ k_predict_full(PredictArgs a) {
           load_jones(pblk, q, Jq);
           cur = px;
         }
-        double2 T1[4], T2[4];
+        double2 T1[4];
         mat_ab(Jp, C, T1);
-        mat_abh(T1, Jq, T2);
-#pragma unroll
-        for (int c = 0; c < 4; c++) acc[i][c] = cadd(acc[i][c], T2[c]);
+        mat_abh_acc(T1, Jq, acc[i]);
       }
     }
 #pragma unroll

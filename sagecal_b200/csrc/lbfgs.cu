@@ -41,10 +41,10 @@ static void line_alloc(dirac_b200_problem *pr) {
   if (pr->E0) return;
   DevProblem &d = pr->d;
   const size_t n = (size_t)4 * d.R;
-  DB_CHECK(cudaMalloc((void **)&pr->E0, sizeof(double2) * n));
-  DB_CHECK(cudaMalloc((void **)&pr->E1, sizeof(double2) * n));
-  DB_CHECK(cudaMalloc((void **)&pr->E2, sizeof(double2) * n));
-  DB_CHECK(cudaMalloc((void **)&pr->pk_dev, sizeof(double) * d.npar));
+  pr->E0 = (decltype(pr->E0))db_malloc(sizeof(double2) * n);
+  pr->E1 = (decltype(pr->E1))db_malloc(sizeof(double2) * n);
+  pr->E2 = (decltype(pr->E2))db_malloc(sizeof(double2) * n);
+  pr->pk_dev = (decltype(pr->pk_dev))db_malloc(sizeof(double) * d.npar);
 }
 
 // line model along pk from xk (both host vectors)

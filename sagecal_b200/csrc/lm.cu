@@ -12,6 +12,7 @@
 #include <float.h>
 #include <math.h>
 #include <string.h>
+#include <vector>
 
 #include "../../include/dirac_b200.h"
 #include "problem.h"
@@ -43,13 +44,15 @@ void db_launch_update_weights(const double2 *e, double2 *wt, long long R, long l
 void db_launch_scale_vis(double2 *v, long long R, long long r0, long long r1, double alpha,
                          int set_const, cudaStream_t st);
 void db_launch_extract_diag(const double *A, double *dst, int n, cudaStream_t st);
+void db_launch_assemble_batched(const BatchAssembleArgs *b, int ntile, int nb, double tau,
+                                double *mu, double *Afac, cudaStream_t st);
+void db_launch_lm_step(const double *p, const double *Dp, const double *jte, double *pnew,
+                       double *sc, int n, cudaStream_t st);
 }
 
 template <typename T>
 static T *dalloc(size_t n) {
-  T *p = nullptr;
-  DB_CHECK(cudaMalloc((void **)&p, n * sizeof(T) + 16));
-  return p;
+  return (T *)db_malloc(n * sizeof(T) + 16);
 }
 
 void db_lm_init(dirac_b200_problem *pr) {
@@ -74,10 +77,22 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.svdS = w.svdU = w.svdVT = nullptr;
   w.wbuf = w.ebuf = nullptr;
   w.HP = w.HQ = nullptr;
-  DB_CHECK(cudaMallocHost((void **)&w.h_vec, sizeof(double) * (5 * n8 + 4 * d.N + 32)));
-  CS_CHECK(cusolverDnCreate(&w.cs));
+  w.JB = w.LB = nullptr;
+  w.pref_slot = (int *)malloc(sizeof(int) * d.M);
+  for (int k = 0; k < d.M; k++) w.pref_slot[k] = -1;
+  w.jtj0_cur = nullptr;
+  DB_CHECK(cudaMallocHost((void **)&w.h_vec, sizeof(double) * (5 * n8 + 4 * d.N + 64)));
+  // library handles are process-wide (creating them costs tens of ms; the drop-in entry points
+  // build and tear down a problem per call)
+  static cusolverDnHandle_t g_cs = nullptr;
+  static cublasHandle_t g_cb = nullptr;
+  if (!g_cs) {
+    CS_CHECK(cusolverDnCreate(&g_cs));
+    CB_CHECK(cublasCreate(&g_cb));
+  }
+  w.cs = g_cs;
+  w.cb = g_cb;
   CS_CHECK(cusolverDnSetStream(w.cs, d.stream));
-  CB_CHECK(cublasCreate(&w.cb));
   CB_CHECK(cublasSetStream(w.cb, d.stream));
   int l1 = 0, l2 = 0, l3 = 0;
   CS_CHECK(cusolverDnDpotrf_bufferSize(w.cs, CUBLAS_FILL_MODE_LOWER, n8, w.JTJ, n8, &l1));
@@ -107,22 +122,28 @@ static void robust_init(dirac_b200_problem *pr) {
 void db_lm_free(dirac_b200_problem *pr) {
   LMWork &w = pr->lm;
   if (!w.ready) return;
-  cudaFree(w.T); cudaFree(w.Tsub); cudaFree(w.JTJ0); cudaFree(w.JTJ); cudaFree(w.JTe);
-  cudaFree(w.JTe_new); cudaFree(w.Hst); cudaFree(w.Dp); cudaFree(w.pnew); cudaFree(w.plast);
-  cudaFree(w.devinfo); cudaFree(w.tau); cudaFree(w.cswork); cudaFree(w.dbuf);
-  if (w.svdS) { cudaFree(w.svdS); cudaFree(w.svdU); cudaFree(w.svdVT); }
-  if (w.wbuf) { cudaFree(w.wbuf); cudaFree(w.ebuf); cudaFree(w.HP); cudaFree(w.HQ); }
+  db_free(w.T); db_free(w.Tsub); db_free(w.JTJ0); db_free(w.JTJ); db_free(w.JTe);
+  db_free(w.JTe_new); db_free(w.Hst); db_free(w.Dp); db_free(w.pnew); db_free(w.plast);
+  db_free(w.devinfo); db_free(w.tau); db_free(w.cswork); db_free(w.dbuf);
+  if (w.svdS) { db_free(w.svdS); db_free(w.svdU); db_free(w.svdVT); }
+  if (w.wbuf) { db_free(w.wbuf); db_free(w.ebuf); db_free(w.HP); db_free(w.HQ); }
+  if (w.JB) {
+    db_free(w.JB); db_free(w.LB); db_free(w.HB); db_free(w.mu_dev); db_free(w.binfo_dev);
+    db_free(w.LBptr_dev); db_free(w.blist_dev); db_free(w.btix_dev); db_free(w.bpoff_dev);
+    cudaFreeHost(w.h_mu); cudaFreeHost(w.h_binfo);
+  }
+  free(w.pref_slot);
   cudaFreeHost(w.h_vec);
   free(w.T_valid);
-  cusolverDnDestroy(w.cs);
-  cublasDestroy(w.cb);
   w.ready = false;
 }
 
 // timeslots per CTA slice of a per-cluster pass: enough slices to fill the GPU, long enough to
 // amortise the per-slice station reduction
+static int g_tslice_override = 0;  // tuning hook (dirac_b200_bench_cluster_pass)
 static int pick_tslice(const DevProblem &d, int nt) {
-  int target_ctas = 148 * 2;
+  if (g_tslice_override > 0) return g_tslice_override < nt ? g_tslice_override : nt;
+  int target_ctas = 148;  // one wave: these kernels run 1 CTA per SM (register bound)
   int slices = (target_ctas + d.ntile - 1) / d.ntile;
   if (slices < 1) slices = 1;
   int ts = (nt + slices - 1) / slices;
@@ -226,11 +247,13 @@ static void chunk_range(const DevProblem &d, int k, int ck, int *t0, int *t1) {
 // linsolv: 0 Cholesky (dpotrf/dpotrs, clmfit.c:373-395), 1 QR (dgels, :396-409),
 //          2 SVD with singular-value cut at eps1 (:410-436)
 // ------------------------------------------------------------------------------------------------
-static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double eps1) {
+// enqueues the factorisation and the solve; the status lands in w.devinfo[0..1] (read by the caller
+// together with the trial results).  The SVD variant finishes on the host and returns solved.
+static int enqueue_solve(dirac_b200_problem *pr, double mu, int linsolv, double eps1) {
   DevProblem &d = pr->d;
   LMWork &w = pr->lm;
   const int n = w.n8;
-  db_launch_copy_add_diag(w.JTJ0, w.JTJ, n, mu, d.stream);
+  db_launch_copy_add_diag(w.jtj0_cur ? w.jtj0_cur : w.JTJ0, w.JTJ, n, mu, d.stream);
   db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice, d.stream));
   int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
@@ -242,7 +265,6 @@ static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double e
     CS_CHECK(cusolverDnDpotrs(w.cs, CUBLAS_FILL_MODE_LOWER, n, 1, w.JTJ, n, w.Dp, n,
                               w.devinfo + 1));
     db_count_launch(2);
-    DB_CHECK(cudaMemcpyAsync(hinfo, w.devinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
   } else if (linsolv == 1) {
     // A = QR ; dp = R^-1 Q^T b   (A symmetric: row/column-major views coincide)
     CS_CHECK(cusolverDnDgeqrf(w.cs, n, n, w.JTJ, n, w.tau, w.cswork, w.lwork, w.devinfo));
@@ -252,7 +274,6 @@ static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double e
     CB_CHECK(cublasDtrsm(w.cb, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N,
                          CUBLAS_DIAG_NON_UNIT, n, 1, &one, w.JTJ, n, w.Dp, n));
     db_count_launch(3);
-    DB_CHECK(cudaMemcpyAsync(hinfo, w.devinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, d.stream));
   } else {
     if (!w.svdS) {
       w.svdS = dalloc<double>(n);
@@ -283,17 +304,85 @@ static int damped_solve(dirac_b200_problem *pr, double mu, int linsolv, double e
     return 1;
   }
   db_prof_end(d.stream);
-  // the step itself comes back with the status
-  DB_CHECK(cudaMemcpyAsync(w.h_vec + 2 * n, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost,
-                           d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
-  return (hinfo[0] == 0 && hinfo[1] == 0) ? 1 : 0;
+  (void)hinfo;
+  return 1;
 }
 
 static double nrm2sq(const double *v, int n) {
   double s = 0.0;
   for (int i = 0; i < n; i++) s += v[i] * v[i];
   return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Before a SAGE sweep of plain LM: J^T J of every (single-chunk) cluster at its current Jones, mu0 =
+// tau max diag, and the Cholesky factor of J^T J + mu0 I — assembled and factorised as ONE batch
+// (cusolverDnDpotrfBatched runs the M factorisations concurrently: ~15 us per 496x496 matrix against
+// ~200 us one at a time).  A cluster's Jones only change during its own visit, so the factor is
+// still exact when the visit starts; its first LM solve is then two triangular solves.
+// ------------------------------------------------------------------------------------------------
+void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
+  DevProblem &d = pr->d;
+  db_lm_init(pr);
+  LMWork &w = pr->lm;
+  const int n = w.n8;
+  const size_t nn = (size_t)n * n;
+  if ((double)d.M * nn * 16.0 > 24e9) return;  // keep the two batch buffers within 24 GB
+  if (!w.JB) {
+    w.JB = dalloc<double>(nn * d.M);
+    w.LB = dalloc<double>(nn * d.M);
+    w.HB = dalloc<double>((size_t)4 * d.N * d.M);
+    w.mu_dev = dalloc<double>(d.M);
+    w.binfo_dev = dalloc<int>(d.M);
+    w.LBptr_dev = (double **)dalloc<double *>(d.M);
+    w.blist_dev = dalloc<int>(d.M);
+    w.btix_dev = dalloc<int>(d.M);
+    w.bpoff_dev = dalloc<int>(d.M);
+    DB_CHECK(cudaMallocHost((void **)&w.h_mu, sizeof(double) * d.M));
+    DB_CHECK(cudaMallocHost((void **)&w.h_binfo, sizeof(int) * d.M));
+    std::vector<int> tix(d.M), poff(d.M);
+    std::vector<double *> ptr(d.M);
+    for (int k = 0; k < d.M; k++) {
+      tix[k] = d.h_clus[k].chunk0;
+      poff[k] = d.h_chunk_poff[d.h_clus[k].chunk0];
+      ptr[k] = w.LB + nn * k;
+    }
+    DB_CHECK(cudaMemcpy(w.btix_dev, tix.data(), sizeof(int) * d.M, cudaMemcpyHostToDevice));
+    DB_CHECK(cudaMemcpy(w.bpoff_dev, poff.data(), sizeof(int) * d.M, cudaMemcpyHostToDevice));
+    DB_CHECK(cudaMemcpy(w.LBptr_dev, ptr.data(), sizeof(double *) * d.M, cudaMemcpyHostToDevice));
+  }
+  std::vector<int> list;
+  for (int k = 0; k < d.M; k++) {
+    w.pref_slot[k] = -1;
+    if (d.h_clus[k].nchunk != 1) continue;
+    const int tix = d.h_clus[k].chunk0;
+    if (!w.T_valid[tix]) {
+      gram(pr, k, 0, d.tilesz, 1, w.T + (size_t)tix * d.Nbase * 16);
+      w.T_valid[tix] = 1;
+    }
+    w.pref_slot[k] = (int)list.size();
+    list.push_back(k);
+  }
+  const int nb = (int)list.size();
+  if (nb == 0) return;
+  DB_CHECK(cudaMemcpyAsync(w.blist_dev, list.data(), sizeof(int) * nb, cudaMemcpyHostToDevice,
+                           d.stream));
+  DB_CHECK(cudaMemsetAsync(w.HB, 0, sizeof(double) * 4 * d.N * nb, d.stream));
+  BatchAssembleArgs b;
+  b.T = w.T; b.pp = d.pp; b.list = w.blist_dev; b.tix = w.btix_dev; b.poff = w.bpoff_dev;
+  b.JTJ = w.JB; b.Hst = w.HB; b.tiles = d.tiles; b.N = d.N; b.Nbase = d.Nbase;
+  db_prof_begin(4, nb * (128.0 * d.Nbase + 8.0 * 64.0 * d.N * d.N), d.stream);
+  db_launch_assemble_batched(&b, d.ntile, nb, tau, w.mu_dev, w.LB, d.stream);
+  db_prof_end(d.stream);
+  db_count_launch(4);
+  db_prof_begin(5, 0.0, d.stream);
+  CS_CHECK(cusolverDnDpotrfBatched(w.cs, CUBLAS_FILL_MODE_LOWER, n, w.LBptr_dev, n, w.binfo_dev, nb));
+  db_prof_end(d.stream);
+  db_count_launch(1);
+  DB_CHECK(cudaMemcpyAsync(w.h_mu, w.mu_dev, sizeof(double) * nb, cudaMemcpyDeviceToHost, d.stream));
+  DB_CHECK(cudaMemcpyAsync(w.h_binfo, w.binfo_dev, sizeof(int) * nb, cudaMemcpyDeviceToHost,
+                           d.stream));
+  DB_CHECK(cudaStreamSynchronize(d.stream));  // list goes out of scope; mu0 is needed on the host
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -361,6 +450,11 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
     w.T_valid[tix] = 1;
   }
 
+  // Host/device handshake: ONE synchronisation per trial.  Everything between two decisions —
+  // damping, factorisation, solve, p + dp, trial pass (cost and, speculatively, J^T e at the trial
+  // point) — is enqueued back to back; the scalars the decision needs come back together.
+  double *hsc = w.h_vec + 4 * n + 4 * d.N + 8;  // [n: diag][4: |dp|^2, dp.jte, cost, -]
+  double *hjte_new = hpnew;                     // the trial point itself is formed on the device
   int kiter;
   for (kiter = 0; kiter < itmax && !stop; ++kiter) {
     if (p_eL2 <= eps3) {
@@ -385,20 +479,20 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
                                  d.stream));
       }
       double mx = 0.0;
-      if (wt) {
+      // first iteration of a prefactored cluster: J^T J, mu0 and the factor are already there
+      const int slot = (!wt && !os && kiter == 0 && linsolv == 0) ? w.pref_slot[k] : -1;
+      const bool prefac = slot >= 0;
+      const bool need_mx = (kiter == 0) && !prefac;
+      w.jtj0_cur = prefac ? w.JB + (size_t)slot * n * n : nullptr;
+      if (prefac) {
+        w.pref_slot[k] = -1;  // valid for this visit only
+      } else if (wt) {
         weighted_jtj(pr, k, s0, s1, pblk_dev, wt, w.JTJ0);
-        // mu0 needs max_i (J^T J)_ii: gather the diagonal and bring it back
-        if (kiter == 0) {
-          double *hdiag = w.h_vec + 4 * n + 4 * d.N + 8;
+        if (need_mx) {
           db_launch_extract_diag(w.JTJ0, w.JTe_new, n, d.stream);  // JTe_new is free scratch here
           db_count_launch(1);
-          DB_CHECK(cudaMemcpyAsync(hdiag, w.JTe_new, sizeof(double) * n, cudaMemcpyDeviceToHost,
+          DB_CHECK(cudaMemcpyAsync(hsc, w.JTe_new, sizeof(double) * n, cudaMemcpyDeviceToHost,
                                    d.stream));
-          DB_CHECK(cudaStreamSynchronize(d.stream));
-          for (int i = 0; i < n; i++)
-            if (fabs(hdiag[i]) > fabs(mx)) mx = hdiag[i];
-        } else {
-          DB_CHECK(cudaStreamSynchronize(d.stream));
         }
       } else {
         const double *Tuse = Tfull;
@@ -407,13 +501,21 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           Tuse = w.Tsub;
         }
         assemble(pr, Tuse, pblk_dev, w.JTJ0);
-        DB_CHECK(cudaMemcpyAsync(hH, w.Hst, sizeof(double) * 4 * d.N, cudaMemcpyDeviceToHost,
-                                 d.stream));
-        DB_CHECK(cudaStreamSynchronize(d.stream));
-        // the diagonal is (h00 x4, h11 x4) per station
-        for (int s = 0; s < d.N; s++) {
-          if (fabs(hH[4 * s]) > fabs(mx)) mx = hH[4 * s];
-          if (fabs(hH[4 * s + 1]) > fabs(mx)) mx = hH[4 * s + 1];
+        if (need_mx)
+          DB_CHECK(cudaMemcpyAsync(hH, w.Hst, sizeof(double) * 4 * d.N, cudaMemcpyDeviceToHost,
+                                   d.stream));
+      }
+      if (need_mx || os) DB_CHECK(cudaStreamSynchronize(d.stream));
+      if (need_mx) {
+        if (wt) {
+          for (int i = 0; i < n; i++)
+            if (fabs(hsc[i]) > fabs(mx)) mx = hsc[i];
+        } else {
+          // the diagonal is (h00 x4, h11 x4) per station
+          for (int s = 0; s < d.N; s++) {
+            if (fabs(hH[4 * s]) > fabs(mx)) mx = hH[4 * s];
+            if (fabs(hH[4 * s + 1]) > fabs(mx)) mx = hH[4 * s + 1];
+          }
         }
       }
       jacTe_inf = 0.0;
@@ -427,13 +529,46 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
         stop = 1;
         break;
       }
-      if (kiter == 0) mu = tau * mx;  // clmfit.c:342-352 (inside the OS loop in the OS variants)
+      if (kiter == 0) mu = prefac ? w.h_mu[slot] : tau * mx;  // clmfit.c:342-352
+      bool use_factor = prefac;
       // adaptive damping loop (clmfit.c:356-540)
       while (1) {
-        int issolved = damped_solve(pr, mu, linsolv, eps1);
+        int issolved;
+        if (use_factor) {
+          // (J^T J + mu0 I) = L L^T came out of the batch: only the two triangular solves remain
+          use_factor = false;
+          DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                                   d.stream));
+          DB_CHECK(cudaMemsetAsync(w.devinfo, 0, 2 * sizeof(int), d.stream));
+          db_prof_begin(5, 0.0, d.stream);
+          CS_CHECK(cusolverDnDpotrs(w.cs, CUBLAS_FILL_MODE_LOWER, n, 1, w.LB + (size_t)slot * n * n,
+                                    n, w.Dp, n, w.devinfo + 1));
+          db_prof_end(d.stream);
+          db_count_launch(1);
+          issolved = (w.h_binfo[slot] == 0) ? 1 : 0;
+        } else {
+          issolved = enqueue_solve(pr, mu, linsolv, eps1);
+        }
+        // p + dp, |dp|^2, dp.J^T e on the device; trial pass; everything back in one go
+        db_launch_lm_step(pblk_dev, w.Dp, w.JTe, w.pnew, d.scal + 8, n, d.stream);
+        db_cluster_pass(pr, k, w.pnew, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe_new, 1, t0, t1,
+                        wt);
+        db_count_launch(1);
+        int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
+        DB_CHECK(cudaMemcpyAsync(hinfo, w.devinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                                 d.stream));
+        DB_CHECK(cudaMemcpyAsync(hDp, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+        DB_CHECK(cudaMemcpyAsync(hsc + n, d.scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                                 d.stream));
+        DB_CHECK(cudaMemcpyAsync(hsc + n + 2, d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost,
+                                 d.stream));
+        if (!os)
+          DB_CHECK(cudaMemcpyAsync(hjte_new, w.JTe_new, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                                   d.stream));
+        DB_CHECK(cudaStreamSynchronize(d.stream));
+        if (issolved && linsolv != 2) issolved = (hinfo[0] == 0 && hinfo[1] == 0) ? 1 : 0;
         if (issolved) {
-          for (int i = 0; i < n; i++) hpnew[i] = hp[i] + hDp[i];
-          Dp_L2 = nrm2sq(hDp, n);
+          Dp_L2 = hsc[n];
           if (Dp_L2 <= eps2_sq * p_L2) {
             stop = 2;
             break;
@@ -442,35 +577,28 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
             stop = 4;
             break;
           }
-          DB_CHECK(cudaMemcpyAsync(w.pnew, hpnew, sizeof(double) * n, cudaMemcpyHostToDevice,
-                                   d.stream));
-          // trial residual norm and, speculatively, J^T e at the trial point
-          db_cluster_pass(pr, k, w.pnew, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe_new, 1, t0,
-                          t1, wt);
+          // only now does the trial count as evaluated (the reference stops before evaluating it)
           DB_CHECK(cudaMemcpyAsync(w.plast, w.pnew, sizeof(double) * n, cudaMemcpyDeviceToDevice,
                                    d.stream));
           *evaluated_trial = true;
-          const double pDp_eL2 = db_read_scalar(pr, 1);
+          const double pDp_eL2 = hsc[n + 2];
           if (!isfinite(pDp_eL2)) {
             stop = 7;
             break;
           }
-          double dL = 0.0;
-          for (int i = 0; i < n; i++) dL += hDp[i] * (mu * hDp[i] + hjte[i]);
+          const double dL = mu * Dp_L2 + hsc[n + 1];  // dp^T (mu dp + J^T e)
           const double dF = p_eL2 - pDp_eL2;
           if (dL > 0.0 && dF > 0.0) {
             double tmp = (2.0 * dF / dL - 1.0);
             tmp = 1.0 - tmp * tmp * tmp;
             mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);  // CLM_ONE_THIRD
             nu = 2;
-            memcpy(hp, hpnew, sizeof(double) * n);
+            for (int i = 0; i < n; i++) hp[i] += hDp[i];
             DB_CHECK(cudaMemcpyAsync(pblk_dev, w.pnew, sizeof(double) * n,
                                      cudaMemcpyDeviceToDevice, d.stream));
             if (!os) {
-              DB_CHECK(cudaMemcpyAsync(hjte, w.JTe_new, sizeof(double) * n,
-                                       cudaMemcpyDeviceToHost, d.stream));
+              memcpy(hjte, hjte_new, sizeof(double) * n);
               double *t = w.JTe; w.JTe = w.JTe_new; w.JTe_new = t;
-              DB_CHECK(cudaStreamSynchronize(d.stream));
             }
             p_eL2 = pDp_eL2;
             break;
@@ -677,4 +805,35 @@ extern "C" double dirac_b200_normal_eq_weighted(dirac_b200_problem *pr, int clus
     DB_CHECK(cudaMemcpy(JTJ, w.JTJ0, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
   DB_CHECK(cudaGetLastError());
   return c;
+}
+
+// micro-benchmark of one k_cluster_pass configuration on the resident problem: average device time
+// (us, CUDA events on the launching stream) of `reps` back-to-back launches over the full interval.
+// with_grad: also accumulate J^T e; write_out: write the residual; tslice <= 0: default slicing.
+extern "C" double dirac_b200_bench_cluster_pass(dirac_b200_problem *pr, int clus, int mode,
+                                                int with_grad, int write_out, int tslice,
+                                                int reps) {
+  DevProblem &d = pr->d;
+  db_lm_init(pr);
+  LMWork &w = pr->lm;
+  g_tslice_override = tslice;
+  double *pblk = d.pp + d.h_chunk_poff[d.h_clus[clus].chunk0];
+  cudaEvent_t e0, e1;
+  DB_CHECK(cudaEventCreate(&e0));
+  DB_CHECK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; i++)
+    db_cluster_pass(pr, clus, pblk, pr->res, w.dbuf, mode, write_out, with_grad ? w.JTe : nullptr,
+                    1, 0, d.tilesz, nullptr);
+  DB_CHECK(cudaEventRecord(e0, d.stream));
+  for (int i = 0; i < reps; i++)
+    db_cluster_pass(pr, (clus + i) % d.M, pblk, pr->res, w.dbuf, mode, write_out,
+                    with_grad ? w.JTe : nullptr, 1, 0, d.tilesz, nullptr);
+  DB_CHECK(cudaEventRecord(e1, d.stream));
+  DB_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  g_tslice_override = 0;
+  return 1e3 * ms / reps;
 }

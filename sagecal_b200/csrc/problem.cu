@@ -80,11 +80,58 @@ static void require_gpu() {
   }
 }
 
+// ---- caching device allocator ---------------------------------------------------------------------
+// The drop-in entry points build and tear down a resident problem per call, like the reference
+// (lmfit.c:831-1046 allocates and frees every scratch vector per call).  cudaMalloc/cudaFree of GBs
+// cost milliseconds and serialise the device, so freed blocks are kept and handed out again when a
+// request of exactly the same size comes back (the driver calls with the same shapes tile after
+// tile).  Bounded: blocks above 2 GiB and anything beyond 6 GiB of cache go back to the driver.
+#include <map>
+#include <unordered_map>
+static std::multimap<size_t, void *> g_free_blocks;
+static std::unordered_map<void *, size_t> g_live_blocks;
+static size_t g_cached_bytes = 0;
+void *db_malloc(size_t bytes) {
+  bytes = (bytes + 255) & ~(size_t)255;
+  auto it = g_free_blocks.find(bytes);
+  void *p = nullptr;
+  if (it != g_free_blocks.end()) {
+    p = it->second;
+    g_free_blocks.erase(it);
+    g_cached_bytes -= bytes;
+  } else {
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {  // give the cache back and retry once
+      cudaGetLastError();
+      for (auto &kv : g_free_blocks) cudaFree(kv.second);
+      g_free_blocks.clear();
+      g_cached_bytes = 0;
+      DB_CHECK(cudaMalloc(&p, bytes));
+    }
+  }
+  g_live_blocks[p] = bytes;
+  return p;
+}
+void db_free(void *p) {
+  if (!p) return;
+  auto it = g_live_blocks.find(p);
+  if (it == g_live_blocks.end()) {
+    cudaFree(p);
+    return;
+  }
+  const size_t bytes = it->second;
+  g_live_blocks.erase(it);
+  if (bytes > ((size_t)2 << 30) || g_cached_bytes + bytes > ((size_t)6 << 30)) {
+    cudaFree(p);
+  } else {
+    g_free_blocks.insert({bytes, p});
+    g_cached_bytes += bytes;
+  }
+}
+
 template <typename T>
 static T *dev_alloc(size_t n) {
-  T *p = nullptr;
-  DB_CHECK(cudaMalloc((void **)&p, n * sizeof(T) + 16));
-  return p;
+  return (T *)db_malloc(n * sizeof(T) + 16);
 }
 
 static void build_tiles(int N, std::vector<TileDesc> &tiles) {
@@ -235,7 +282,7 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
       db_count_launch(1);
     }
     DB_CHECK(cudaStreamSynchronize(d.stream));
-    DB_CHECK(cudaFree(stage));
+    db_free(stage);
   }
 
   // --- scratch ---
@@ -258,11 +305,11 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   DevProblem &d = pr->d;
   cudaStreamSynchronize(d.stream);
   db_lm_free(pr);
-  cudaFree(d.coh); cudaFree(d.x); cudaFree(d.flag); cudaFree(d.pp); cudaFree(d.clus);
-  cudaFree(d.chunk_poff); cudaFree(d.tiles); cudaFree(d.scal); cudaFree(d.counters);
-  cudaFree(pr->partials); cudaFree(pr->res); cudaFree(pr->g); cudaFree(pr->vis_stage);
-  if (pr->pm) cudaFree(pr->pm);
-  if (pr->E0) { cudaFree(pr->E0); cudaFree(pr->E1); cudaFree(pr->E2); cudaFree(pr->pk_dev); }
+  db_free(d.coh); db_free(d.x); db_free(d.flag); db_free(d.pp); db_free(d.clus);
+  db_free(d.chunk_poff); db_free(d.tiles); db_free(d.scal); db_free(d.counters);
+  db_free(pr->partials); db_free(pr->res); db_free(pr->g); db_free(pr->vis_stage);
+  if (pr->pm) db_free(pr->pm);
+  if (pr->E0) { db_free(pr->E0); db_free(pr->E1); db_free(pr->E2); db_free(pr->pk_dev); }
   cudaFreeHost(d.h_scal);
   free(d.h_clus); free(d.h_chunk_poff);
   if (pr->own_stream) cudaStreamDestroy(d.stream);
@@ -304,7 +351,7 @@ extern "C" void dirac_b200_get_coherencies(dirac_b200_problem *pr, double *coh) 
                              cudaMemcpyDeviceToHost, d.stream));
   }
   DB_CHECK(cudaStreamSynchronize(d.stream));
-  DB_CHECK(cudaFree(stage));
+  db_free(stage);
 }
 
 // ------------------------------------------------------------------------------------------------

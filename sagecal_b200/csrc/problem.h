@@ -30,6 +30,17 @@ struct LMWork {
   double2 *ebuf;          // [4][R] unweighted residual for the weight update
   double *HP, *HQ;        // [N][2][10] station sums of the weighted normal matrix
   double *plast;          // [8N] device copy of the last evaluated trial point
+  // normal matrices of ALL clusters of a sweep, assembled and factorised in one batch before the
+  // sweep (each cluster's first LM solve then only needs the triangular solves)
+  double *JB, *LB;        // [M][8N][8N] J^T J and its damped Cholesky factor
+  double *HB;             // [M][N][4]
+  double *mu_dev;         // [M] mu0 of each cluster
+  double *h_mu;           // pinned
+  int *binfo_dev, *h_binfo;
+  double **LBptr_dev;     // [M] pointers into LB
+  int *blist_dev, *btix_dev, *bpoff_dev;
+  int *pref_slot;         // host [M]: slot of cluster k in the current batch, -1 if not prefactored
+  const double *jtj0_cur; // matrix the damping loop of the current iteration starts from
 };
 
 struct dirac_b200_problem {
@@ -55,6 +66,8 @@ struct dirac_b200_problem {
   double *pk_dev;         // [8*N*Mt] search direction
 };
 
+void *db_malloc(size_t bytes);
+void db_free(void *p);
 void db_count_launch(int n);
 void db_prof_begin(int kind, double bytes, cudaStream_t st);
 void db_prof_end(cudaStream_t st);
@@ -67,6 +80,7 @@ double db_read_scalar(dirac_b200_problem *pr, int slot);
 void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, int robust,
                  double nu);
 void db_lm_init(dirac_b200_problem *pr);
+void db_prefactor_sweep(dirac_b200_problem *pr, double tau);
 void db_allreduce(dirac_b200_problem *pr, void *dev, long long count);
 extern "C" {
 void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, long long n4,

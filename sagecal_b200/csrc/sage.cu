@@ -58,7 +58,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
   const bool robust = is_robust_mode(solver_mode);
   if (sharded) {
     db_lm_init(pr);
-    if (!pr->pm) DB_CHECK(cudaMalloc((void **)&pr->pm, sizeof(double2) * 4 * d.R));
+    if (!pr->pm) pr->pm = (decltype(pr->pm))db_malloc(sizeof(double2) * 4 * d.R);
     pp_start.resize(m);
     hsum.resize(m > MG ? m : MG);
   }
@@ -89,6 +89,12 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
       DB_CHECK(cudaStreamSynchronize(d.stream));
       for (int g = 0; g < MG; g++)
         if (g < k0 || g >= k0 + M) nerr[g] = 0.0;  // other ranks' entries come back by the sum
+    }
+    {
+      // plain LM this sweep?  then assemble + factorise every cluster's first system as one batch
+      const bool last_em = (ci == max_emiter - 1);
+      const bool plain = (solver_mode == SM_LM_LBFGS) || (solver_mode == SM_OSLM_LBFGS && last_em);
+      if (plain && linsolv == 0 && max_iter > 0 && !weighted_iter) db_prefactor_sweep(pr, opts[0]);
     }
     for (int cl = 0; cl < M; cl++) {
       const int cj = cl;          // local cluster index (device tables)

@@ -141,6 +141,53 @@ k_line_eval(const double2 *__restrict__ E0, const double2 *__restrict__ E1,
   grid_reduce_sum_l(s, partials, out, counter);
 }
 
+// Gaussian cost along the line is the quartic sum |E0 - a E1 - a^2 E2|^2 = c0 + c1 a + ... + c4 a^4:
+// the five coefficients in one deterministic reduction (per-CTA partials, fixed-order final sum)
+__global__ void __launch_bounds__(256)
+k_line_poly(const double2 *__restrict__ E0, const double2 *__restrict__ E1,
+            const double2 *__restrict__ E2, long long n4, double *partials, double *out,
+            unsigned int *counter) {
+  double c[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double2 e0 = E0[i], e1 = E1[i], e2 = E2[i];
+    c[0] = fma(e0.x, e0.x, fma(e0.y, e0.y, c[0]));
+    c[1] = fma(e0.x, e1.x, fma(e0.y, e1.y, c[1]));
+    c[2] = fma(e1.x, e1.x, fma(e1.y, e1.y, c[2]));
+    c[2] = fma(-2.0 * e0.x, e2.x, fma(-2.0 * e0.y, e2.y, c[2]));
+    c[3] = fma(e1.x, e2.x, fma(e1.y, e2.y, c[3]));
+    c[4] = fma(e2.x, e2.x, fma(e2.y, e2.y, c[4]));
+  }
+  __shared__ double ws[5][8];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const double v = warp_sum(c[j]);
+    if (lane == 0) ws[j][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    for (int i = 0; i < 8; i++) s += ws[threadIdx.x][i];
+    partials[(size_t)blockIdx.x * 5 + threadIdx.x] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x < 5) {
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++)
+      s += ((volatile double *)partials)[(size_t)b * 5 + threadIdx.x];
+    // c1 = -2 sum E0.E1, c3 = 2 sum E1.E2
+    if (threadIdx.x == 1) s *= -2.0;
+    if (threadIdx.x == 3) s *= 2.0;
+    out[threadIdx.x] = s;
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
 // res = E0 - alpha E1 - alpha^2 E2
 __global__ void __launch_bounds__(256)
 k_line_residual(const double2 *__restrict__ E0, const double2 *__restrict__ E1,
@@ -209,6 +256,10 @@ void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, 
 void db_launch_axpby(const double2 *x, double2 *y, long long n4, double a, double b,
                      cudaStream_t st) {
   k_axpby<<<592, 256, 0, st>>>(x, y, n4, a, b);
+}
+void db_launch_line_poly(const double2 *E0, const double2 *E1, const double2 *E2, long long n4,
+                         double *partials, double *out, unsigned int *counter, cudaStream_t st) {
+  k_line_poly<<<192, 256, 0, st>>>(E0, E1, E2, n4, partials, out, counter);
 }
 void db_launch_line_residual(const double2 *E0, const double2 *E1, const double2 *E2, double2 *res,
                              long long n4, double alpha, cudaStream_t st) {

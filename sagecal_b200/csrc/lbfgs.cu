@@ -27,6 +27,8 @@ void db_launch_line_eval(const double2 *E0, const double2 *E1, const double2 *E2
                          unsigned int *counter, cudaStream_t st);
 void db_launch_line_residual(const double2 *E0, const double2 *E1, const double2 *E2, double2 *res,
                              long long n4, double alpha, cudaStream_t st);
+void db_launch_line_poly(const double2 *E0, const double2 *E1, const double2 *E2, long long n4,
+                         double *partials, double *out, unsigned int *counter, cudaStream_t st);
 }
 
 struct LbfgsCtx {
@@ -35,6 +37,7 @@ struct LbfgsCtx {
   double nu;
   int m;
   long long ncost, ngrad;
+  double poly[5];  // Gaussian cost along the current line: sum_j poly[j] alpha^j
 };
 
 static void line_alloc(dirac_b200_problem *pr) {
@@ -72,12 +75,28 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
     db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);
     db_count_launch(1);
   }
+  if (!c->robust) {
+    // the Gaussian cost along the line is a quartic in alpha: five reductions, then every cost
+    // evaluation of the line search is arithmetic on the host
+    db_launch_line_poly(pr->E0, pr->E1, pr->E2, 4 * d.R, pr->partials, d.scal + 16, d.counters,
+                        d.stream);
+    db_count_launch(1);
+    DB_CHECK(cudaMemcpyAsync(d.h_scal + 16, d.scal + 16, 5 * sizeof(double), cudaMemcpyDeviceToHost,
+                             d.stream));
+    DB_CHECK(cudaStreamSynchronize(d.stream));
+    for (int j = 0; j < 5; j++) c->poly[j] = d.h_scal[16 + j];
+  }
 }
 
 // phi(alpha) = cost(xk + alpha pk)
 static double line_cost(LbfgsCtx *c, double alpha) {
   dirac_b200_problem *pr = c->pr;
   DevProblem &d = pr->d;
+  if (!c->robust) {
+    c->ncost++;
+    const double *q = c->poly;
+    return q[0] + alpha * (q[1] + alpha * (q[2] + alpha * (q[3] + alpha * q[4])));
+  }
   db_launch_line_eval(pr->E0, pr->E1, pr->E2, 4 * d.R, alpha, c->robust ? 2 : 1,
                       c->robust ? 1.0 / c->nu : 0.0, pr->partials, d.scal, d.counters, d.stream);
   db_count_launch(1);

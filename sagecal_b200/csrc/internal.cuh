@@ -54,6 +54,7 @@ struct DevProblem {
   int *chunk_poff;         // [Mt] offsets of each (cluster,chunk) block in pp (carr[k].p[ck])
   TileDesc *tiles;         // [ntile]
   int ntile;
+  short2 *blpq;            // [Nbase] (p,q) of canonical baseline b (linear-mapped kernels)
   // host mirrors
   ClusterDesc *h_clus;
   int *h_chunk_poff;
@@ -287,6 +288,27 @@ struct WeightedJtjArgs {
   int t_begin, t_end, tslice;
 };
 
+// all-cluster TMA-pipelined passes (kernels_tma.cu)
+struct StreamAllArgs {
+  const double2 *coh;        // [M][4][R]
+  const double2 *x;          // [4][R]
+  const unsigned char *flag;
+  const double *pp;          // Jones (device)
+  const double *pk;          // search direction (MODE 1)
+  const ClusterDesc *clus;
+  const int *chunk_poff;
+  const short2 *blpq;
+  double2 *out;              // MODE 0
+  double2 *E0, *E1, *E2;     // MODE 1
+  double *partials, *cost;
+  unsigned int *counter;
+  long long R;
+  int N, Nbase, tilesz, M;
+  int out_mode, cost_mode;
+  double inv_nu;
+  int partial;
+};
+
 // line model of the LBFGS line search: e(alpha) = E0 - alpha E1 - alpha^2 E2 (kernels_line.cu)
 struct LineSetupArgs {
   const double2 *coh;        // [M][4][R]
@@ -351,4 +373,13 @@ void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st
 void db_launch_coh_gram(const GramArgs *a, int ntile, int nk, cudaStream_t st);
 void db_launch_assemble(const AssembleArgs *a, int ntile, cudaStream_t st);
 void db_launch_copy_add_diag(const double *A0, double *A, int n, double mu, cudaStream_t st);
+// kernels_chol.cu: (A + mu I) x = b on one thread-block cluster
+int db_chol_max_n();
+int db_chol_available();
+size_t db_chol_ws_doubles(int n);
+void db_launch_chol_solve(const double *A, int n, double mu, const double *b, double *x, double *ws,
+                          int *info, cudaStream_t st);
+int db_stream_all_nblocks(int Nbase, int tilesz);
+void db_launch_predict_tma(const StreamAllArgs *a, cudaStream_t st);
+void db_launch_line_setup_tma(const StreamAllArgs *a, cudaStream_t st);
 }

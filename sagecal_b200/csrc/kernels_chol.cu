@@ -1,0 +1,518 @@
+// Damped normal-equation solve (A + mu I) x = b for one cluster's 8N x 8N system, as ONE kernel on a
+// thread-block cluster (replaces the dpotrf + dpotrs pair of clmfit.c:373-395 / the cuSOLVER calls).
+//
+// The system is tiny (n = 496 for 62 stations: 41 MFLOP) and strictly latency bound: cuSOLVER spends
+// ~200 us in potrf and ~90 us in potrs on it, almost all of it launch gaps and grid-wide dependencies.
+// Here a cluster of CL CTAs (16 SMs when the device grants it, else 8) runs a right-looking blocked
+// Cholesky with 32 x 32 blocks and synchronises with barrier.cluster (~380 cycles) instead of kernel
+// boundaries:
+//   - the matrix lives in an L2-resident column-major workspace (ld = 32*nblk, identity padding);
+//   - one warp = one 32 x 32 block operation, lane l owns row l of the block in registers;
+//   - per panel j:   trsm of the blocks below L_jj  ->  cluster barrier  ->  rank-32 update of the
+//     trailing blocks; the warp that updates block (j+1,j+1) factors it in registers right away
+//     (32 pivots by warp shuffles), so potf2 never needs a phase of its own  ->  cluster barrier;
+//   - the two triangular solves run in CTA 0 once the factor is complete, with the blocks of the
+//     next column prefetched into registers while warp 0 walks the 32-step substitution chain.
+// info: 0, or (1-based) index of the first non-positive pivot, like dpotrf.
+#include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
+
+#include "internal.cuh"
+#include "tma.cuh"
+
+namespace {
+
+constexpr int CH_WARPS = 8;
+constexpr int CH_THREADS = CH_WARPS * 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct CholArgs {
+  const double *A;  // n x n symmetric, lower triangle read (column-major, ld = n)
+  const double *b;  // right-hand side (n)
+  double *x;        // solution (n)
+  double *ws;       // workspace: npad*npad factor | npad reciprocal diagonal | nblk*2048 inverses | npad rhs | npad y
+  int *info;
+  double mu;
+  int n, nblk;
+  long long *ts;  // optional phase timestamps (globaltimer ns), tuning only
+};
+
+// release/acquire at cluster scope orders the workspace stores (L2) before the other CTAs' .cg loads
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::
+                   : "memory");
+}
+__device__ __forceinline__ void stamp(const CholArgs &p, int &i) {
+  if (p.ts && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.ts[i] = t;
+  }
+  i++;
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// lane l <- row l of the 32 x 32 block at `base` (column-major, ld): 32 coalesced 256-byte reads
+__device__ __forceinline__ void load_rows(double (&a)[32], const double *base, int ld, int lane) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) a[c] = __ldcg(base + (size_t)c * ld + lane);
+}
+__device__ __forceinline__ void store_rows(const double (&a)[32], double *base, int ld, int lane) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) base[(size_t)c * ld + lane] = a[c];
+}
+// lane l <- column l of the block (32 contiguous doubles)
+__device__ __forceinline__ void load_cols(double (&a)[32], const double *base, int ld, int lane) {
+  const double2 *src = reinterpret_cast<const double2 *>(base + (size_t)lane * ld);
+#pragma unroll
+  for (int r = 0; r < 16; r++) {
+    const double2 v = __ldcg(src + r);
+    a[2 * r] = v.x;
+    a[2 * r + 1] = v.y;
+  }
+}
+// warp copy of a block into shared memory, column-major with ld 32
+__device__ __forceinline__ void stage_block(double *dst, const double *base, int ld, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int e = i * 32 + lane;  // double2 index: 16 per column
+    const int c = e >> 4, r2 = e & 15;
+    const double2 v = __ldcg(reinterpret_cast<const double2 *>(base + (size_t)c * ld) + r2);
+    reinterpret_cast<double2 *>(dst + c * 32)[r2] = v;
+  }
+}
+
+// Cholesky of a 32 x 32 block held one row per lane.  returns 0 or the 1-based failing pivot.
+// The pivot chain is what bounds the whole factorisation, so two columns are eliminated per step:
+// with d0 = a_kk, e = a_k+1,k, d1 = a_k+1,k+1 the second pivot is d1 - e^2/d0 = (d1 d0 - e^2)/d0, whose
+// inverse root rsqrt(d1 d0 - e^2) sqrt(d0) does not wait for the first one: both rsqrt run side by
+// side.  Columns k, k+1 of L reach the other lanes through shared memory (cols: 32 x 32 scratch, fresh
+// columns every step, one __syncwarp per pair); the three pivot entries travel by shuffle.
+__device__ __forceinline__ int potf2_warp(double (&a)[32], double &myrd, double *cols, int lane) {
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < 32; k += 2) {
+    const double d0 = __shfl_sync(FULL, a[k], k);
+    const double e = __shfl_sync(FULL, a[k], k + 1);
+    const double d1 = __shfl_sync(FULL, a[k + 1], k + 1);
+    const double num = fma(d1, d0, -e * e);
+    if (!bad) {
+      if (!(d0 > 0.0)) bad = k + 1;
+      else if (!(num > 0.0)) bad = k + 2;
+    }
+    const double r0 = rsqrt(d0), rn = rsqrt(num);
+    const double r1 = rn * (d0 * r0);
+    const double l0 = a[k] * r0;
+    const double l10 = e * r0;
+    const double l1 = fma(-l0, l10, a[k + 1]) * r1;
+    a[k] = l0;
+    a[k + 1] = l1;
+    if (lane == k) myrd = r0;
+    if (lane == k + 1) myrd = r1;
+    if (k < 30) {
+      cols[k * 32 + lane] = l0;
+      cols[(k + 1) * 32 + lane] = l1;
+      __syncwarp();
+#pragma unroll
+      for (int m = k + 2; m < 32; m += 2) {
+        const double2 c0 = lds_v2(reinterpret_cast<const double2 *>(cols + k * 32 + m));
+        const double2 c1 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 1) * 32 + m));
+        a[m] = fma(-l1, c1.x, fma(-l0, c0.x, a[m]));
+        a[m + 1] = fma(-l1, c1.y, fma(-l0, c0.y, a[m + 1]));
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 1; c < 32; c++)
+    if (c > lane) a[c] = 0.0;
+  return bad;
+}
+
+// x <- x L^-T for the staged diagonal block Ls (column-major) with reciprocal diagonal rds
+__device__ __forceinline__ void trsm_warp(double (&x)[32], const double *Ls, const double *rds) {
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    x[c] *= rds[c];
+    const double xc = x[c];
+    int m0 = c + 1;
+    if (m0 & 1) {  // odd start: one scalar element, then aligned pairs (c is static after unrolling)
+      if (m0 < 32) x[m0] = fma(-xc, Ls[c * 32 + m0], x[m0]);
+      m0++;
+    }
+#pragma unroll
+    for (int m = m0; m < 32; m += 2) {
+      const double2 l = lds_v2(reinterpret_cast<const double2 *>(Ls + c * 32 + m));
+      x[m] = fma(-xc, l.x, x[m]);
+      x[m + 1] = fma(-xc, l.y, x[m + 1]);
+    }
+  }
+}
+
+// c <- c - a B^T with B staged column-major (B[k][m] at m*32+k)
+__device__ __forceinline__ void update_warp(double (&c)[32], const double (&a)[32],
+                                            const double *Bs) {
+#pragma unroll
+  for (int m = 0; m < 32; m++) {
+    const double am = -a[m];
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+      const double2 bv = lds_v2(reinterpret_cast<const double2 *>(Bs + m * 32 + k));
+      c[k] = fma(am, bv.x, c[k]);
+      c[k + 1] = fma(am, bv.y, c[k + 1]);
+    }
+  }
+}
+
+// row `lane` of block (I,K) of A + mu I (identity on the padding)
+__device__ __forceinline__ void load_rows_A(double (&a)[32], const CholArgs &p, int I, int K,
+                                            int lane) {
+  const int r = I * 32 + lane;
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    const int cc = K * 32 + c;
+    double v;
+    if (r < p.n && cc < p.n) {
+      v = p.A[(size_t)cc * p.n + r];
+      if (r == cc) v += p.mu;
+    } else {
+      v = (r == cc) ? 1.0 : 0.0;
+    }
+    a[c] = v;
+  }
+}
+
+__device__ __forceinline__ double dot32(const double (&a)[32], const double *v) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+  for (int m = 0; m < 32; m += 4) {
+    const double2 v0 = lds_v2(reinterpret_cast<const double2 *>(v + m));
+    const double2 v1 = lds_v2(reinterpret_cast<const double2 *>(v + m + 2));
+    s0 = fma(a[m], v0.x, s0);
+    s1 = fma(a[m + 1], v0.y, s1);
+    s2 = fma(a[m + 2], v1.x, s2);
+    s3 = fma(a[m + 3], v1.y, s3);
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+// y_j = L_jj^-1 b_j by one warp (L_jj staged column-major in Ls): the forward solve of block j
+__device__ __forceinline__ double fwd_block(double val, const double *Ls, double myrd, int lane) {
+#pragma unroll 4
+  for (int c = 0; c < 32; c++) {
+    const double yc = __shfl_sync(FULL, val * myrd, c);
+    if (lane == c) val = yc;
+    if (lane > c) val = fma(-yc, Ls[c * 32 + lane], val);
+  }
+  return val;
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_rank(), CL = (int)cluster_size();
+  const int G = CL * CH_WARPS;     // warps of the cluster
+  const int g = w * CL + crank;    // spread consecutive work items over the SMs first
+  const int ld = p.nblk * 32, nblk = p.nblk;
+  double *ws = p.ws;
+  double *wrd = p.ws + (size_t)ld * ld;
+  double *winv = wrd + ld;  // per diagonal block: L_jj^-1 (1024) then its transpose (1024)
+  double *wb = winv + (size_t)nblk * 2048;  // running right-hand side (forward solve rides along)
+  double *wy = wb + ld;                     // y = L^-1 b
+  double *Bs = sm + (size_t)w * (32 * 32 + 32);  // per-warp staging block + 32 reciprocals
+  double *rds = Bs + 32 * 32;
+
+  int si = 0;
+  stamp(p, si);
+  if (g == 0 && lane == 0) p.info[0] = p.info[1] = 0;  // [0] factor status, [1] solve status
+
+  // Panel j = -1 only factors block (0,0).  Panel 0 reads its blocks from A (+ mu on the diagonal,
+  // identity padding), later panels from the workspace, so A is never copied as a whole.
+  for (int j = -1; j < nblk - 1; j++) {
+    const int nrem = nblk - 1 - j;
+    if (j >= 0) {
+      // ---- panel: L_Ij = A_Ij L_jj^-T
+      for (int t = g; t < nrem; t += G) {
+        const int I = j + 1 + t;
+        __syncwarp();
+        stage_block(Bs, ws + (size_t)(j * 32) * ld + j * 32, ld, lane);
+        rds[lane] = __ldcg(wrd + j * 32 + lane);
+        double x[32];
+        double *blk = ws + (size_t)(j * 32) * ld + I * 32;
+        if (j == 0) load_rows_A(x, p, I, 0, lane);
+        else load_rows(x, blk, ld, lane);
+        __syncwarp();
+        trsm_warp(x, Bs, rds);
+        store_rows(x, blk, ld, lane);
+      }
+      if (g == G - 1) {
+        // the forward solve rides along: y_j = L_jj^-1 b_j on an otherwise idle warp
+        __syncwarp();
+        stage_block(Bs, ws + (size_t)(j * 32) * ld + j * 32, ld, lane);
+        const double myrd = __ldcg(wrd + j * 32 + lane);
+        const int r = j * 32 + lane;
+        const double bj = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+        __syncwarp();
+        wy[r] = fwd_block(bj, Bs, myrd, lane);
+      }
+      cluster_barrier();
+      stamp(p, si);
+    }
+    // ---- trailing update A_IK -= L_Ij L_Kj^T, j < K <= I; item 0 is block (j+1,j+1), factored at once
+    const int T = (j < 0) ? 1 : nrem * (nrem + 1) / 2;
+    for (int t = g; t < T; t += G) {
+      int u = 0;
+      while ((u + 1) * (u + 2) / 2 <= t) u++;
+      const int v = t - u * (u + 1) / 2;
+      const int I = j + 1 + u, K = j + 1 + v;
+      double c[32];
+      double *blk = ws + (size_t)(K * 32) * ld + I * 32;
+      __syncwarp();
+      if (j >= 0) {
+        stage_block(Bs, ws + (size_t)(j * 32) * ld + K * 32, ld, lane);
+        double a[32];
+        load_rows(a, ws + (size_t)(j * 32) * ld + I * 32, ld, lane);
+        if (j == 0) load_rows_A(c, p, I, K, lane);
+        else load_rows(c, blk, ld, lane);
+        if (v == 0) {
+          // first trailing column: this warp holds row I of L_Ij, so b_I -= L_Ij y_j costs 32 FMAs
+          rds[lane] = __ldcg(wy + j * 32 + lane);
+          const int r = I * 32 + lane;
+          const double bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+          __syncwarp();
+          wb[r] = bI - dot32(a, rds);
+        }
+        __syncwarp();
+        update_warp(c, a, Bs);
+      } else {
+        load_rows_A(c, p, 0, 0, lane);
+      }
+      if (t == 0) {
+        double myrd = 0.0;
+        __syncwarp();
+        const int bad = potf2_warp(c, myrd, Bs, lane);
+        wrd[(j + 1) * 32 + lane] = myrd;
+        if (bad && lane == 0) atomicCAS(p.info, 0, (j + 1) * 32 + bad);
+      }
+      store_rows(c, blk, ld, lane);
+    }
+    cluster_barrier();
+    stamp(p, si);
+  }
+
+  // ---- inverses of the diagonal blocks (one warp each, all concurrent): they turn the 32-step
+  // substitutions of the two triangular solves into 32 x 32 matrix-vector products.
+  for (int t = g; t < nblk; t += G) {
+    __syncwarp();
+    stage_block(Bs, ws + (size_t)(t * 32) * ld + t * 32, ld, lane);
+    rds[lane] = __ldcg(wrd + t * 32 + lane);
+    double x[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) x[c] = (c == lane) ? 1.0 : 0.0;
+    __syncwarp();
+    trsm_warp(x, Bs, rds);  // x[c] = (L^-1)[c][lane]
+    double *inv = winv + (size_t)t * 2048;
+    // inv[m*32 + l] = Linv[l][m] (row l per lane for the forward solve); the transpose behind it
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      inv[lane * 32 + c] = x[c];         // (l = c, m = lane)
+      inv[1024 + c * 32 + lane] = x[c];  // T[l = lane][m = c] = Linv[c][lane]
+    }
+  }
+  if (g == G - 1) {
+    const int j = nblk - 1;
+    __syncwarp();
+    stage_block(Bs, ws + (size_t)(j * 32) * ld + j * 32, ld, lane);
+    const double myrd = __ldcg(wrd + j * 32 + lane);
+    const int r = j * 32 + lane;
+    const double bj = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+    __syncwarp();
+    wy[r] = fwd_block(bj, Bs, myrd, lane);
+  }
+  cluster_barrier();
+  stamp(p, si);
+  if (crank != 0) return;
+
+  // ---- L^T x = y in CTA 0 (y was produced alongside the factorisation).  Each step is a 32 x 32
+  // product by warp 0, a CTA barrier, and the rank-32 update of the rows still to be solved; the
+  // blocks of the NEXT step are already being fetched while this one runs.
+  double *rhs = sm;
+  for (int i = threadIdx.x; i < ld; i += CH_THREADS) rhs[i] = __ldcg(wy + i);
+  double li[32], p0[32], p1[32];
+  {
+    const int j = nblk - 1;
+    if (w == 0) load_rows(li, winv + (size_t)j * 2048 + 1024, 32, lane);
+    if (j - 1 - w >= 0) load_cols(p0, ws + (size_t)((j - 1 - w) * 32) * ld + j * 32, ld, lane);
+    if (j - 1 - w - CH_WARPS >= 0)
+      load_cols(p1, ws + (size_t)((j - 1 - w - CH_WARPS) * 32) * ld + j * 32, ld, lane);
+  }
+  __syncthreads();
+  for (int j = nblk - 1; j >= 0; j--) {
+    const int K0 = j - 1 - w, K1 = K0 - CH_WARPS;
+    if (w == 0) {
+      const double xv = dot32(li, rhs + j * 32);
+      __syncwarp();
+      rhs[j * 32 + lane] = xv;
+    }
+    __syncthreads();
+    if (K0 >= 0) rhs[K0 * 32 + lane] -= dot32(p0, rhs + j * 32);
+    if (K1 >= 0) rhs[K1 * 32 + lane] -= dot32(p1, rhs + j * 32);
+    if (j - 1 >= 0) {
+      if (w == 0) load_rows(li, winv + (size_t)(j - 1) * 2048 + 1024, 32, lane);
+      if (K0 - 1 >= 0) load_cols(p0, ws + (size_t)((K0 - 1) * 32) * ld + (j - 1) * 32, ld, lane);
+      if (K1 - 1 >= 0) load_cols(p1, ws + (size_t)((K1 - 1) * 32) * ld + (j - 1) * 32, ld, lane);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < p.n; i += CH_THREADS) p.x[i] = rhs[i];
+  stamp(p, si);
+}
+
+int g_cluster = -1;  // 16, 8 or 0 (unavailable)
+
+size_t chol_smem(int nblk) {
+  const size_t stage = (size_t)CH_WARPS * (32 * 32 + 32) * sizeof(double);
+  const size_t rhs = (size_t)nblk * 32 * sizeof(double);
+  return stage > rhs ? stage : rhs;
+}
+
+bool try_cluster(int cl, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl);
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nclus = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclus, k_chol_solve, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return nclus > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// largest system the cluster solver takes (32*16 rows); larger ones stay on cuSOLVER
+int db_chol_max_n() { return 512; }
+
+size_t db_chol_ws_doubles(int n) {
+  const size_t npad = (size_t)((n + 31) / 32) * 32;
+  return npad * npad + 3 * npad + (npad / 32) * 2048;
+}
+
+// 1 if the device grants a cluster of 8 or 16 CTAs for the solver
+int db_chol_available() {
+  if (g_cluster < 0) {
+    const size_t smem = chol_smem(16);
+    cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    const char *e = getenv("DIRAC_B200_CHOL_CLUSTER");
+    const int want = e ? atoi(e) : 16;
+    g_cluster = 0;
+    if (want >= 16 && try_cluster(16, smem)) g_cluster = 16;
+    else if (want >= 8 && try_cluster(8, smem)) g_cluster = 8;
+    else if (want >= 1 && want < 8 && try_cluster(want, smem)) g_cluster = want;
+    cudaGetLastError();
+  }
+  return g_cluster > 0;
+}
+
+// (A + mu I) x = b, n <= db_chol_max_n().  ws: db_chol_ws_doubles(n) doubles.  info: device int.
+static long long *g_ts = nullptr;
+void db_launch_chol_solve(const double *A, int n, double mu, const double *b, double *x, double *ws,
+                          int *info, cudaStream_t st) {
+  CholArgs p;
+  p.ts = g_ts;
+  p.A = A; p.b = b; p.x = x; p.ws = ws; p.info = info; p.mu = mu; p.n = n; p.nblk = (n + 31) / 32;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g_cluster);
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = chol_smem(16);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = g_cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  DB_CHECK(cudaLaunchKernelEx(&cfg, k_chol_solve, p));
+}
+
+
+// host-buffer convenience wrapper (tests, diagnostics): returns 0, or -1 when the cluster solver is
+// unavailable / n too large.  *info as dpotrf.
+int dirac_b200_spd_solve(int n, const double *A, const double *b, double mu, double *x, int *info) {
+  if (n < 1 || n > db_chol_max_n() || !db_chol_available()) return -1;
+  double *dA, *db, *dx, *dws;
+  int *dinfo;
+  DB_CHECK(cudaMalloc(&dA, sizeof(double) * n * n));
+  DB_CHECK(cudaMalloc(&db, sizeof(double) * n));
+  DB_CHECK(cudaMalloc(&dx, sizeof(double) * n));
+  DB_CHECK(cudaMalloc(&dws, sizeof(double) * db_chol_ws_doubles(n)));
+  DB_CHECK(cudaMalloc(&dinfo, 2 * sizeof(int)));
+  DB_CHECK(cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  DB_CHECK(cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+  db_launch_chol_solve(dA, n, mu, db, dx, dws, dinfo, 0);
+  DB_CHECK(cudaMemcpy(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  DB_CHECK(cudaMemcpy(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(dws); cudaFree(dinfo);
+  return 0;
+}
+
+// average device time (us) of `reps` back-to-back solves of one resident system (tuning hook)
+double dirac_b200_bench_spd_solve(int n, const double *A, const double *b, double mu, int reps) {
+  if (n < 1 || n > db_chol_max_n() || !db_chol_available()) return -1.0;
+  double *dA, *db, *dx, *dws;
+  int *dinfo;
+  DB_CHECK(cudaMalloc(&dA, sizeof(double) * n * n));
+  DB_CHECK(cudaMalloc(&db, sizeof(double) * n));
+  DB_CHECK(cudaMalloc(&dx, sizeof(double) * n));
+  DB_CHECK(cudaMalloc(&dws, sizeof(double) * db_chol_ws_doubles(n)));
+  DB_CHECK(cudaMalloc(&dinfo, 2 * sizeof(int)));
+  DB_CHECK(cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  DB_CHECK(cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; i++) db_launch_chol_solve(dA, n, mu, db, dx, dws, dinfo, 0);
+  cudaEventRecord(e0, 0);
+  for (int i = 0; i < reps; i++) db_launch_chol_solve(dA, n, mu, db, dx, dws, dinfo, 0);
+  cudaEventRecord(e1, 0);
+  DB_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (getenv("DIRAC_B200_CHOL_TS")) {
+    long long *dts, hts[64] = {0};
+    cudaMalloc(&dts, sizeof(hts));
+    cudaMemset(dts, 0, sizeof(hts));
+    g_ts = dts;
+    db_launch_chol_solve(dA, n, mu, db, dx, dws, dinfo, 0);
+    g_ts = nullptr;
+    cudaMemcpy(hts, dts, sizeof(hts), cudaMemcpyDeviceToHost);
+    for (int i = 1; i < 64 && hts[i]; i++) printf("  phase %2d: %7.2f us\n", i, 1e-3 * (hts[i] - hts[i - 1]));
+    cudaFree(dts);
+  }
+  cudaFree(dA); cudaFree(db); cudaFree(dx); cudaFree(dws); cudaFree(dinfo);
+  return 1e3 * ms / reps;
+}
+
+}  // extern "C"

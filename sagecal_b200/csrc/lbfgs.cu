@@ -64,7 +64,16 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
   a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.tilesz = d.tilesz; a.M = d.M;
   a.partial = (pr->world > 1) ? 1 : 0;
   db_prof_begin(7, (double)d.R * (64.0 * d.M + 65.0 + 192.0), d.stream);
-  db_launch_line_setup(&a, d.ntile, d.stream);
+  if (db_use_tma()) {
+    StreamAllArgs s;
+    memset(&s, 0, sizeof(s));
+    s.coh = a.coh; s.x = a.x; s.flag = a.flag; s.pp = a.xk; s.pk = a.pk; s.clus = a.clus;
+    s.chunk_poff = a.chunk_poff; s.blpq = d.blpq; s.E0 = a.E0; s.E1 = a.E1; s.E2 = a.E2;
+    s.R = a.R; s.N = a.N; s.Nbase = a.Nbase; s.tilesz = a.tilesz; s.M = a.M; s.partial = a.partial;
+    db_launch_line_setup_tma(&s, d.stream);
+  } else {
+    db_launch_line_setup(&a, d.ntile, d.stream);
+  }
   db_prof_end(d.stream);
   db_count_launch(1);
   if (pr->world > 1) {

@@ -104,6 +104,9 @@ void db_lm_init(dirac_b200_problem *pr) {
   int l4 = 0;
   CS_CHECK(cusolverDnDgesvd_bufferSize(w.cs, n8, n8, &l4));
   if (l4 > w.lwork) w.lwork = l4;
+  // the cluster Cholesky solver (kernels_chol.cu) shares the workspace
+  w.own_chol = n8 <= db_chol_max_n() && db_chol_available() && !getenv("DIRAC_B200_CUSOLVER");
+  if (w.own_chol && (size_t)w.lwork < db_chol_ws_doubles(n8)) w.lwork = (int)db_chol_ws_doubles(n8);
   w.cswork = dalloc<double>((size_t)w.lwork);
   w.dbuf = dalloc<double2>((size_t)4 * d.R);
   w.ready = true;
@@ -253,11 +256,20 @@ static int enqueue_solve(dirac_b200_problem *pr, double mu, int linsolv, double 
   DevProblem &d = pr->d;
   LMWork &w = pr->lm;
   const int n = w.n8;
+  int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
+  hinfo[0] = hinfo[1] = 0;
+  if (linsolv == 0 && w.own_chol) {
+    // one cluster kernel: damping, factorisation and both triangular solves (kernels_chol.cu)
+    db_prof_begin(5, 0.0, d.stream);
+    db_launch_chol_solve(w.jtj0_cur ? w.jtj0_cur : w.JTJ0, n, mu, w.JTe, w.Dp, w.cswork, w.devinfo,
+                         d.stream);
+    db_prof_end(d.stream);
+    db_count_launch(1);
+    return 1;
+  }
   db_launch_copy_add_diag(w.jtj0_cur ? w.jtj0_cur : w.JTJ0, w.JTJ, n, mu, d.stream);
   db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice, d.stream));
-  int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
-  hinfo[0] = hinfo[1] = 0;
   db_prof_begin(5, 0.0, d.stream);
   if (linsolv == 0) {
     CS_CHECK(cusolverDnDpotrf(w.cs, CUBLAS_FILL_MODE_LOWER, n, w.JTJ, n, w.cswork, w.lwork,
@@ -805,6 +817,24 @@ extern "C" double dirac_b200_normal_eq_weighted(dirac_b200_problem *pr, int clus
     DB_CHECK(cudaMemcpy(JTJ, w.JTJ0, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
   DB_CHECK(cudaGetLastError());
   return c;
+}
+
+// micro-benchmark of the all-cluster predict (cost_mode 1, no output): average device time in us
+extern "C" double dirac_b200_bench_predict(dirac_b200_problem *pr, int out_mode, int reps) {
+  DevProblem &d = pr->d;
+  cudaEvent_t e0, e1;
+  DB_CHECK(cudaEventCreate(&e0));
+  DB_CHECK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; i++) db_predict_dev(pr, d.pp, pr->res, out_mode, 1, 0.0, 0);
+  DB_CHECK(cudaEventRecord(e0, d.stream));
+  for (int i = 0; i < reps; i++) db_predict_dev(pr, d.pp, pr->res, out_mode, 1, 0.0, 0);
+  DB_CHECK(cudaEventRecord(e1, d.stream));
+  DB_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 1e3 * ms / reps;
 }
 
 // micro-benchmark of one k_cluster_pass configuration on the resident problem: average device time

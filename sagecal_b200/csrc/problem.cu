@@ -262,6 +262,15 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
   DB_CHECK(cudaMemcpy(d.tiles, tiles.data(), sizeof(TileDesc) * tiles.size(),
                       cudaMemcpyHostToDevice));
 
+  {
+    std::vector<short2> pq(Nbase);
+    int b = 0;
+    for (int p = 0; p < N - 1; p++)
+      for (int q = p + 1; q < N; q++, b++) pq[b] = make_short2((short)p, (short)q);
+    d.blpq = dev_alloc<short2>(Nbase);
+    DB_CHECK(cudaMemcpy(d.blpq, pq.data(), sizeof(short2) * Nbase, cudaMemcpyHostToDevice));
+  }
+
   // --- Jones, data, coherencies ---
   d.pp = dev_alloc<double>((size_t)d.npar);
   d.x = dev_alloc<double2>((size_t)4 * R);
@@ -288,7 +297,8 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
   // --- scratch ---
   int nb1 = db_predict_nblocks(d.ntile, tilesz);
   int nb2 = db_cluster_pass_nblocks(d.ntile, tilesz, 1);
-  pr->npartials = (nb1 > nb2 ? nb1 : nb2) + 1024;  // also covers the fixed-grid reductions
+  const int nb3 = db_stream_all_nblocks(Nbase, tilesz);
+  pr->npartials = (nb1 > nb2 ? (nb1 > nb3 ? nb1 : nb3) : (nb2 > nb3 ? nb2 : nb3)) + 1024;  // also covers the fixed-grid reductions
   pr->partials = dev_alloc<double>(pr->npartials);
   d.scal = dev_alloc<double>(64);
   DB_CHECK(cudaMallocHost((void **)&d.h_scal, 64 * sizeof(double)));
@@ -306,7 +316,7 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   cudaStreamSynchronize(d.stream);
   db_lm_free(pr);
   db_free(d.coh); db_free(d.x); db_free(d.flag); db_free(d.pp); db_free(d.clus);
-  db_free(d.chunk_poff); db_free(d.tiles); db_free(d.scal); db_free(d.counters);
+  db_free(d.chunk_poff); db_free(d.tiles); db_free(d.blpq); db_free(d.scal); db_free(d.counters);
   db_free(pr->partials); db_free(pr->res); db_free(pr->g); db_free(pr->vis_stage);
   if (pr->pm) db_free(pr->pm);
   if (pr->E0) { db_free(pr->E0); db_free(pr->E1); db_free(pr->E2); db_free(pr->pk_dev); }
@@ -359,6 +369,29 @@ extern "C" void dirac_b200_get_coherencies(dirac_b200_problem *pr, double *coh) 
 // ------------------------------------------------------------------------------------------------
 // model/residual/cost over all clusters at the Jones currently in d.pp; returns after queuing;
 // the cost lands in d.scal[slot] (device)
+// TMA-pipelined kernels unless DIRAC_B200_NO_TMA is set (A/B comparison, fallback for debugging)
+int db_use_tma() {
+  static int v = -1;
+  if (v < 0) v = getenv("DIRAC_B200_NO_TMA") ? 0 : 1;
+  return v;
+}
+
+static void predict_launch(dirac_b200_problem *pr, const PredictArgs &a) {
+  DevProblem &d = pr->d;
+  if (db_use_tma()) {
+    StreamAllArgs s;
+    memset(&s, 0, sizeof(s));
+    s.coh = a.coh; s.x = a.x; s.flag = a.flag; s.pp = a.pp; s.clus = a.clus;
+    s.chunk_poff = a.chunk_poff; s.blpq = d.blpq; s.out = a.out; s.partials = a.partials;
+    s.cost = a.cost; s.counter = a.counter; s.R = a.R; s.N = a.N; s.Nbase = a.Nbase;
+    s.tilesz = a.tilesz; s.M = a.M; s.out_mode = a.out_mode; s.cost_mode = a.cost_mode;
+    s.inv_nu = a.inv_nu;
+    db_launch_predict_tma(&s, d.stream);
+  } else {
+    db_launch_predict_full(&a, d.ntile, d.stream);
+  }
+}
+
 void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, int out_mode,
                     int cost_mode, double nu, int slot) {
   DevProblem &d = pr->d;
@@ -374,7 +407,7 @@ void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, 
     if (!pr->pm) pr->pm = dev_alloc<double2>((size_t)4 * d.R);
     a.out = pr->pm; a.out_mode = 2; a.cost_mode = 0;
     db_prof_begin(0, (double)d.R * (64.0 * d.M + 65.0 + 64.0), d.stream);
-    db_launch_predict_full(&a, d.ntile, d.stream);
+    predict_launch(pr, a);
     db_prof_end(d.stream);
     db_allreduce(pr, pr->pm, 8 * d.R);
     db_launch_residual_cost(d.x, pr->pm, out, 4 * d.R, out ? out_mode : 0, cost_mode, a.inv_nu,
@@ -383,7 +416,7 @@ void db_predict_dev(dirac_b200_problem *pr, const double *pp_dev, double2 *out, 
     return;
   }
   db_prof_begin(0, (double)d.R * (64.0 * d.M + 65.0 + (out_mode ? 64.0 : 0.0)), d.stream);
-  db_launch_predict_full(&a, d.ntile, d.stream);
+  predict_launch(pr, a);
   db_prof_end(d.stream);
   db_count_launch(1);
 }

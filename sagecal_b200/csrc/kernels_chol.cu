@@ -26,6 +26,7 @@ namespace {
 constexpr int CH_WARPS = 8;
 constexpr int CH_THREADS = CH_WARPS * 32;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned long long X_PENDING = 0xFFF8DEADBEEF0001ull;
 
 struct CholArgs {
   const double *A;  // n x n symmetric, lower triangle read (column-major, ld = n)
@@ -99,19 +100,33 @@ __device__ __forceinline__ void stage_block(double *dst, const double *base, int
 // inverse root rsqrt(d1 d0 - e^2) sqrt(d0) does not wait for the first one: both rsqrt run side by
 // side.  Columns k, k+1 of L reach the other lanes through shared memory (cols: 32 x 32 scratch, fresh
 // columns every step, one __syncwarp per pair); the three pivot entries travel by shuffle.
+// branch-free 1/sqrt(d) for normal positive d (anything else yields NaN/Inf, caught by the pivot
+// test): hardware seed, one third-order and one second-order correction.  No slow-path branch, so the
+// scheduler can overlap it with the trailing updates of the previous pivot pair.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d * y, y, 1.0);
+  y = fma(y, e * fma(0.375, e, 0.5), y);
+  e = fma(-d * y, y, 1.0);
+  return fma(y, 0.5 * e, y);
+}
+
 __device__ __forceinline__ int potf2_warp(double (&a)[32], double &myrd, double *cols, int lane) {
   int bad = 0;
+  // pivots of the current pair (software pipelined: those of the next pair are started as soon as
+  // columns k+2, k+3 are up to date, before the rest of the trailing update is issued)
+  double d0 = __shfl_sync(FULL, a[0], 0);
+  double e = __shfl_sync(FULL, a[0], 1);
+  double d1 = __shfl_sync(FULL, a[1], 1);
+  double num = fma(d1, d0, -e * e);
+  double r0 = fast_rsqrt(d0), rn = fast_rsqrt(num);
 #pragma unroll
   for (int k = 0; k < 32; k += 2) {
-    const double d0 = __shfl_sync(FULL, a[k], k);
-    const double e = __shfl_sync(FULL, a[k], k + 1);
-    const double d1 = __shfl_sync(FULL, a[k + 1], k + 1);
-    const double num = fma(d1, d0, -e * e);
     if (!bad) {
       if (!(d0 > 0.0)) bad = k + 1;
       else if (!(num > 0.0)) bad = k + 2;
     }
-    const double r0 = rsqrt(d0), rn = rsqrt(num);
     const double r1 = rn * (d0 * r0);
     const double l0 = a[k] * r0;
     const double l10 = e * r0;
@@ -124,8 +139,20 @@ __device__ __forceinline__ int potf2_warp(double (&a)[32], double &myrd, double 
       cols[k * 32 + lane] = l0;
       cols[(k + 1) * 32 + lane] = l1;
       __syncwarp();
+      {
+        const double2 c0 = lds_v2(reinterpret_cast<const double2 *>(cols + k * 32 + k + 2));
+        const double2 c1 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 1) * 32 + k + 2));
+        a[k + 2] = fma(-l1, c1.x, fma(-l0, c0.x, a[k + 2]));
+        a[k + 3] = fma(-l1, c1.y, fma(-l0, c0.y, a[k + 3]));
+      }
+      d0 = __shfl_sync(FULL, a[k + 2], k + 2);
+      e = __shfl_sync(FULL, a[k + 2], k + 3);
+      d1 = __shfl_sync(FULL, a[k + 3], k + 3);
+      num = fma(d1, d0, -e * e);
+      r0 = fast_rsqrt(d0);
+      rn = fast_rsqrt(num);
 #pragma unroll
-      for (int m = k + 2; m < 32; m += 2) {
+      for (int m = k + 4; m < 32; m += 2) {
         const double2 c0 = lds_v2(reinterpret_cast<const double2 *>(cols + k * 32 + m));
         const double2 c1 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 1) * 32 + m));
         a[m] = fma(-l1, c1.x, fma(-l0, c0.x, a[m]));
@@ -172,6 +199,30 @@ __device__ __forceinline__ void update_warp(double (&c)[32], const double (&a)[3
       c[k + 1] = fma(am, bv.y, c[k + 1]);
     }
   }
+}
+
+// shared-memory offset (doubles) of the backward-solve control block: behind the per-warp staging
+// areas and behind the column tiles of CTA 0 (which owns the most), identical in every CTA
+__host__ __device__ inline size_t ctrl_off(int nblk, int cl) {
+  size_t t = 0;
+  for (int j = 0; j < nblk; j += cl) t += 1024 + (size_t)(nblk - 1 - j) * 1056;
+  const size_t stage = (size_t)CH_WARPS * (32 * 32 + 32) + 2048;  // + cooperative diagonal block
+  return t > stage ? t : stage;
+}
+
+// doubles of tile storage the solve-only kernel needs (max over CTAs and over the two directions)
+__host__ __device__ inline size_t tri_tiles(int nblk, int cl) {
+  size_t best = 0;
+  for (int c = 0; c < cl && c < nblk; c++) {
+    size_t f = 0, b = 0;
+    for (int j = c; j < nblk; j += cl) {
+      f += (size_t)j * 1056;
+      b += (size_t)(nblk - 1 - j) * 1056;
+    }
+    if (f > best) best = f;
+    if (b > best) best = b;
+  }
+  return best;
 }
 
 // row `lane` of block (I,K) of A + mu I (identity on the padding)
@@ -235,6 +286,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
   int si = 0;
   stamp(p, si);
   if (g == 0 && lane == 0) p.info[0] = p.info[1] = 0;  // [0] factor status, [1] solve status
+  {
+    // the solution blocks double as their own arrival flags: a NaN pattern no computation produces
+    unsigned long long *xs0 = reinterpret_cast<unsigned long long *>(sm + ctrl_off(nblk, CL));
+    for (int i = threadIdx.x; i < ld; i += CH_THREADS) xs0[i] = X_PENDING;
+  }
 
   // Panel j = -1 only factors block (0,0).  Panel 0 reads its blocks from A (+ mu on the diagonal,
   // identity padding), later panels from the workspace, so A is never copied as a whole.
@@ -270,7 +326,66 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
     }
     // ---- trailing update A_IK -= L_Ij L_Kj^T, j < K <= I; item 0 is block (j+1,j+1), factored at once
     const int T = (j < 0) ? 1 : nrem * (nrem + 1) / 2;
+    if (crank == 0 && j >= 0) {
+      // The diagonal block is on the critical path (its factorisation follows): the 8 warps of CTA 0
+      // update 4 columns each, warp 0 then factors it in registers.
+      double *coopA = sm + (size_t)CH_WARPS * (32 * 32 + 32);  // L_{j+1,j}, column-major
+      double *coopC = coopA + 1024;
+      const int J1 = j + 1;
+      const double *src = ws + (size_t)(j * 32) * ld + J1 * 32;
+      double cv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int k = 4 * w + i, r = J1 * 32 + lane, cc = J1 * 32 + k;
+        if (j == 0) {
+          cv[i] = (r < p.n && cc < p.n) ? p.A[(size_t)cc * p.n + r] + (r == cc ? p.mu : 0.0)
+                                        : (r == cc ? 1.0 : 0.0);
+        } else {
+          cv[i] = __ldcg(ws + (size_t)cc * ld + r);
+        }
+      }
+      double yv = 0.0, bI = 0.0;
+      if (w == 1) {
+        const int r = J1 * 32 + lane;
+        yv = __ldcg(wy + j * 32 + lane);
+        bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+      }
+      for (int e = threadIdx.x; e < 512; e += CH_THREADS) {
+        const int c = e >> 4, r2 = e & 15;
+        reinterpret_cast<double2 *>(coopA + c * 32)[r2] =
+            __ldcg(reinterpret_cast<const double2 *>(src + (size_t)c * ld) + r2);
+      }
+      if (w == 1) rds[lane] = yv;
+      __syncthreads();
+      double a[32];
+#pragma unroll
+      for (int m = 0; m < 32; m++) a[m] = coopA[m * 32 + lane];
+#pragma unroll
+      for (int m = 0; m < 32; m++) {
+        const double2 b0 = lds_v2(reinterpret_cast<const double2 *>(coopA + m * 32 + 4 * w));
+        const double2 b1 = lds_v2(reinterpret_cast<const double2 *>(coopA + m * 32 + 4 * w + 2));
+        cv[0] = fma(-a[m], b0.x, cv[0]);
+        cv[1] = fma(-a[m], b0.y, cv[1]);
+        cv[2] = fma(-a[m], b1.x, cv[2]);
+        cv[3] = fma(-a[m], b1.y, cv[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) coopC[(4 * w + i) * 32 + lane] = cv[i];
+      if (w == 1) wb[J1 * 32 + lane] = bI - dot32(a, rds);  // b_{j+1} -= L_{j+1,j} y_j
+      __syncthreads();
+      if (w == 0) {
+        double c[32], myrd = 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) c[k] = coopC[k * 32 + lane];
+        __syncwarp();
+        const int bad = potf2_warp(c, myrd, Bs, lane);
+          wrd[J1 * 32 + lane] = myrd;
+        if (bad && lane == 0) atomicCAS(p.info, 0, J1 * 32 + bad);
+        store_rows(c, ws + (size_t)(J1 * 32) * ld + J1 * 32, ld, lane);
+        }
+    }
     for (int t = g; t < T; t += G) {
+      if (t == 0 && j >= 0) continue;  // done above
       int u = 0;
       while ((u + 1) * (u + 2) / 2 <= t) u++;
       const int v = t - u * (u + 1) / 2;
@@ -341,49 +456,339 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
   }
   cluster_barrier();
   stamp(p, si);
-  if (crank != 0) return;
 
-  // ---- L^T x = y in CTA 0 (y was produced alongside the factorisation).  Each step is a 32 x 32
-  // product by warp 0, a CTA barrier, and the rank-32 update of the rows still to be solved; the
-  // blocks of the NEXT step are already being fetched while this one runs.
-  double *rhs = sm;
-  for (int i = threadIdx.x; i < ld; i += CH_THREADS) rhs[i] = __ldcg(wy + i);
-  double li[32], p0[32], p1[32];
+  // ---- L^T x = y across the cluster.  CTA c owns the block columns j = c, c+CL, ...: it keeps their
+  // sub-diagonal blocks and L_jj^-T in shared memory (one L2 round trip for everything), so no step
+  // of the substitution waits on L2 and no SM has to stream the whole factor.  x_j = L_jj^-T (y_j -
+  // sum_{I>j} L_Ij^T x_I): as soon as an x_I lands in this CTA's shared memory the warp I%8 adds its
+  // term; the owner finishes the block, pushes x_j into every CTA (distributed shared memory) and
+  // x_j itself is the arrival flag (the slots start as a NaN pattern no computation produces).
+  double *ctrl = sm + ctrl_off(nblk, CL);  // behind the staging area: remote CTAs write here early
+  double *xs = ctrl;                                                 // [ld]   solution, all CTAs
+  double *partial = ctrl + ld + 2;                                   // [8][32]
+  double *vbuf = partial + CH_WARPS * 32;                            // [32]
+  double *tiles = sm;                                                // overlays the staging area
+  const int ncol = (nblk - 1 - crank + CL) / CL;                     // own columns (crank < nblk)
   {
-    const int j = nblk - 1;
-    if (w == 0) load_rows(li, winv + (size_t)j * 2048 + 1024, 32, lane);
-    if (j - 1 - w >= 0) load_cols(p0, ws + (size_t)((j - 1 - w) * 32) * ld + j * 32, ld, lane);
-    if (j - 1 - w - CH_WARPS >= 0)
-      load_cols(p1, ws + (size_t)((j - 1 - w - CH_WARPS) * 32) * ld + j * 32, ld, lane);
+    // preload own columns, highest first (they are needed in that order)
+    double *dst = tiles;
+    for (int q = ncol - 1; q >= 0; q--) {
+      const int j = crank + q * CL;
+      for (int e = threadIdx.x; e < 1024; e += CH_THREADS) dst[e] = __ldcg(winv + (size_t)j * 2048 + 1024 + e);
+      dst += 1024;
+      for (int I = nblk - 1; I > j; I--) {
+        if ((I & (CH_WARPS - 1)) == w) {
+          double *tile = dst + (size_t)(nblk - 1 - I) * 1056;
+          const double *src = ws + (size_t)(j * 32) * ld + I * 32;
+#pragma unroll 8
+          for (int c = 0; c < 32; c++) tile[c * 33 + lane] = __ldcg(src + (size_t)c * ld + lane);
+        }
+      }
+      dst += (size_t)(nblk - 1 - j) * 1056;
+    }
   }
   __syncthreads();
-  for (int j = nblk - 1; j >= 0; j--) {
-    const int K0 = j - 1 - w, K1 = K0 - CH_WARPS;
-    if (w == 0) {
-      const double xv = dot32(li, rhs + j * 32);
-      __syncwarp();
-      rhs[j * 32 + lane] = xv;
+  {
+    double *src = tiles;
+    for (int q = ncol - 1; q >= 0; q--) {
+      const int j = crank + q * CL;
+      const double *T = src;
+      const double *col = src + 1024;
+      src += 1024 + (size_t)(nblk - 1 - j) * 1056;
+      double part = 0.0;
+      const double yj = (w == 0) ? __ldcg(wy + j * 32 + lane) : 0.0;  // off the chain: fetched now
+      for (int I = nblk - 1; I > j; I--) {
+        if ((I & (CH_WARPS - 1)) != w) continue;
+        // wait for x_I: every lane watches one element (64-bit stores are single-copy atomic)
+        {
+          const unsigned addr = smem_u32(xs + I * 32 + lane);
+          unsigned long long bits;
+          do {
+            asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
+          } while (bits == X_PENDING);
+          __syncwarp();
+        }
+        const double *tile = col + (size_t)(nblk - 1 - I) * 1056 + lane * 33;  // element (r, c) at c*33 + r
+        const double *xv = xs + I * 32;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < 32; r += 2) {
+          const double2 x2 = lds_v2(reinterpret_cast<const double2 *>(xv + r));
+          s0 = fma(tile[r], x2.x, s0);  // L_Ij[r][lane]
+          s1 = fma(tile[r + 1], x2.y, s1);
+        }
+        part += s0 + s1;
+      }
+      partial[w * 32 + lane] = part;
+      __syncthreads();
+      if (w == 0) {
+        double v = yj;
+#pragma unroll
+        for (int ww = 0; ww < CH_WARPS; ww++) v -= partial[ww * 32 + lane];
+        vbuf[lane] = v;
+        __syncwarp();
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < 32; m += 2) {
+          const double2 v2 = lds_v2(reinterpret_cast<const double2 *>(vbuf + m));
+          s0 = fma(T[m * 32 + lane], v2.x, s0);
+          s1 = fma(T[(m + 1) * 32 + lane], v2.y, s1);
+        }
+        const double xj = s0 + s1;
+        const unsigned la = smem_u32(xs + j * 32 + lane);
+        for (int r = 0; r < CL; r++) {
+          unsigned ra;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(r));
+          asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(xj) : "memory");
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (K0 >= 0) rhs[K0 * 32 + lane] -= dot32(p0, rhs + j * 32);
-    if (K1 >= 0) rhs[K1 * 32 + lane] -= dot32(p1, rhs + j * 32);
-    if (j - 1 >= 0) {
-      if (w == 0) load_rows(li, winv + (size_t)(j - 1) * 2048 + 1024, 32, lane);
-      if (K0 - 1 >= 0) load_cols(p0, ws + (size_t)((K0 - 1) * 32) * ld + (j - 1) * 32, ld, lane);
-      if (K1 - 1 >= 0) load_cols(p1, ws + (size_t)((K1 - 1) * 32) * ld + (j - 1) * 32, ld, lane);
-    }
-    __syncthreads();
   }
-  for (int i = threadIdx.x; i < p.n; i += CH_THREADS) p.x[i] = rhs[i];
+  if (crank == 0) {
+    for (int i = threadIdx.x; i < p.n; i += CH_THREADS) {
+      const unsigned addr = smem_u32(xs + i);
+      unsigned long long bits;
+      do {
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
+      } while (bits == X_PENDING);
+      p.x[i] = __longlong_as_double((long long)bits);
+    }
+  }
+  // nobody leaves while a neighbour may still be writing into its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
   stamp(p, si);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Triangular solves only: L L^T x = b for a factor that already exists (column-major lower triangle,
+// ld = n, as cusolverDnDpotrfBatched leaves it).  Used for the first LM solve of a cluster visit, whose
+// factor comes out of the per-sweep batch.  Same cluster scheme as the tail of k_chol_solve, for both
+// directions: CTA c owns block row/column c (+CL, ...); its diagonal blocks are inverted locally, its
+// off-diagonal blocks sit in shared memory, every finished block of y (then x) is pushed into all
+// CTAs and doubles as its own arrival flag.
+// ------------------------------------------------------------------------------------------------
+struct TriArgs {
+  const double *L;  // n x n, lower triangle (column-major, ld = n)
+  const double *b;
+  double *x;
+  int n, nblk;
+};
+
+__device__ __forceinline__ double l_elem(const TriArgs &p, int r, int c) {
+  return (r < p.n && c < p.n) ? __ldg(p.L + (size_t)c * p.n + r) : (r == c ? 1.0 : 0.0);
+}
+
+__device__ __forceinline__ void wait_block(const double *slot, int lane) {
+  const unsigned addr = smem_u32(slot + lane);
+  unsigned long long bits;
+  do {
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
+  } while (bits == X_PENDING);
+  __syncwarp();
+}
+__device__ __forceinline__ void publish_block(double *slot, double v, int lane, int CL) {
+  const unsigned la = smem_u32(slot + lane);
+  for (int r = 0; r < CL; r++) {
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(r));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) k_tri_solve(TriArgs p) {
+  extern __shared__ __align__(16) double sm[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = (int)cluster_rank(), CL = (int)cluster_size();
+  const int nblk = p.nblk, ld = nblk * 32;
+  // layout: tiles (CTA 0 of the backward pass owns the most) | ys | xs | partial | vbuf | inverses
+  double *tiles = sm;
+  double *ctrl = sm + tri_tiles(nblk, CL);
+  double *ys = ctrl, *xs = ctrl + ld;
+  double *partial = xs + ld, *vbuf = partial + CH_WARPS * 32;
+  double *invs = vbuf + 32;  // per own diagonal block: Tf (32 x 33) then Tb (32 x 32)
+  const int nown = (nblk - 1 - crank + CL) / CL;  // own block rows / columns: crank, crank+CL, ...
+
+  for (int i = threadIdx.x; i < 2 * ld; i += CH_THREADS)
+    reinterpret_cast<unsigned long long *>(ctrl)[i] = X_PENDING;
+  // inverses of the own diagonal blocks (warp q for the q-th one; nown <= 2 in practice)
+  for (int q = w; q < nown; q += CH_WARPS) {
+    const int j = crank + q * CL;
+    double *Tf = invs + (size_t)q * (32 * 33 + 1024), *Tb = Tf + 32 * 33;
+    // stage L_jj column-major into Tb (scratch for now), reciprocal diagonal in registers
+#pragma unroll 8
+    for (int c = 0; c < 32; c++) Tb[c * 32 + lane] = l_elem(p, j * 32 + lane, j * 32 + c);
+    __syncwarp();
+    double xr[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) xr[c] = (c == lane) ? 1.0 : 0.0;
+    // x <- e_lane L^-T (same recurrence as trsm_warp, reciprocals taken on the fly)
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      xr[c] = xr[c] / Tb[c * 32 + c];
+      const double xc = xr[c];
+#pragma unroll
+      for (int m = c + 1; m < 32; m++) xr[m] = fma(-xc, Tb[c * 32 + m], xr[m]);
+    }
+    __syncwarp();
+    // xr[c] = Linv[c][lane]
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      Tf[lane * 33 + c] = xr[c];   // forward: lane l reads Tf[m*33 + l] = Linv[l][m]
+      Tb[c * 32 + lane] = xr[c];   // backward: lane l reads Tb[m*32 + l] = Linv[m][l]
+    }
+  }
+  // cluster barrier: every CTA has initialised its slots before anybody publishes into them
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+
+  // ---- forward: y_I = L_II^-1 (b_I - sum_{K<I} L_IK y_K), rows ascending
+  {
+    double *dst = tiles;
+    for (int q = 0; q < nown; q++) {
+      const int I = crank + q * CL;
+      for (int K = 0; K < I; K++) {
+        if ((K & (CH_WARPS - 1)) == w) {
+          double *tile = dst + (size_t)K * 1056;
+#pragma unroll 8
+          for (int c = 0; c < 32; c++) tile[c * 33 + lane] = l_elem(p, I * 32 + lane, K * 32 + c);
+        }
+      }
+      dst += (size_t)I * 1056;
+    }
+  }
+  __syncthreads();
+  {
+    const double *src = tiles;
+    for (int q = 0; q < nown; q++) {
+      const int I = crank + q * CL;
+      const double *Tf = invs + (size_t)q * (32 * 33 + 1024);
+      const int r = I * 32 + lane;
+      const double bI = (w == 0 && r < p.n) ? p.b[r] : 0.0;
+      double part = 0.0;
+      for (int K = 0; K < I; K++) {
+        if ((K & (CH_WARPS - 1)) != w) continue;
+        wait_block(ys + K * 32, lane);
+        const double *tile = src + (size_t)K * 1056 + lane;  // element (lane, m) at m*33 + lane
+        const double *yv = ys + K * 32;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < 32; m += 2) {
+          const double2 y2 = lds_v2(reinterpret_cast<const double2 *>(yv + m));
+          s0 = fma(tile[m * 33], y2.x, s0);
+          s1 = fma(tile[(m + 1) * 33], y2.y, s1);
+        }
+        part += s0 + s1;
+      }
+      src += (size_t)I * 1056;
+      partial[w * 32 + lane] = part;
+      __syncthreads();
+      if (w == 0) {
+        double v = bI;
+#pragma unroll
+        for (int ww = 0; ww < CH_WARPS; ww++) v -= partial[ww * 32 + lane];
+        vbuf[lane] = v;
+        __syncwarp();
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < 32; m += 2) {
+          const double2 v2 = lds_v2(reinterpret_cast<const double2 *>(vbuf + m));
+          s0 = fma(Tf[m * 33 + lane], v2.x, s0);
+          s1 = fma(Tf[(m + 1) * 33 + lane], v2.y, s1);
+        }
+        publish_block(ys + I * 32, s0 + s1, lane, CL);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- backward: x_j = L_jj^-T (y_j - sum_{I>j} L_Ij^T x_I), columns descending
+  {
+    double *dst = tiles;
+    for (int q = nown - 1; q >= 0; q--) {
+      const int j = crank + q * CL;
+      for (int I = nblk - 1; I > j; I--) {
+        if ((I & (CH_WARPS - 1)) == w) {
+          double *tile = dst + (size_t)(nblk - 1 - I) * 1056;
+#pragma unroll 8
+          for (int c = 0; c < 32; c++) tile[c * 33 + lane] = l_elem(p, I * 32 + lane, j * 32 + c);
+        }
+      }
+      dst += (size_t)(nblk - 1 - j) * 1056;
+    }
+  }
+  __syncthreads();
+  {
+    const double *src = tiles;
+    for (int q = nown - 1; q >= 0; q--) {
+      const int j = crank + q * CL;
+      const double *Tb = invs + (size_t)q * (32 * 33 + 1024) + 32 * 33;
+      double yj = 0.0;
+      if (w == 0) {
+        wait_block(ys + j * 32, lane);
+        yj = ys[j * 32 + lane];
+      }
+      double part = 0.0;
+      for (int I = nblk - 1; I > j; I--) {
+        if ((I & (CH_WARPS - 1)) != w) continue;
+        wait_block(xs + I * 32, lane);
+        const double *tile = src + (size_t)(nblk - 1 - I) * 1056 + lane * 33;  // (r, lane) at lane*33 + r
+        const double *xv = xs + I * 32;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int r = 0; r < 32; r += 2) {
+          const double2 x2 = lds_v2(reinterpret_cast<const double2 *>(xv + r));
+          s0 = fma(tile[r], x2.x, s0);
+          s1 = fma(tile[r + 1], x2.y, s1);
+        }
+        part += s0 + s1;
+      }
+      src += (size_t)(nblk - 1 - j) * 1056;
+      partial[w * 32 + lane] = part;
+      __syncthreads();
+      if (w == 0) {
+        double v = yj;
+#pragma unroll
+        for (int ww = 0; ww < CH_WARPS; ww++) v -= partial[ww * 32 + lane];
+        vbuf[lane] = v;
+        __syncwarp();
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int m = 0; m < 32; m += 2) {
+          const double2 v2 = lds_v2(reinterpret_cast<const double2 *>(vbuf + m));
+          s0 = fma(Tb[m * 32 + lane], v2.x, s0);
+          s1 = fma(Tb[(m + 1) * 32 + lane], v2.y, s1);
+        }
+        publish_block(xs + j * 32, s0 + s1, lane, CL);
+      }
+      __syncthreads();
+    }
+  }
+  if (crank == 0) {
+    for (int i = threadIdx.x; i < p.n; i += CH_THREADS) {
+      const unsigned addr = smem_u32(xs + i);
+      unsigned long long bits;
+      do {
+        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
+      } while (bits == X_PENDING);
+      p.x[i] = __longlong_as_double((long long)bits);
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+size_t tri_smem(int nblk, int cl) {
+  const int nown = (nblk - 1 + cl) / cl;
+  return sizeof(double) * (tri_tiles(nblk, cl) + 2 * (size_t)nblk * 32 + CH_WARPS * 32 + 32 +
+                           (size_t)nown * (32 * 33 + 1024));
 }
 
 int g_cluster = -1;  // 16, 8 or 0 (unavailable)
 
-size_t chol_smem(int nblk) {
-  const size_t stage = (size_t)CH_WARPS * (32 * 32 + 32) * sizeof(double);
-  const size_t rhs = (size_t)nblk * 32 * sizeof(double);
-  return stage > rhs ? stage : rhs;
+size_t chol_smem(int nblk, int cl) {
+  // staging / column tiles, then xs, ready, partial, vbuf
+  return sizeof(double) * (ctrl_off(nblk, cl) + (size_t)nblk * 32 + 2 + CH_WARPS * 32 + 32);
 }
 
 bool try_cluster(int cl, size_t smem) {
@@ -421,7 +826,7 @@ size_t db_chol_ws_doubles(int n) {
 // 1 if the device grants a cluster of 8 or 16 CTAs for the solver
 int db_chol_available() {
   if (g_cluster < 0) {
-    const size_t smem = chol_smem(16);
+    const size_t smem = chol_smem(16, 8);
     cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     const char *e = getenv("DIRAC_B200_CHOL_CLUSTER");
@@ -429,7 +834,6 @@ int db_chol_available() {
     g_cluster = 0;
     if (want >= 16 && try_cluster(16, smem)) g_cluster = 16;
     else if (want >= 8 && try_cluster(8, smem)) g_cluster = 8;
-    else if (want >= 1 && want < 8 && try_cluster(want, smem)) g_cluster = want;
     cudaGetLastError();
   }
   return g_cluster > 0;
@@ -445,7 +849,7 @@ void db_launch_chol_solve(const double *A, int n, double mu, const double *b, do
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g_cluster);
   cfg.blockDim = dim3(CH_THREADS);
-  cfg.dynamicSmemBytes = chol_smem(16);
+  cfg.dynamicSmemBytes = chol_smem(p.nblk, g_cluster);
   cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -457,6 +861,66 @@ void db_launch_chol_solve(const double *A, int n, double mu, const double *b, do
   DB_CHECK(cudaLaunchKernelEx(&cfg, k_chol_solve, p));
 }
 
+
+// L L^T x = b with an existing factor (column-major lower, ld = n <= db_chol_max_n())
+// 1 if the solve-only kernel fits this device's cluster size for n
+int db_tri_available(int n) {
+  if (n < 1 || n > db_chol_max_n() || !db_chol_available()) return 0;
+  return tri_smem((n + 31) / 32, g_cluster) <= 227 * 1024;
+}
+
+void db_launch_tri_solve(const double *L, int n, const double *b, double *x, cudaStream_t st) {
+  TriArgs p;
+  p.L = L; p.b = b; p.x = x; p.n = n; p.nblk = (n + 31) / 32;
+  static bool configured = false;
+  if (!configured) {
+    size_t mx = tri_smem(16, g_cluster);
+    if (mx > 227 * 1024) mx = 227 * 1024;
+    cudaFuncSetAttribute(k_tri_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx);
+    cudaFuncSetAttribute(k_tri_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g_cluster);
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = tri_smem(p.nblk, g_cluster);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = g_cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  DB_CHECK(cudaLaunchKernelEx(&cfg, k_tri_solve, p));
+}
+
+// test hook: x = (L L^T)^-1 b from host buffers; returns -1 when the cluster solver is unavailable
+int dirac_b200_tri_solve(int n, const double *L, const double *b, double *x, int reps, double *us) {
+  if (!db_tri_available(n)) return -1;
+  double *dL, *db, *dx;
+  DB_CHECK(cudaMalloc(&dL, sizeof(double) * n * n));
+  DB_CHECK(cudaMalloc(&db, sizeof(double) * n));
+  DB_CHECK(cudaMalloc(&dx, sizeof(double) * n));
+  DB_CHECK(cudaMemcpy(dL, L, sizeof(double) * n * n, cudaMemcpyHostToDevice));
+  DB_CHECK(cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+  db_launch_tri_solve(dL, n, db, dx, 0);
+  DB_CHECK(cudaMemcpy(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  if (reps > 0 && us) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, 0);
+    for (int i = 0; i < reps; i++) db_launch_tri_solve(dL, n, db, dx, 0);
+    cudaEventRecord(e1, 0);
+    DB_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *us = 1e3 * ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  cudaFree(dL); cudaFree(db); cudaFree(dx);
+  return 0;
+}
 
 // host-buffer convenience wrapper (tests, diagnostics): returns 0, or -1 when the cluster solver is
 // unavailable / n too large.  *info as dpotrf.

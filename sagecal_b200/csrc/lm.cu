@@ -549,12 +549,16 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
         if (use_factor) {
           // (J^T J + mu0 I) = L L^T came out of the batch: only the two triangular solves remain
           use_factor = false;
-          DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice,
-                                   d.stream));
           DB_CHECK(cudaMemsetAsync(w.devinfo, 0, 2 * sizeof(int), d.stream));
           db_prof_begin(5, 0.0, d.stream);
-          CS_CHECK(cusolverDnDpotrs(w.cs, CUBLAS_FILL_MODE_LOWER, n, 1, w.LB + (size_t)slot * n * n,
-                                    n, w.Dp, n, w.devinfo + 1));
+          if (w.own_chol && db_tri_available(n)) {
+            db_launch_tri_solve(w.LB + (size_t)slot * n * n, n, w.JTe, w.Dp, d.stream);
+          } else {
+            DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                                     d.stream));
+            CS_CHECK(cusolverDnDpotrs(w.cs, CUBLAS_FILL_MODE_LOWER, n, 1,
+                                      w.LB + (size_t)slot * n * n, n, w.Dp, n, w.devinfo + 1));
+          }
           db_prof_end(d.stream);
           db_count_launch(1);
           issolved = (w.h_binfo[slot] == 0) ? 1 : 0;

@@ -428,12 +428,26 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   double *hH = w.h_vec + 4 * n;    // station sums [N][4]
 
   double p_eL2;
+  // Prefactored visit: nothing the host knows is needed to enqueue the first trial (mu0 and the factor
+  // come from the batch), so the entry values (p, J^T e, ||e||^2) ride back with the trial's results
+  // and the entry tests of clmfit.c:300-340 are applied after the fact (a trial that should not have
+  // been taken is simply discarded: it only wrote scratch buffers).
+  const bool defer = have_first && !os && !wt && linsolv == 0 && itmax > 0 && w.pref_slot[k] >= 0 &&
+                     std::isnan(first_cost);
   DB_CHECK(cudaMemcpyAsync(hp, pblk_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
   if (have_first) {
     p_eL2 = first_cost;
     if (!os)
       DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    if (std::isnan(first_cost))
+      DB_CHECK(cudaMemcpyAsync(d.h_scal + 1, d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost,
+                               d.stream));
+    if (!defer) {
+      DB_CHECK(cudaStreamSynchronize(d.stream));
+      if (std::isnan(first_cost)) p_eL2 = d.h_scal[1];
+    } else {
+      p_eL2 = 1.0;  // placeholder until the first synchronisation
+    }
   } else {
     // e = wt.(d - f(p)), ||e||^2, J^T e     (clmfit.c:241-252 / robustlm.c:2235-2251)
     db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe, 1, t0, t1, wt);
@@ -441,12 +455,14 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
     p_eL2 = db_read_scalar(pr, 1);
   }
-  const double init_p_eL2 = p_eL2;
+  double init_p_eL2 = p_eL2;
   int stop = 0;
   if (!isfinite(p_eL2)) stop = 7;
   int nu = *nu_damp, nu2;
   double mu = 0.0, Dp_L2 = DBL_MAX, jacTe_inf = 0.0;
   *evaluated_trial = false;
+  bool pending_entry = defer;  // entry values not on the host yet
+  int kiter_adjust = 0;
 
   // ordered subsets (clmfit.c:1313-1356)
   int Nsubsets = 10;
@@ -469,7 +485,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   double *hjte_new = hpnew;                     // the trial point itself is formed on the device
   int kiter;
   for (kiter = 0; kiter < itmax && !stop; ++kiter) {
-    if (p_eL2 <= eps3) {
+    if (!pending_entry && p_eL2 <= eps3) {
       stop = 6;
       break;
     }
@@ -530,16 +546,19 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           }
         }
       }
-      jacTe_inf = 0.0;
-      for (int i = 0; i < n; i++) {
-        double a = fabs(hjte[i]);
-        if (a > jacTe_inf) jacTe_inf = a;
-      }
-      const double p_L2 = nrm2sq(hp, n);
-      if (jacTe_inf <= eps1) {
-        Dp_L2 = 0.0;
-        stop = 1;
-        break;
+      double p_L2 = 0.0;
+      if (!pending_entry) {
+        jacTe_inf = 0.0;
+        for (int i = 0; i < n; i++) {
+          double a = fabs(hjte[i]);
+          if (a > jacTe_inf) jacTe_inf = a;
+        }
+        p_L2 = nrm2sq(hp, n);
+        if (jacTe_inf <= eps1) {
+          Dp_L2 = 0.0;
+          stop = 1;
+          break;
+        }
       }
       if (kiter == 0) mu = prefac ? w.h_mu[slot] : tau * mx;  // clmfit.c:342-352
       bool use_factor = prefac;
@@ -582,6 +601,32 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           DB_CHECK(cudaMemcpyAsync(hjte_new, w.JTe_new, sizeof(double) * n, cudaMemcpyDeviceToHost,
                                    d.stream));
         DB_CHECK(cudaStreamSynchronize(d.stream));
+        if (pending_entry) {
+          // the deferred entry tests, in the reference's order
+          pending_entry = false;
+          p_eL2 = init_p_eL2 = d.h_scal[1];
+          if (!isfinite(p_eL2)) {
+            stop = 7;
+            kiter_adjust = 1;
+            break;
+          }
+          if (p_eL2 <= eps3) {
+            stop = 6;
+            kiter_adjust = 1;
+            break;
+          }
+          jacTe_inf = 0.0;
+          for (int i = 0; i < n; i++) {
+            double a = fabs(hjte[i]);
+            if (a > jacTe_inf) jacTe_inf = a;
+          }
+          p_L2 = nrm2sq(hp, n);
+          if (jacTe_inf <= eps1) {
+            Dp_L2 = 0.0;
+            stop = 1;
+            break;
+          }
+        }
         if (issolved && linsolv != 2) issolved = (hinfo[0] == 0 && hinfo[1] == 0) ? 1 : 0;
         if (issolved) {
           Dp_L2 = hsc[n];
@@ -631,7 +676,8 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       if (stop) break;
     }
   }
-  if (kiter >= itmax) stop = 3;
+  if (kiter >= itmax && !kiter_adjust) stop = 3;
+  kiter -= kiter_adjust;
   *nu_damp = nu;
   out->init_eL2 = init_p_eL2;
   out->eL2 = p_eL2;
@@ -668,7 +714,9 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
   // (sharded runs weight the residual share of the hidden data with beta, SAGE: d = f + beta r)
   const double beta = pr->world > 1 ? pr->beta : 1.0;
   db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 1, t0, t1, nullptr, beta);
-  const double c0 = db_read_scalar(pr, 1);
+  // ||e||^2 at entry stays on the device for now: lm_core fetches it together with p and J^T e
+  // (NaN = "still in d.scal[1]")
+  const double c0 = nan("");
   int nu = 2;
   bool ev;
   LmOut o;

@@ -368,6 +368,7 @@ void db_launch_vis_from_planar(const double2 *src, double2 *dst, long long R, cu
 int db_predict_nblocks(int ntile, int tilesz);
 void db_launch_predict_full(const PredictArgs *a, int ntile, cudaStream_t st);
 void db_launch_grad_full(const GradArgs *a, int ntile, cudaStream_t st);
+void db_launch_grad_tma(const GradArgs *a, int ntile, cudaStream_t st);
 int db_cluster_pass_nblocks(int ntile, int nt, int tslice);
 void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st);
 void db_launch_coh_gram(const GramArgs *a, int ntile, int nk, cudaStream_t st);

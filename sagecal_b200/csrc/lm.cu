@@ -66,13 +66,13 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.Tsub = dalloc<double>((size_t)d.Nbase * 16);
   w.JTJ0 = dalloc<double>((size_t)n8 * n8);
   w.JTJ = dalloc<double>((size_t)n8 * n8);
-  w.JTe = dalloc<double>(n8);
-  w.JTe_new = dalloc<double>(n8);
+  w.JTe = d.scal + 64 + n8;       // mailbox, see create_impl
+  w.JTe_new = d.scal + 64 + 2 * n8;
   w.Hst = dalloc<double>((size_t)4 * d.N);
-  w.Dp = dalloc<double>(n8);
+  w.Dp = d.scal + 64;
   w.pnew = dalloc<double>(n8);
   w.plast = dalloc<double>(n8);
-  w.devinfo = dalloc<int>(4);
+  w.devinfo = reinterpret_cast<int *>(d.scal + 64 + 3 * n8);
   w.tau = dalloc<double>(n8);
   w.svdS = w.svdU = w.svdVT = nullptr;
   w.wbuf = w.ebuf = nullptr;
@@ -125,9 +125,9 @@ static void robust_init(dirac_b200_problem *pr) {
 void db_lm_free(dirac_b200_problem *pr) {
   LMWork &w = pr->lm;
   if (!w.ready) return;
-  db_free(w.T); db_free(w.Tsub); db_free(w.JTJ0); db_free(w.JTJ); db_free(w.JTe);
-  db_free(w.JTe_new); db_free(w.Hst); db_free(w.Dp); db_free(w.pnew); db_free(w.plast);
-  db_free(w.devinfo); db_free(w.tau); db_free(w.cswork); db_free(w.dbuf);
+  db_free(w.T); db_free(w.Tsub); db_free(w.JTJ0); db_free(w.JTJ);
+  db_free(w.Hst); db_free(w.pnew); db_free(w.plast);
+  db_free(w.tau); db_free(w.cswork); db_free(w.dbuf);
   if (w.svdS) { db_free(w.svdS); db_free(w.svdU); db_free(w.svdVT); }
   if (w.wbuf) { db_free(w.wbuf); db_free(w.ebuf); db_free(w.HP); db_free(w.HQ); }
   if (w.JB) {
@@ -437,16 +437,17 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   DB_CHECK(cudaMemcpyAsync(hp, pblk_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
   if (have_first) {
     p_eL2 = first_cost;
-    if (!os)
-      DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-    if (std::isnan(first_cost))
-      DB_CHECK(cudaMemcpyAsync(d.h_scal + 1, d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost,
-                               d.stream));
     if (!defer) {
+      if (!os)
+        DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                                 d.stream));
+      if (std::isnan(first_cost))
+        DB_CHECK(cudaMemcpyAsync(d.h_scal + 2, d.scal + 2, sizeof(double), cudaMemcpyDeviceToHost,
+                                 d.stream));
       DB_CHECK(cudaStreamSynchronize(d.stream));
-      if (std::isnan(first_cost)) p_eL2 = d.h_scal[1];
+      if (std::isnan(first_cost)) p_eL2 = d.h_scal[2];
     } else {
-      p_eL2 = 1.0;  // placeholder until the first synchronisation
+      p_eL2 = 1.0;  // placeholder: J^T e and ||e||^2 (slot 2) come back with the first trial
     }
   } else {
     // e = wt.(d - f(p)), ||e||^2, J^T e     (clmfit.c:241-252 / robustlm.c:2235-2251)
@@ -565,14 +566,17 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       // adaptive damping loop (clmfit.c:356-540)
       while (1) {
         int issolved;
+        bool skip_info = false;
         if (use_factor) {
           // (J^T J + mu0 I) = L L^T came out of the batch: only the two triangular solves remain
           use_factor = false;
-          DB_CHECK(cudaMemsetAsync(w.devinfo, 0, 2 * sizeof(int), d.stream));
           db_prof_begin(5, 0.0, d.stream);
           if (w.own_chol && db_tri_available(n)) {
+            // no status of its own: the factor's status came back with the batch
+            skip_info = true;
             db_launch_tri_solve(w.LB + (size_t)slot * n * n, n, w.JTe, w.Dp, d.stream);
           } else {
+            DB_CHECK(cudaMemsetAsync(w.devinfo, 0, 2 * sizeof(int), d.stream));
             DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice,
                                      d.stream));
             CS_CHECK(cusolverDnDpotrs(w.cs, CUBLAS_FILL_MODE_LOWER, n, 1,
@@ -590,21 +594,24 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
                         wt);
         db_count_launch(1);
         int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
-        DB_CHECK(cudaMemcpyAsync(hinfo, w.devinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost,
-                                 d.stream));
-        DB_CHECK(cudaMemcpyAsync(hDp, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-        DB_CHECK(cudaMemcpyAsync(hsc + n, d.scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost,
-                                 d.stream));
-        DB_CHECK(cudaMemcpyAsync(hsc + n + 2, d.scal + 1, sizeof(double), cudaMemcpyDeviceToHost,
-                                 d.stream));
-        if (!os)
-          DB_CHECK(cudaMemcpyAsync(hjte_new, w.JTe_new, sizeof(double) * n, cudaMemcpyDeviceToHost,
-                                   d.stream));
+        DB_CHECK(cudaMemcpyAsync(d.h_scal, d.scal, sizeof(double) * (64 + 3 * n + 2),
+                                 cudaMemcpyDeviceToHost, d.stream));
         DB_CHECK(cudaStreamSynchronize(d.stream));
+        {
+          const double *hm = d.h_scal + 64;
+          memcpy(hDp, hm, sizeof(double) * n);
+          hsc[n] = d.h_scal[8];
+          hsc[n + 1] = d.h_scal[9];
+          hsc[n + 2] = d.h_scal[1];
+          if (!os) memcpy(hjte_new, hm + (w.JTe_new - w.Dp), sizeof(double) * n);
+          if (pending_entry) memcpy(hjte, hm + (w.JTe - w.Dp), sizeof(double) * n);
+          memcpy(hinfo, hm + 3 * n, 2 * sizeof(int));
+          if (skip_info) hinfo[0] = hinfo[1] = 0;
+        }
         if (pending_entry) {
           // the deferred entry tests, in the reference's order
           pending_entry = false;
-          p_eL2 = init_p_eL2 = d.h_scal[1];
+          p_eL2 = init_p_eL2 = d.h_scal[2];
           if (!isfinite(p_eL2)) {
             stop = 7;
             kiter_adjust = 1;
@@ -713,9 +720,9 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
   // the first func/jacf evaluation, clmfit.c:241-252)
   // (sharded runs weight the residual share of the hidden data with beta, SAGE: d = f + beta r)
   const double beta = pr->world > 1 ? pr->beta : 1.0;
-  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 1, t0, t1, nullptr, beta);
+  db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 2, t0, t1, nullptr, beta);
   // ||e||^2 at entry stays on the device for now: lm_core fetches it together with p and J^T e
-  // (NaN = "still in d.scal[1]")
+  // (NaN = "still in d.scal[2]")
   const double c0 = nan("");
   int nu = 2;
   bool ev;
@@ -880,6 +887,29 @@ extern "C" double dirac_b200_bench_predict(dirac_b200_problem *pr, int out_mode,
   for (int i = 0; i < 2; i++) db_predict_dev(pr, d.pp, pr->res, out_mode, 1, 0.0, 0);
   DB_CHECK(cudaEventRecord(e0, d.stream));
   for (int i = 0; i < reps; i++) db_predict_dev(pr, d.pp, pr->res, out_mode, 1, 0.0, 0);
+  DB_CHECK(cudaEventRecord(e1, d.stream));
+  DB_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 1e3 * ms / reps;
+}
+
+extern "C" void db_set_dbg_reduce(int v);
+extern "C" double dirac_b200_bench_grad(dirac_b200_problem *pr, int reps) {
+  DevProblem &d = pr->d;
+  if (reps < 0) {  // tuning: reps = -1-mode selects the reduction debug mode
+    db_set_dbg_reduce(-1 - reps);
+    return 0.0;
+  }
+  cudaEvent_t e0, e1;
+  DB_CHECK(cudaEventCreate(&e0));
+  DB_CHECK(cudaEventCreate(&e1));
+  db_predict_dev(pr, d.pp, pr->res, 1, 0, 0.0, 0);
+  for (int i = 0; i < 2; i++) db_grad_dev(pr, d.pp, pr->g, 0, 0.0);
+  DB_CHECK(cudaEventRecord(e0, d.stream));
+  for (int i = 0; i < reps; i++) db_grad_dev(pr, d.pp, pr->g, 0, 0.0);
   DB_CHECK(cudaEventRecord(e1, d.stream));
   DB_CHECK(cudaEventSynchronize(e1));
   float ms = 0.f;

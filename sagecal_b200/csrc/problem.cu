@@ -300,8 +300,11 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
   const int nb3 = db_stream_all_nblocks(Nbase, tilesz);
   pr->npartials = (nb1 > nb2 ? (nb1 > nb3 ? nb1 : nb3) : (nb2 > nb3 ? nb2 : nb3)) + 1024;  // also covers the fixed-grid reductions
   pr->partials = dev_alloc<double>(pr->npartials);
-  d.scal = dev_alloc<double>(64);
-  DB_CHECK(cudaMallocHost((void **)&d.h_scal, 64 * sizeof(double)));
+  // scalars [0,64) followed by the LM mailbox (step, J^T e at two points, solver status): everything
+  // the host needs after a trial comes back in ONE device-to-host copy
+  d.scal = dev_alloc<double>(64 + 3 * 8 * (size_t)N + 8);
+  DB_CHECK(cudaMemset(d.scal, 0, sizeof(double) * (64 + 3 * 8 * (size_t)N + 8)));
+  DB_CHECK(cudaMallocHost((void **)&d.h_scal, (64 + 3 * 8 * (size_t)N + 8) * sizeof(double)));
   d.counters = dev_alloc<unsigned int>(16);
   DB_CHECK(cudaMemset(d.counters, 0, 16 * sizeof(unsigned int)));
   pr->res = dev_alloc<double2>((size_t)4 * R);
@@ -442,7 +445,8 @@ void db_grad_dev(dirac_b200_problem *pr, const double *pp_dev, double *g_dev, in
   // robust g = +2 (f-d) df/(nu+(f-d)^2) (robust_lbfgs.c:286-299); here e = d-f
   a.scale = robust ? -2.0 : 2.0;
   db_prof_begin(1, (double)d.R * (64.0 * d.M + 65.0) + 64.0 * d.N * d.Mt, d.stream);
-  db_launch_grad_full(&a, d.ntile, d.stream);
+  if (db_use_tma()) db_launch_grad_tma(&a, d.ntile, d.stream);
+  else db_launch_grad_full(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
   db_count_launch(1);
   // sharded: every rank filled the blocks of its own clusters; the sum is the full gradient

@@ -342,6 +342,7 @@ struct AssembleArgs {
   double *JTJ;           // [8N][8N]
   double *Hst;           // [N][4] station sums (H00, H11, Re H01, Im H01), zeroed by the caller
   const TileDesc *tiles;
+  const short2 *blpq;    // [Nbase] (p,q) of baseline b
   int N, Nbase;
 };
 
@@ -355,6 +356,7 @@ struct BatchAssembleArgs {
   double *JTJ;           // [nb][8N][8N]
   double *Hst;           // [nb][N][4], zeroed by the caller
   const TileDesc *tiles;
+  const short2 *blpq;    // [Nbase] (p,q) of baseline b
   int N, Nbase;
 };
 

@@ -27,12 +27,12 @@ struct Gram {
 };
 
 
-__device__ __forceinline__ void assemble_tile(const AssembleArgs &a, const TileDesc td) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = td.pb * TILE_P + w;
-  const int q = td.qb * TILE_Q + lane;
-  if (!((q > p) && (q < a.N))) return;
-  const long long b = baseline_index(p, q, a.N);
+// One baseline's contribution to J^T J.  The 16 2x2 sub-blocks of the (p,q) coupling (and their
+// mirror images) are shared out over 16 threads (`sub`): each thread recomputes the few hundred flops
+// (indices stay static, everything in registers) and writes only its own 8 entries, so the scattered
+// stores of a baseline are spread over 16 threads and the grid has Nbase*16 threads instead of 13 CTAs.
+__device__ __forceinline__ void assemble_baseline(const AssembleArgs &a, int p, int q, long long b,
+                                                  int sub) {
   Gram G;
   {
     const double2 *Tb = reinterpret_cast<const double2 *>(a.T + b * 16);
@@ -62,6 +62,7 @@ __device__ __forceinline__ void assemble_tile(const AssembleArgs &a, const TileD
               double2 jj = cmul(Jq[2 * j + aa], Jp[2 * i + bb]);
               cfma(z, jj, G.at(2 * l + aa, 2 * bb + lp));
             }
+          if (sub != ((i * 2 + l) * 2 + j) * 2 + lp) continue;
           const int r0 = 8 * p + 2 * (2 * i + l);
           const int c0 = 8 * q + 2 * (2 * j + lp);
           // R(z) S = [[zr, zi],[zi, -zr]]
@@ -95,23 +96,32 @@ __device__ __forceinline__ void assemble_tile(const AssembleArgs &a, const TileD
       Hp[2 * l + lp] = hp;
       Hq[2 * l + lp] = hq;
     }
-  atomicAdd(a.Hst + 4 * p + 0, Hp[0].x);
-  atomicAdd(a.Hst + 4 * p + 1, Hp[3].x);
-  atomicAdd(a.Hst + 4 * p + 2, Hp[1].x);
-  atomicAdd(a.Hst + 4 * p + 3, Hp[1].y);
-  atomicAdd(a.Hst + 4 * q + 0, Hq[0].x);
-  atomicAdd(a.Hst + 4 * q + 1, Hq[3].x);
-  atomicAdd(a.Hst + 4 * q + 2, Hq[1].x);
-  atomicAdd(a.Hst + 4 * q + 3, Hq[1].y);
+  if (sub == 0) atomicAdd(a.Hst + 4 * p + 0, Hp[0].x);
+  if (sub == 1) atomicAdd(a.Hst + 4 * p + 1, Hp[3].x);
+  if (sub == 2) atomicAdd(a.Hst + 4 * p + 2, Hp[1].x);
+  if (sub == 3) atomicAdd(a.Hst + 4 * p + 3, Hp[1].y);
+  if (sub == 4) atomicAdd(a.Hst + 4 * q + 0, Hq[0].x);
+  if (sub == 5) atomicAdd(a.Hst + 4 * q + 1, Hq[3].x);
+  if (sub == 6) atomicAdd(a.Hst + 4 * q + 2, Hq[1].x);
+  if (sub == 7) atomicAdd(a.Hst + 4 * q + 3, Hq[1].y);
 }
 
-__global__ void __launch_bounds__(TILE_THREADS)
+// thread -> (baseline, sub-block): 16 consecutive threads share a baseline
+__device__ __forceinline__ void assemble_lin(const AssembleArgs &a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gid >> 4;
+  if (b >= a.Nbase) return;
+  const short2 pq = a.blpq[b];
+  assemble_baseline(a, pq.x, pq.y, b, (int)(gid & 15));
+}
+
+__global__ void __launch_bounds__(256)
 k_assemble_offdiag(AssembleArgs a) {
-  assemble_tile(a, a.tiles[blockIdx.x]);
+  assemble_lin(a);
 }
 
 // batched over clusters (blockIdx.y): all normal matrices of a SAGE sweep in one launch
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(256)
 k_assemble_offdiag_batched(BatchAssembleArgs b) {
   const int k = b.list[blockIdx.y];
   AssembleArgs a;
@@ -120,9 +130,10 @@ k_assemble_offdiag_batched(BatchAssembleArgs b) {
   a.JTJ = b.JTJ + (long long)blockIdx.y * 64 * b.N * b.N;
   a.Hst = b.Hst + (long long)blockIdx.y * 4 * b.N;
   a.tiles = b.tiles;
+  a.blpq = b.blpq;
   a.N = b.N;
   a.Nbase = b.Nbase;
-  assemble_tile(a, b.tiles[blockIdx.x]);
+  assemble_lin(a);
 }
 
 __device__ __forceinline__ void assemble_diag_station(const double *__restrict__ Hst,
@@ -213,14 +224,17 @@ __global__ void k_extract_diag(const double *__restrict__ A, double *__restrict_
 }
 
 // pnew = p + dp ; sc[0] = |dp|^2 ; sc[1] = dp . J^T e   (clmfit.c:440-449,487-497), one CTA
+// zero (optional): accumulator of the trial pass that follows, cleared here instead of by a memset
 __global__ void __launch_bounds__(512)
 k_lm_step(const double *__restrict__ p, const double *__restrict__ Dp,
-          const double *__restrict__ jte, double *__restrict__ pnew, double *__restrict__ sc, int n) {
+          const double *__restrict__ jte, double *__restrict__ pnew, double *__restrict__ sc,
+          double *__restrict__ zero, int n) {
   __shared__ double s0[16], s1[16];
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double dp = Dp[i];
     pnew[i] = p[i] + dp;
+    if (zero) zero[i] = 0.0;
     a = fma(dp, dp, a);
     b = fma(dp, jte[i], b);
   }
@@ -244,20 +258,22 @@ k_lm_step(const double *__restrict__ p, const double *__restrict__ Dp,
 
 extern "C" {
 void db_launch_lm_step(const double *p, const double *Dp, const double *jte, double *pnew,
-                       double *sc, int n, cudaStream_t st) {
-  k_lm_step<<<1, 512, 0, st>>>(p, Dp, jte, pnew, sc, n);
+                       double *sc, double *zero, int n, cudaStream_t st) {
+  k_lm_step<<<1, 512, 0, st>>>(p, Dp, jte, pnew, sc, zero, n);
 }
 void db_launch_extract_diag(const double *A, double *dst, int n, cudaStream_t st) {
   k_extract_diag<<<(n + 127) / 128, 128, 0, st>>>(A, dst, n);
 }
 void db_launch_assemble(const AssembleArgs *a, int ntile, cudaStream_t st) {
-  k_assemble_offdiag<<<ntile, TILE_THREADS, 0, st>>>(*a);
+  (void)ntile;
+  k_assemble_offdiag<<<(a->Nbase * 16 + 255) / 256, 256, 0, st>>>(*a);
   k_assemble_diag<<<(a->N + 63) / 64, 64, 0, st>>>(a->Hst, a->JTJ, a->N);
 }
 void db_launch_assemble_batched(const BatchAssembleArgs *b, int ntile, int nb, double tau,
                                 double *mu, double *Afac, cudaStream_t st) {
-  dim3 g1(ntile, nb);
-  k_assemble_offdiag_batched<<<g1, TILE_THREADS, 0, st>>>(*b);
+  (void)ntile;
+  dim3 g1((b->Nbase * 16 + 255) / 256, nb);
+  k_assemble_offdiag_batched<<<g1, 256, 0, st>>>(*b);
   dim3 g2((b->N + 63) / 64, nb);
   k_assemble_diag_batched<<<g2, 64, 0, st>>>(b->Hst, b->JTJ, b->N);
   k_batch_mu0<<<nb, 128, 0, st>>>(b->Hst, mu, b->N, tau);

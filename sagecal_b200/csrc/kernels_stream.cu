@@ -494,9 +494,11 @@ k_grad_tma(GradArgs a) {
 // per-cluster E-step pass (LM): one cluster, one hybrid chunk, timeslots [t_begin, t_end)
 // ------------------------------------------------------------------------------------------------
 
+// GRAD = false (ADD / SUB passes, ordered-subset trials): no W accumulator, about half the registers
+template <bool GRAD>
 __global__ void __launch_bounds__(TILE_THREADS)
 k_cluster_pass(ClusterPassArgs a) {
-  __shared__ double sq[TILE_P][8][TILE_Q];
+  __shared__ double sq[GRAD ? TILE_P : 1][8][TILE_Q];
   const TileDesc td = a.tiles[blockIdx.x];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = td.pb * TILE_P + w;
@@ -504,11 +506,11 @@ k_cluster_pass(ClusterPassArgs a) {
   const bool valid = (q > p) && (q < a.N);
   const int ts = a.t_begin + blockIdx.y * a.tslice;
   const int te = min(ts + a.tslice, a.t_end);
-  const bool want_grad = (a.jte != nullptr) && (a.mode <= 1);
+  constexpr bool want_grad = GRAD;
   double cost = 0.0;
-  double2 Jp[4], Jq[4], W[16];
+  double2 Jp[4], Jq[4], W[GRAD ? 16 : 1];
 #pragma unroll
-  for (int z = 0; z < 16; z++) W[z] = make_double2(0.0, 0.0);
+  for (int z = 0; z < (GRAD ? 16 : 1); z++) W[z] = make_double2(0.0, 0.0);
 #pragma unroll
   for (int c = 0; c < 4; c++) Jp[c] = Jq[c] = make_double2(0.0, 0.0);
   if (valid) {
@@ -575,11 +577,13 @@ k_cluster_pass(ClusterPassArgs a) {
             cost = fma(e[c].y, e[c].y, cost);
           }
         }
-        if (want_grad && !fl) accum_W(W, e, C);
+        if constexpr (GRAD) {
+          if (!fl) accum_W(W, e, C);
+        }
       }
     }
   }
-  if (want_grad) {
+  if constexpr (GRAD) {
     double2 Gp[4], Gq[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) Gp[c] = Gq[c] = make_double2(0.0, 0.0);
@@ -587,6 +591,145 @@ k_cluster_pass(ClusterPassArgs a) {
     tile_reduce_station_grad(Gp, Gq, a.jte, p, q, a.N, p < a.N - 1, sq, 1.0);
   }
   if (a.mode <= 1) grid_reduce_sum(cost, a.partials, a.cost, a.counter);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gradient-carrying passes (INIT, TRIAL), polarisation-split: two threads per baseline, thread h owns
+// row h of the 2x2 visibility (components 2h, 2h+1) and the half W[i=h] of the outer-product
+// accumulator.  Nothing is computed twice (row h of Jp C Jq^H needs only row h of Jp), the per-thread
+// state halves (W: 16 -> 8 complex), and a CTA carries 16 warps instead of 8: these passes run on
+// L2-resident data and are latency bound, so resident warps are what they need.
+// threadIdx.x = h*256 + w*32 + lane; p = pb*8 + w, q = qb*32 + lane.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(2 * TILE_THREADS)
+k_cluster_pass_split(ClusterPassArgs a) {
+  __shared__ double sq[2 * TILE_P][8][TILE_Q];
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int h = threadIdx.x >> 8, w = (threadIdx.x >> 5) & 7, lane = threadIdx.x & 31;
+  const int p = td.pb * TILE_P + w;
+  const int q = td.qb * TILE_Q + lane;
+  const bool valid = (q > p) && (q < a.N);
+  const int ts = a.t_begin + blockIdx.y * a.tslice;
+  const int te = min(ts + a.tslice, a.t_end);
+  double cost = 0.0;
+  double2 Jr[2], Jq[4], W[8];
+#pragma unroll
+  for (int z = 0; z < 8; z++) W[z] = make_double2(0.0, 0.0);
+  Jr[0] = Jr[1] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) Jq[c] = make_double2(0.0, 0.0);
+  if (valid) {
+    {
+      const double2 *jp = reinterpret_cast<const double2 *>(a.pblk + 8 * (long long)p + 4 * h);
+      Jr[0] = __ldg(jp);
+      Jr[1] = __ldg(jp + 1);
+    }
+    load_jones(a.pblk, q, Jq);
+    const long long b = baseline_index(p, q, a.N);
+    const long long c0 = (long long)(2 * h) * a.R, c1 = c0 + a.R;
+#pragma unroll 2
+    for (int t = ts; t < te; t++) {
+      const long long row = (long long)t * a.Nbase + b;
+      double2 C[4], v[2];
+#pragma unroll
+      for (int c = 0; c < 4; c++) C[c] = ld_stream(a.coh_k + (long long)c * a.R + row);
+      v[0] = ld_stream(a.in + c0 + row);
+      v[1] = ld_stream(a.in + c1 + row);
+      const bool fl = a.flag[row] != 0;
+      // row h of Jp C, then of (Jp C) Jq^H
+      const double2 T0 = cdot2(Jr[0], C[0], Jr[1], C[2]);
+      const double2 T1 = cdot2(Jr[0], C[1], Jr[1], C[3]);
+      double2 m[2];
+      m[0] = cdot2c(T0, Jq[0], T1, Jq[1]);
+      m[1] = cdot2c(T0, Jq[2], T1, Jq[3]);
+      if (fl) m[0] = m[1] = make_double2(0.0, 0.0);
+      double2 e[2];
+      if (a.mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const double2 d = cadd(make_double2(a.beta * v[j].x, a.beta * v[j].y), m[j]);
+          if (a.write_out) st_stream(a.out + (j ? c1 : c0) + row, d);
+          e[j] = csub(d, m[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          e[j] = csub(v[j], m[j]);
+          if (a.write_out) st_stream(a.out + (j ? c1 : c0) + row, e[j]);
+        }
+      }
+      if (a.wt) {
+        // robust LM: e <- wt.e for the cost, J^T (wt.(wt.e)) for the gradient
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const double2 wv = ld_stream(a.wt + (j ? c1 : c0) + row);
+          const double ex = wv.x * e[j].x, ey = wv.y * e[j].y;
+          cost = fma(ex, ex, cost);
+          cost = fma(ey, ey, cost);
+          e[j] = make_double2(wv.x * ex, wv.y * ey);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          cost = fma(e[j].x, e[j].x, cost);
+          cost = fma(e[j].y, e[j].y, cost);
+        }
+      }
+      if (!fl) {
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int lm = 0; lm < 4; lm++) cfmac(W[j * 4 + lm], e[j], C[lm]);
+      }
+    }
+  }
+  // contraction with the Jones: Gp row h complete, Gq partial (the other half adds its share below)
+  double2 Gp[2], Gq[4];
+  Gp[0] = Gp[1] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) Gq[c] = make_double2(0.0, 0.0);
+  if (valid) {
+#pragma unroll
+    for (int l = 0; l < 2; l++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int m = 0; m < 2; m++) cfma(Gp[l], Jq[2 * j + m], W[j * 4 + l * 2 + m]);
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+      for (int m = 0; m < 2; m++)
+#pragma unroll
+        for (int l = 0; l < 2; l++) cfmac(Gq[2 * j + m], Jr[l], W[j * 4 + l * 2 + m]);
+  }
+  // station p: butterfly over the lanes; 4 reals per half (components 4h .. 4h+3 of station p)
+  {
+    double vp[4];
+    vp[0] = warp_sum(Gp[0].x);
+    vp[1] = warp_sum(Gp[0].y);
+    vp[2] = warp_sum(Gp[1].x);
+    vp[3] = warp_sum(Gp[1].y);
+    if (p < a.N - 1 && lane < 4) {
+      double v = vp[0];
+#pragma unroll
+      for (int c = 1; c < 4; c++) v = (lane == c) ? vp[c] : v;
+      atomicAdd(a.jte + 8 * (long long)p + 4 * h + lane, v);
+    }
+  }
+  // station q: [half*8 + warp][component][lane] in smem, warp c of half 0 sums component c
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    sq[h * TILE_P + w][2 * c][lane] = Gq[c].x;
+    sq[h * TILE_P + w][2 * c + 1][lane] = Gq[c].y;
+  }
+  __syncthreads();
+  if (h == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < 2 * TILE_P; ww++) s += sq[ww][w][lane];
+    if (q < a.N && s != 0.0) atomicAdd(a.jte + 8 * (long long)q + w, s);
+  }
+  grid_reduce_sum(cost, a.partials, a.cost, a.counter);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -702,7 +845,12 @@ int db_cluster_pass_nblocks(int ntile, int nt, int tslice) { return ntile * ((nt
 void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st) {
   int nt = a->t_end - a->t_begin;
   dim3 grid(ntile, (nt + a->tslice - 1) / a->tslice);
-  k_cluster_pass<<<grid, TILE_THREADS, 0, st>>>(*a);
+  if (a->jte != nullptr && a->mode <= 1) {
+    static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
+    if (unsplit) k_cluster_pass<true><<<grid, TILE_THREADS, 0, st>>>(*a);
+    else k_cluster_pass_split<<<grid, 2 * TILE_THREADS, 0, st>>>(*a);
+  }
+  else k_cluster_pass<false><<<grid, TILE_THREADS, 0, st>>>(*a);
 }
 void db_launch_coh_gram(const GramArgs *a, int ntile, int nk, cudaStream_t st) {
   dim3 grid(ntile, nk);

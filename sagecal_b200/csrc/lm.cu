@@ -47,7 +47,7 @@ void db_launch_extract_diag(const double *A, double *dst, int n, cudaStream_t st
 void db_launch_assemble_batched(const BatchAssembleArgs *b, int ntile, int nb, double tau,
                                 double *mu, double *Afac, cudaStream_t st);
 void db_launch_lm_step(const double *p, const double *Dp, const double *jte, double *pnew,
-                       double *sc, int n, cudaStream_t st);
+                       double *sc, double *zero, int n, cudaStream_t st);
 }
 
 template <typename T>
@@ -158,12 +158,13 @@ static int pick_tslice(const DevProblem &d, int nt) {
 
 void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
                      double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
-                     int t1, const double2 *wt, double beta = 1.0, const double2 *in2 = nullptr);
+                     int t1, const double2 *wt, double beta = 1.0, const double2 *in2 = nullptr,
+                     bool jte_zeroed = false);
 
 // one streaming pass of cluster k over timeslots [t0,t1): see ClusterPassArgs for the modes
 void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
                      double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
-                     int t1, const double2 *wt, double beta, const double2 *in2) {
+                     int t1, const double2 *wt, double beta, const double2 *in2, bool jte_zeroed) {
   DevProblem &d = pr->d;
   if (t1 <= t0) {
     if (mode <= 1) DB_CHECK(cudaMemsetAsync(d.scal + cost_slot, 0, sizeof(double), d.stream));
@@ -176,7 +177,9 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   a.partials = pr->partials; a.cost = d.scal + cost_slot; a.counter = d.counters; a.R = d.R;
   a.N = d.N; a.Nbase = d.Nbase; a.t_begin = t0; a.t_end = t1; a.tslice = pick_tslice(d, t1 - t0);
   a.mode = mode; a.write_out = write_out; a.wt = wt; a.beta = beta; a.in2 = in2;
-  if (jte_dev && mode <= 1)
+  // passes without the gradient accumulator fit two CTAs per SM: twice as many, half as long
+  if (!(jte_dev && mode <= 1) && g_tslice_override <= 0 && a.tslice > 1) a.tslice = (a.tslice + 1) / 2;
+  if (jte_dev && mode <= 1 && !jte_zeroed)
     DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
   db_prof_begin(2, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
                                                  (wt ? 64.0 : 0.0)), d.stream);
@@ -204,7 +207,8 @@ static void assemble(dirac_b200_problem *pr, const double *T, const double *pblk
   LMWork &w = pr->lm;
   DB_CHECK(cudaMemsetAsync(w.Hst, 0, sizeof(double) * 4 * d.N, d.stream));
   AssembleArgs a;
-  a.T = T; a.pblk = pblk_dev; a.JTJ = JTJ; a.Hst = w.Hst; a.tiles = d.tiles; a.N = d.N;
+  a.T = T; a.pblk = pblk_dev; a.JTJ = JTJ; a.Hst = w.Hst; a.tiles = d.tiles; a.blpq = d.blpq;
+  a.N = d.N;
   a.Nbase = d.Nbase;
   db_prof_begin(4, 128.0 * d.Nbase + 8.0 * 64.0 * d.N * d.N, d.stream);
   db_launch_assemble(&a, d.ntile, d.stream);
@@ -364,14 +368,33 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
     DB_CHECK(cudaMemcpy(w.LBptr_dev, ptr.data(), sizeof(double *) * d.M, cudaMemcpyHostToDevice));
   }
   std::vector<int> list;
+  // Gram tensors still missing: one launch per run of consecutive single-chunk clusters (their slots
+  // are consecutive too), i.e. one launch for a sky without hybrid clusters
+  for (int k = 0; k < d.M;) {
+    const int tix = d.h_clus[k].chunk0;
+    if (d.h_clus[k].nchunk != 1 || w.T_valid[tix]) {
+      k++;
+      continue;
+    }
+    int k1 = k + 1;
+    while (k1 < d.M && d.h_clus[k1].nchunk == 1 && !w.T_valid[d.h_clus[k1].chunk0] &&
+           d.h_clus[k1].chunk0 == tix + (k1 - k))
+      k1++;
+    GramArgs a;
+    a.coh = d.coh; a.flag = d.flag; a.tiles = d.tiles; a.T = w.T + (size_t)tix * d.Nbase * 16;
+    a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.k0 = k; a.t_begin = 0; a.t_end = d.tilesz;
+    a.t_step = 1;
+    db_prof_begin(3, (double)(k1 - k) * ((double)d.tilesz * d.Nbase * 65.0 + 128.0 * d.Nbase),
+                  d.stream);
+    db_launch_coh_gram(&a, d.ntile, k1 - k, d.stream);
+    db_prof_end(d.stream);
+    db_count_launch(1);
+    for (int kk = k; kk < k1; kk++) w.T_valid[d.h_clus[kk].chunk0] = 1;
+    k = k1;
+  }
   for (int k = 0; k < d.M; k++) {
     w.pref_slot[k] = -1;
     if (d.h_clus[k].nchunk != 1) continue;
-    const int tix = d.h_clus[k].chunk0;
-    if (!w.T_valid[tix]) {
-      gram(pr, k, 0, d.tilesz, 1, w.T + (size_t)tix * d.Nbase * 16);
-      w.T_valid[tix] = 1;
-    }
     w.pref_slot[k] = (int)list.size();
     list.push_back(k);
   }
@@ -382,7 +405,7 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   DB_CHECK(cudaMemsetAsync(w.HB, 0, sizeof(double) * 4 * d.N * nb, d.stream));
   BatchAssembleArgs b;
   b.T = w.T; b.pp = d.pp; b.list = w.blist_dev; b.tix = w.btix_dev; b.poff = w.bpoff_dev;
-  b.JTJ = w.JB; b.Hst = w.HB; b.tiles = d.tiles; b.N = d.N; b.Nbase = d.Nbase;
+  b.JTJ = w.JB; b.Hst = w.HB; b.tiles = d.tiles; b.blpq = d.blpq; b.N = d.N; b.Nbase = d.Nbase;
   db_prof_begin(4, nb * (128.0 * d.Nbase + 8.0 * 64.0 * d.N * d.N), d.stream);
   db_launch_assemble_batched(&b, d.ntile, nb, tau, w.mu_dev, w.LB, d.stream);
   db_prof_end(d.stream);
@@ -589,9 +612,10 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           issolved = enqueue_solve(pr, mu, linsolv, eps1);
         }
         // p + dp, |dp|^2, dp.J^T e on the device; trial pass; everything back in one go
-        db_launch_lm_step(pblk_dev, w.Dp, w.JTe, w.pnew, d.scal + 8, n, d.stream);
+        db_launch_lm_step(pblk_dev, w.Dp, w.JTe, w.pnew, d.scal + 8, os ? nullptr : w.JTe_new, n,
+                          d.stream);
         db_cluster_pass(pr, k, w.pnew, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe_new, 1, t0, t1,
-                        wt);
+                        wt, 1.0, nullptr, true);
         db_count_launch(1);
         int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
         DB_CHECK(cudaMemcpyAsync(d.h_scal, d.scal, sizeof(double) * (64 + 3 * n + 2),
@@ -646,8 +670,9 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
             break;
           }
           // only now does the trial count as evaluated (the reference stops before evaluating it)
-          DB_CHECK(cudaMemcpyAsync(w.plast, w.pnew, sizeof(double) * n, cudaMemcpyDeviceToDevice,
-                                   d.stream));
+          if (wt)  // only the robust driver looks at the last evaluated point
+            DB_CHECK(cudaMemcpyAsync(w.plast, w.pnew, sizeof(double) * n, cudaMemcpyDeviceToDevice,
+                                     d.stream));
           *evaluated_trial = true;
           const double pDp_eL2 = hsc[n + 2];
           if (!isfinite(pDp_eL2)) {

@@ -45,6 +45,9 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
   const int m = (int)pr->d.npar;
   const long long n = (long long)d.Nbase * d.tilesz * 8;
   const ClusterDesc *hc = d.h_clus;
+  // every solve derives the Gram tensors of the coherencies afresh (nothing computed from the inputs
+  // of a previous call is reused, even when the same coherencies are still resident)
+  if (pr->lm.ready) memset(pr->lm.T_valid, 0, d.Mt);
   // CPU-path LM thresholds (lmfit.c:801)
   double opts[5] = {1e-3, 1e-15, 1e-15, 1e-20, -1e-6};
   double info[10];

@@ -77,3 +77,18 @@ def test_tri_solve_matches_numpy(n):
         pytest.skip("cluster size on this device too small for the solve-only kernel")
     ref = np.linalg.solve(A, b)
     assert np.max(np.abs(x - ref)) <= 1e-10 * np.max(np.abs(ref))
+
+
+def test_pivot_rsqrt_accuracy():
+    """The branch-free 1/sqrt of the pivot chain (hardware seed + one cubic correction)."""
+    api = blib.load()
+    L = api.lib
+    L.dirac_b200_test_rsqrt.restype = C.c_int
+    L.dirac_b200_test_rsqrt.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    x = np.concatenate([10.0 ** rng.uniform(-30, 30, 200000), rng.uniform(0.5, 4.0, 200000)])
+    y = np.zeros_like(x)
+    L.dirac_b200_test_rsqrt(x.size, x.ctypes.data, y.ctypes.data)
+    ref = 1.0 / np.sqrt(x.astype(np.longdouble))
+    rel = np.max(np.abs((y - ref) / ref).astype(np.float64))
+    assert rel <= 4 * np.finfo(np.float64).eps, rel

@@ -847,10 +847,14 @@ void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st
   dim3 grid(ntile, (nt + a->tslice - 1) / a->tslice);
   if (a->jte != nullptr && a->mode <= 1) {
     static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
+    // (a per-warp TMA ring was tried here and measured equal, 18.5 us: with 144 x 16 warps x 10 rows
+    //  x 6 runs of <= 512 B the pass is bound by the bulk-copy issue rate, ~1 per 32 clk per SM; see
+    //  DESIGN.md "what did not work")
     if (unsplit) k_cluster_pass<true><<<grid, TILE_THREADS, 0, st>>>(*a);
     else k_cluster_pass_split<<<grid, 2 * TILE_THREADS, 0, st>>>(*a);
+  } else {
+    k_cluster_pass<false><<<grid, TILE_THREADS, 0, st>>>(*a);
   }
-  else k_cluster_pass<false><<<grid, TILE_THREADS, 0, st>>>(*a);
 }
 void db_launch_coh_gram(const GramArgs *a, int ntile, int nk, cudaStream_t st) {
   dim3 grid(ntile, nk);

@@ -81,6 +81,8 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.pref_slot = (int *)malloc(sizeof(int) * d.M);
   for (int k = 0; k < d.M; k++) w.pref_slot[k] = -1;
   w.jtj0_cur = nullptr;
+  w.jtj_spec = nullptr;
+  DB_CHECK(cudaEventCreateWithFlags(&w.ev_mail, cudaEventDisableTiming));
   DB_CHECK(cudaMallocHost((void **)&w.h_vec, sizeof(double) * (5 * n8 + 4 * d.N + 64)));
   // library handles are process-wide (creating them costs tens of ms; the drop-in entry points
   // build and tear down a problem per call)
@@ -136,6 +138,7 @@ void db_lm_free(dirac_b200_problem *pr) {
     cudaFreeHost(w.h_mu); cudaFreeHost(w.h_binfo);
   }
   free(w.pref_slot);
+  cudaEventDestroy(w.ev_mail);
   cudaFreeHost(w.h_vec);
   free(w.T_valid);
   w.ready = false;
@@ -486,6 +489,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   double mu = 0.0, Dp_L2 = DBL_MAX, jacTe_inf = 0.0;
   *evaluated_trial = false;
   bool pending_entry = defer;  // entry values not on the host yet
+  w.jtj_spec = nullptr;
   int kiter_adjust = 0;
 
   // ordered subsets (clmfit.c:1313-1356)
@@ -552,7 +556,13 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           gram(pr, k, s0, s1, 1, w.Tsub);
           Tuse = w.Tsub;
         }
-        assemble(pr, Tuse, pblk_dev, w.JTJ0);
+        if (w.jtj_spec && !os) {
+          // already assembled at this point while the host was deciding on the previous trial
+          w.jtj0_cur = w.jtj_spec;
+          w.jtj_spec = nullptr;
+        } else {
+          assemble(pr, Tuse, pblk_dev, w.JTJ0);
+        }
         if (need_mx)
           DB_CHECK(cudaMemcpyAsync(hH, w.Hst, sizeof(double) * 4 * d.N, cudaMemcpyDeviceToHost,
                                    d.stream));
@@ -620,7 +630,19 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
         int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
         DB_CHECK(cudaMemcpyAsync(d.h_scal, d.scal, sizeof(double) * (64 + 3 * n + 2),
                                  cudaMemcpyDeviceToHost, d.stream));
-        DB_CHECK(cudaStreamSynchronize(d.stream));
+        // While the host waits for these results and decides, the GPU already assembles J^T J at the
+        // trial point into the buffer the current system does not occupy: if the step is accepted
+        // (the usual case) the next iteration finds its matrix ready, otherwise it is dropped.
+        double *spec_buf = nullptr;
+        if (w.own_chol && linsolv == 0 && !wt && !os && kiter + 1 < itmax && w.T_valid[tix]) {
+          const double *cur = w.jtj0_cur ? w.jtj0_cur : w.JTJ0;
+          spec_buf = (cur == w.JTJ0) ? w.JTJ : w.JTJ0;
+          DB_CHECK(cudaEventRecord(w.ev_mail, d.stream));
+          assemble(pr, Tfull, w.pnew, spec_buf);
+          DB_CHECK(cudaEventSynchronize(w.ev_mail));
+        } else {
+          DB_CHECK(cudaStreamSynchronize(d.stream));
+        }
         {
           const double *hm = d.h_scal + 64;
           memcpy(hDp, hm, sizeof(double) * n);
@@ -694,6 +716,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
               double *t = w.JTe; w.JTe = w.JTe_new; w.JTe_new = t;
             }
             p_eL2 = pDp_eL2;
+            w.jtj_spec = spec_buf;
             break;
           }
         }

@@ -21,6 +21,8 @@ struct LMWork {
   double *cswork;
   int lwork;
   bool own_chol;  // damped solves by the cluster Cholesky kernel (else cuSOLVER)
+  double *jtj_spec;       // J^T J assembled speculatively at the trial point (nullptr: none)
+  cudaEvent_t ev_mail;    // marks the trial results' copy; the host waits on it, not on the stream
   double *tau;            // QR
   double *svdS, *svdU, *svdVT;
   cusolverDnHandle_t cs;

@@ -120,49 +120,68 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 
 __device__ __forceinline__ int potf2_warp(double (&a)[32], double &myrd, double *cols, int lane) {
   int bad = 0;
-  // pivots of the current pair (software pipelined: those of the next pair are started as soon as
-  // columns k+2, k+3 are up to date, before the rest of the trailing update is issued)
-  double d0 = __shfl_sync(FULL, a[0], 0);
-  double e = __shfl_sync(FULL, a[0], 1);
-  double d1 = __shfl_sync(FULL, a[1], 1);
-  double num = fma(d1, d0, -e * e);
-  double r0 = fast_rsqrt(d0), rn = fast_rsqrt(num);
+  // Four columns per step: pivot pair (k, k+1) as described above; columns k+2, k+3 then receive its
+  // rank-2 update straight from registers (four shuffles), so the second pivot pair (k+2, k+3) starts
+  // without a trip through shared memory; only then are the four finished columns published and the
+  // rest of the block updated once (rank 4).  Halves the per-column share of the smem round trip and
+  // of the trailing-update issue time on the chain.
 #pragma unroll
-  for (int k = 0; k < 32; k += 2) {
+  for (int k = 0; k < 32; k += 4) {
+    // ---- pair A
+    const double d0 = __shfl_sync(FULL, a[k], k);
+    const double e = __shfl_sync(FULL, a[k], k + 1);
+    const double d1 = __shfl_sync(FULL, a[k + 1], k + 1);
+    const double num = fma(d1, d0, -e * e);
     if (!bad) {
       if (!(d0 > 0.0)) bad = k + 1;
       else if (!(num > 0.0)) bad = k + 2;
     }
+    const double r0 = fast_rsqrt(d0), rn = fast_rsqrt(num);
     const double r1 = rn * (d0 * r0);
     const double l0 = a[k] * r0;
-    const double l10 = e * r0;
-    const double l1 = fma(-l0, l10, a[k + 1]) * r1;
+    const double l1 = fma(-l0, e * r0, a[k + 1]) * r1;
     a[k] = l0;
     a[k + 1] = l1;
     if (lane == k) myrd = r0;
     if (lane == k + 1) myrd = r1;
-    if (k < 30) {
+    // ---- rank-2 update of columns k+2, k+3 from registers
+    {
+      const double l0_2 = __shfl_sync(FULL, l0, k + 2), l1_2 = __shfl_sync(FULL, l1, k + 2);
+      const double l0_3 = __shfl_sync(FULL, l0, k + 3), l1_3 = __shfl_sync(FULL, l1, k + 3);
+      a[k + 2] = fma(-l1, l1_2, fma(-l0, l0_2, a[k + 2]));
+      a[k + 3] = fma(-l1, l1_3, fma(-l0, l0_3, a[k + 3]));
+    }
+    // ---- pair B
+    const double f0 = __shfl_sync(FULL, a[k + 2], k + 2);
+    const double g = __shfl_sync(FULL, a[k + 2], k + 3);
+    const double f1 = __shfl_sync(FULL, a[k + 3], k + 3);
+    const double numb = fma(f1, f0, -g * g);
+    if (!bad) {
+      if (!(f0 > 0.0)) bad = k + 3;
+      else if (!(numb > 0.0)) bad = k + 4;
+    }
+    const double s0 = fast_rsqrt(f0), sn = fast_rsqrt(numb);
+    const double s1 = sn * (f0 * s0);
+    const double l2 = a[k + 2] * s0;
+    const double l3 = fma(-l2, g * s0, a[k + 3]) * s1;
+    a[k + 2] = l2;
+    a[k + 3] = l3;
+    if (lane == k + 2) myrd = s0;
+    if (lane == k + 3) myrd = s1;
+    if (k < 28) {
       cols[k * 32 + lane] = l0;
       cols[(k + 1) * 32 + lane] = l1;
+      cols[(k + 2) * 32 + lane] = l2;
+      cols[(k + 3) * 32 + lane] = l3;
       __syncwarp();
-      {
-        const double2 c0 = lds_v2(reinterpret_cast<const double2 *>(cols + k * 32 + k + 2));
-        const double2 c1 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 1) * 32 + k + 2));
-        a[k + 2] = fma(-l1, c1.x, fma(-l0, c0.x, a[k + 2]));
-        a[k + 3] = fma(-l1, c1.y, fma(-l0, c0.y, a[k + 3]));
-      }
-      d0 = __shfl_sync(FULL, a[k + 2], k + 2);
-      e = __shfl_sync(FULL, a[k + 2], k + 3);
-      d1 = __shfl_sync(FULL, a[k + 3], k + 3);
-      num = fma(d1, d0, -e * e);
-      r0 = fast_rsqrt(d0);
-      rn = fast_rsqrt(num);
 #pragma unroll
       for (int m = k + 4; m < 32; m += 2) {
         const double2 c0 = lds_v2(reinterpret_cast<const double2 *>(cols + k * 32 + m));
         const double2 c1 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 1) * 32 + m));
-        a[m] = fma(-l1, c1.x, fma(-l0, c0.x, a[m]));
-        a[m + 1] = fma(-l1, c1.y, fma(-l0, c0.y, a[m + 1]));
+        const double2 c2 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 2) * 32 + m));
+        const double2 c3 = lds_v2(reinterpret_cast<const double2 *>(cols + (k + 3) * 32 + m));
+        a[m] = fma(-l3, c3.x, fma(-l2, c2.x, fma(-l1, c1.x, fma(-l0, c0.x, a[m]))));
+        a[m + 1] = fma(-l3, c3.y, fma(-l2, c2.y, fma(-l1, c1.y, fma(-l0, c0.y, a[m + 1]))));
       }
     }
   }
@@ -385,7 +404,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
         for (int k = 0; k < 32; k++) c[k] = coopC[k * 32 + lane];
         __syncwarp();
         const int bad = potf2_warp(c, myrd, Bs, lane);
-          wrd[J1 * 32 + lane] = myrd;
+        wrd[J1 * 32 + lane] = myrd;
         if (bad && lane == 0) atomicCAS(p.info, 0, J1 * 32 + bad);
         store_rows(c, ws + (size_t)(J1 * 32) * ld + J1 * 32, ld, lane);
         }

@@ -409,7 +409,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
         store_rows(c, ws + (size_t)(J1 * 32) * ld + J1 * 32, ld, lane);
         }
     }
-    for (int t = g; t < T; t += G) {
+    // generic items: CTA 0 keeps its SM for the diagonal block (the other CL-1 CTAs share items 1..)
+    const bool solo = (j >= 0 && CL > 1);
+    const int gu = solo ? (crank == 0 ? T : 1 + w * (CL - 1) + (crank - 1)) : g;
+    const int Gu = solo ? (CL - 1) * CH_WARPS : G;
+    for (int t = gu; t < T; t += Gu) {
       if (t == 0 && j >= 0) continue;  // done above
       int u = 0;
       while ((u + 1) * (u + 2) / 2 <= t) u++;

@@ -87,3 +87,30 @@ def test_index_helpers_bit_exact(api, ref):
         lib.preset_flags_and_data(flag.copy(), barr, x)
         res.append((barr_to_numpy(barr, n)[2], x))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("switch", ["DIRAC_B200_CUSOLVER", "DIRAC_B200_NO_TMA", "DIRAC_B200_CP_UNSPLIT"])
+def test_alternate_paths_agree(api, switch):
+    """The library fallbacks (cuSOLVER instead of the cluster Cholesky, register-staged instead of
+    TMA-fed kernels, unsplit gradient pass) solve the same problem to the same Jones: they differ in
+    summation order only."""
+    import json
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fallback_check.py")
+
+    def run(env_extra):
+        env = dict(os.environ)
+        for k in ("DIRAC_B200_CUSOLVER", "DIRAC_B200_NO_TMA", "DIRAC_B200_CP_UNSPLIT"):
+            env.pop(k, None)
+        env.update(env_extra)
+        out = subprocess.run([sys.executable, script], env=env, capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    base = run({})
+    alt = run({switch: "1"})
+    assert relerr(np.array(alt["pp"]), np.array(base["pp"])) < 1e-7
+    assert abs(alt["r"][3] - base["r"][3]) <= 1e-7 * base["r"][3]

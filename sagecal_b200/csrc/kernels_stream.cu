@@ -490,6 +490,199 @@ k_grad_tma(GradArgs a) {
   }
 }
 
+// sums of four values over the warp with 6 double shuffles instead of 20: halves of the warp trade
+// the values they do not keep.  Lane 8*c (c = 0..3) ends up with the warp sum of v[c].
+__device__ __forceinline__ double warp_reduce4(double v0, double v1, double v2, double v3, int lane) {
+  const bool hi = (lane & 16) != 0;
+  double k0 = hi ? v2 : v0, k1 = hi ? v3 : v1;
+  k0 += __shfl_xor_sync(0xffffffffu, hi ? v0 : v2, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, hi ? v1 : v3, 16);
+  const bool h8 = (lane & 8) != 0;
+  double kk = h8 ? k1 : k0;
+  kk += __shfl_xor_sync(0xffffffffu, h8 ? k0 : k1, 8);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+  kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+  return kk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_grad_tma with the polarisation split of k_cluster_pass_split: two threads per baseline, thread h
+// owns row h of the residual and the half W[i=h] of the accumulator.  16 warps per CTA share the 8
+// TMA rings (the two warps of a station p consume the same stages; warp h=0 is the producer, the CTA
+// barriers of the per-cluster reduction make a consumed stage reusable).
+// threadIdx.x = h*256 + w*32 + lane.
+// ------------------------------------------------------------------------------------------------
+template <int TB, int NST>
+__global__ void __launch_bounds__(2 * TILE_THREADS)
+k_grad_tma_split(GradArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int STAGE_ELEMS = TB * 4 * 32;  // double2 per stage
+  double (*sq)[8][TILE_Q] = reinterpret_cast<double (*)[8][TILE_Q]>(smem_raw);
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw + sizeof(double) * 2 * TILE_P * 8 * TILE_Q);
+  unsigned long long *bars =
+      reinterpret_cast<unsigned long long *>(ring + (size_t)TILE_P * NST * STAGE_ELEMS);
+  const TileDesc td = a.tiles[blockIdx.x];
+  const int h = threadIdx.x >> 8, w = (threadIdx.x >> 5) & 7, lane = threadIdx.x & 31;
+  const int p = td.pb * TILE_P + w;
+  const int q0 = td.qb * TILE_Q;
+  const int q = q0 + lane;
+  const bool valid = (q > p) && (q < a.N);
+  const int t0 = blockIdx.y * TB;
+  const int nrows = min(TB, a.tilesz - t0);
+  const int qs = max(q0, p + 1);
+  const int nv = max(0, min(q0 + TILE_Q, a.N) - qs);
+  const long long b0 = nv > 0 ? baseline_index(p, qs, a.N) : 0;
+  const int el = q - qs;
+  const long long b = valid ? b0 + el : 0;
+  double2 *my_stage = ring + (size_t)w * NST * STAGE_ELEMS;
+  unsigned long long *my_bar = bars + w * NST;
+  if (h == 0 && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++) mbar_init(&my_bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k, int s) {
+    const unsigned row_bytes = (unsigned)nv * 16u;
+    mbar_expect_tx(&my_bar[s], (unsigned)nrows * 4u * row_bytes);
+    const double2 *ck = a.coh + (long long)k * 4 * a.R + (long long)t0 * a.Nbase + b0;
+    double2 *dst = my_stage + (size_t)s * STAGE_ELEMS;
+    for (int i = 0; i < nrows; i++)
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        bulk_g2s(dst + (i * 4 + c) * 32, ck + (long long)c * a.R + (long long)i * a.Nbase, row_bytes,
+                 &my_bar[s]);
+  };
+  const bool producer = (h == 0 && lane == 0 && nv > 0);
+  if (producer) {
+#pragma unroll
+    for (int s = 0; s < NST - 1; s++)
+      if (s < a.M) issue(s, s);
+  }
+
+  double2 Rm[TB][2];
+  bool use[TB];
+#pragma unroll
+  for (int i = 0; i < TB; i++) {
+    const int t = t0 + i;
+    const long long row = (long long)(t < a.tilesz ? t : a.tilesz - 1) * a.Nbase + b;
+    use[i] = valid && (t < a.tilesz) && (a.flag[row] == 0);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      double2 e = make_double2(0.0, 0.0);
+      if (use[i]) {
+        e = ld_stream(a.res + (long long)(2 * h + j) * a.R + row);
+        if (a.robust) {
+          e.x = e.x / (a.nu + e.x * e.x);
+          e.y = e.y / (a.nu + e.y * e.y);
+        }
+      }
+      Rm[i][j] = e;
+    }
+  }
+  for (int k = 0; k < a.M; k++) {
+    const int s = k % NST;
+    // stage (k-1)%NST was consumed in iteration k-1 by both warps of this p: its closing CTA barrier
+    // has been passed, so the producer may refill it
+    if (producer && k + NST - 1 < a.M) issue(k + NST - 1, (k + NST - 1) % NST);
+    const ClusterDesc cd = a.clus[k];
+    const int tpc = (a.tilesz + cd.nchunk - 1) / cd.nchunk;
+    if (nv > 0) mbar_wait(&my_bar[s], (unsigned)((k / NST) & 1));
+    const double2 *st = my_stage + (size_t)s * STAGE_ELEMS;
+    int i0 = 0;
+    while (i0 < TB) {  // runs of timeslots that share a chunk (one run unless hybrid)
+      int chunk = 0, i1 = TB;
+      double2 W[8];
+#pragma unroll
+      for (int z = 0; z < 8; z++) W[z] = make_double2(0.0, 0.0);
+      if (cd.nchunk == 1) {
+        // the common case: no chunk bookkeeping at all
+#pragma unroll
+        for (int i = 0; i < TB; i++) {
+          if (use[i]) {
+            double2 C[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) C[c] = lds_v2(st + (i * 4 + c) * 32 + el);
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+              for (int lm = 0; lm < 4; lm++) cfmac(W[j * 4 + lm], Rm[i][j], C[lm]);
+          }
+        }
+      } else {
+        chunk = (t0 + i0 < a.tilesz ? t0 + i0 : a.tilesz - 1) / tpc;
+        i1 = i0;
+#pragma unroll
+        for (int i = 0; i < TB; i++) {
+          if (i >= i0 && i == i1) {
+            const int t = t0 + i;
+            const int ch = (t < a.tilesz ? t : a.tilesz - 1) / tpc;
+            if (ch == chunk) {
+              i1 = i + 1;
+              if (use[i]) {
+                double2 C[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) C[c] = lds_v2(st + (i * 4 + c) * 32 + el);
+#pragma unroll
+                for (int j = 0; j < 2; j++)
+#pragma unroll
+                  for (int lm = 0; lm < 4; lm++) cfmac(W[j * 4 + lm], Rm[i][j], C[lm]);
+              }
+            }
+          }
+        }
+      }
+      double *gblk = a.g + a.chunk_poff[cd.chunk0 + chunk];
+      double2 Gp[2], Gq[4];
+      Gp[0] = Gp[1] = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int c = 0; c < 4; c++) Gq[c] = make_double2(0.0, 0.0);
+      if (valid) {
+        const double *pblk = a.pp + a.chunk_poff[cd.chunk0 + chunk];
+        double2 Jr[2], Jq[4];
+        const double2 *jp = reinterpret_cast<const double2 *>(pblk + 8 * (long long)p + 4 * h);
+        Jr[0] = __ldg(jp);
+        Jr[1] = __ldg(jp + 1);
+        load_jones(pblk, q, Jq);
+#pragma unroll
+        for (int l = 0; l < 2; l++)
+#pragma unroll
+          for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int m = 0; m < 2; m++) cfma(Gp[l], Jq[2 * j + m], W[j * 4 + l * 2 + m]);
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+          for (int m = 0; m < 2; m++)
+#pragma unroll
+            for (int l = 0; l < 2; l++) cfmac(Gq[2 * j + m], Jr[l], W[j * 4 + l * 2 + m]);
+      }
+      // station p: 4 reals per half (components 4h .. 4h+3), lane 8c holds component c
+      {
+        const double v = warp_reduce4(Gp[0].x, Gp[0].y, Gp[1].x, Gp[1].y, lane);
+        if (p < a.N - 1 && (lane & 7) == 0)
+          atomicAdd(gblk + 8 * (long long)p + 4 * h + (lane >> 3), a.scale * v);
+      }
+      // station q: sum over the 16 warps through shared memory
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        sq[h * TILE_P + w][2 * c][lane] = Gq[c].x;
+        sq[h * TILE_P + w][2 * c + 1][lane] = Gq[c].y;
+      }
+      __syncthreads();
+      if (h == 0) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int ww = 0; ww < 2 * TILE_P; ww++) sacc += sq[ww][w][lane];
+        if (q < a.N && sacc != 0.0) atomicAdd(gblk + 8 * (long long)q + w, a.scale * sacc);
+      }
+      __syncthreads();
+      i0 = i1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // per-cluster E-step pass (LM): one cluster, one hybrid chunk, timeslots [t_begin, t_end)
 // ------------------------------------------------------------------------------------------------
@@ -783,6 +976,19 @@ k_coh_gram(GramArgs a) {
 // host-side launchers
 // ------------------------------------------------------------------------------------------------
 template <int TB, int NST>
+static void launch_grad_tma_split(const GradArgs *a, int ntile, cudaStream_t st) {
+  const size_t smem = sizeof(double) * 2 * TILE_P * 8 * TILE_Q +
+                      (size_t)TILE_P * NST * TB * 4 * 32 * sizeof(double2) + TILE_P * NST * 8;
+  static bool configured = false;
+  if (!configured) {
+    DB_CHECK(cudaFuncSetAttribute(k_grad_tma_split<TB, NST>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(ntile, (a->tilesz + TB - 1) / TB);
+  k_grad_tma_split<TB, NST><<<grid, 2 * TILE_THREADS, smem, st>>>(*a);
+}
+template <int TB, int NST>
 static void launch_grad_tma(const GradArgs *a, int ntile, cudaStream_t st) {
   const size_t smem = sizeof(double) * TILE_P * 8 * TILE_Q +
                       (size_t)TILE_P * NST * TB * 4 * 32 * sizeof(double2) + TILE_P * NST * 8;
@@ -829,6 +1035,11 @@ void db_launch_grad_full(const GradArgs *a, int ntile, cudaStream_t st) {
 void db_set_dbg_reduce(int v) { cudaMemcpyToSymbol(g_dbg_reduce, &v, sizeof(int)); }
 void db_launch_grad_tma(const GradArgs *a, int ntile, cudaStream_t st) {
   static int cfg = -1;
+  static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
+  if (!unsplit) {
+    launch_grad_tma_split<4, 2>(a, ntile, st);
+    return;
+  }
   if (cfg < 0) {
     const char *e = getenv("DIRAC_B200_GRAD_CFG");
     cfg = e ? atoi(e) : 0;

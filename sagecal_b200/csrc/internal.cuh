@@ -381,6 +381,7 @@ int db_chol_max_n();
 int db_chol_available();
 size_t db_chol_ws_doubles(int n);
 int db_tri_available(int n);
+void db_chol_set_step(const double *pcur, double *pnew, double *sc, double *zero);
 void db_launch_tri_solve(const double *L, int n, const double *b, double *x, cudaStream_t st);
 void db_launch_chol_solve(const double *A, int n, double mu, const double *b, double *x, double *ws,
                           int *info, cudaStream_t st);

@@ -31,6 +31,14 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif
 constexpr unsigned long long X_PENDING = 0xFFF8DEADBEEF0001ull;
 
+// optional epilogue of both solver kernels: the LM trial point and its scalars (k_lm_step fused in)
+struct StepArgs {
+  const double *pcur;  // current parameters (nullptr: no epilogue)
+  double *pnew;        // pcur + x
+  double *sc;          // sc[0] = |x|^2, sc[1] = x . b
+  double *zero;        // vector to clear (accumulator of the trial pass), may be null
+};
+
 struct CholArgs {
   const double *A;  // n x n symmetric, lower triangle read (column-major, ld = n)
   const double *b;  // right-hand side (n)
@@ -40,6 +48,7 @@ struct CholArgs {
   double mu;
   int n, nblk;
   long long *ts;  // optional phase timestamps (globaltimer ns), tuning only
+  StepArgs st;
 };
 
 // release/acquire at cluster scope orders the workspace stores (L2) before the other CTAs' .cg loads
@@ -280,6 +289,47 @@ __device__ __forceinline__ double dot32(const double (&a)[32], const double *v) 
     s3 = fma(a[m + 3], v1.y, s3);
   }
   return (s0 + s1) + (s2 + s3);
+}
+
+// CTA 0: collect the solution from the arrival slots, store it, and (LM) form the trial point
+// p + x with |x|^2 and x.b (clmfit.c:440-449,487-497) — what used to be a kernel of its own.
+__device__ __forceinline__ void solution_epilogue(const double *xs, double *x, const double *b, int n,
+                                                  const StepArgs &st, double *red) {
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = threadIdx.x; i < n; i += CH_THREADS) {
+    const unsigned addr = smem_u32(xs + i);
+    unsigned long long bits;
+    do {
+      asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
+    } while (bits == X_PENDING);
+    const double xv = __longlong_as_double((long long)bits);
+    x[i] = xv;
+    if (st.pcur) {
+      st.pnew[i] = st.pcur[i] + xv;
+      s0 = fma(xv, xv, s0);
+      s1 = fma(xv, b[i], s1);
+      if (st.zero) st.zero[i] = 0.0;
+    }
+  }
+  if (st.pcur) {
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      red[w] = s0;
+      red[CH_WARPS + w] = s1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int i = 0; i < CH_WARPS; i++) {
+        t0 += red[i];
+        t1 += red[CH_WARPS + i];
+      }
+      st.sc[0] = t0;
+      st.sc[1] = t1;
+    }
+  }
 }
 
 // y_j = L_jj^-1 b_j by one warp (L_jj staged column-major in Ls): the forward solve of block j
@@ -574,16 +624,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
       __syncthreads();
     }
   }
-  if (crank == 0) {
-    for (int i = threadIdx.x; i < p.n; i += CH_THREADS) {
-      const unsigned addr = smem_u32(xs + i);
-      unsigned long long bits;
-      do {
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
-      } while (bits == X_PENDING);
-      p.x[i] = __longlong_as_double((long long)bits);
-    }
-  }
+  if (crank == 0) solution_epilogue(xs, p.x, p.b, p.n, p.st, partial);
   // nobody leaves while a neighbour may still be writing into its shared memory
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
@@ -603,6 +644,7 @@ struct TriArgs {
   const double *b;
   double *x;
   int n, nblk;
+  StepArgs st;
 };
 
 __device__ __forceinline__ double l_elem(const TriArgs &p, int r, int c) {
@@ -793,16 +835,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_tri_solve(TriArgs p) {
       __syncthreads();
     }
   }
-  if (crank == 0) {
-    for (int i = threadIdx.x; i < p.n; i += CH_THREADS) {
-      const unsigned addr = smem_u32(xs + i);
-      unsigned long long bits;
-      do {
-        asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(bits) : "r"(addr) : "memory");
-      } while (bits == X_PENDING);
-      p.x[i] = __longlong_as_double((long long)bits);
-    }
-  }
+  if (crank == 0) solution_epilogue(xs, p.x, p.b, p.n, p.st, partial);
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -875,10 +908,16 @@ int db_chol_available() {
 
 // (A + mu I) x = b, n <= db_chol_max_n().  ws: db_chol_ws_doubles(n) doubles.  info: device int.
 static long long *g_ts = nullptr;
+static StepArgs g_step = {nullptr, nullptr, nullptr, nullptr};
+// the next solver launches also form pnew = pcur + x, sc[0..1], and clear `zero` (pcur == nullptr: off)
+void db_chol_set_step(const double *pcur, double *pnew, double *sc, double *zero) {
+  g_step.pcur = pcur; g_step.pnew = pnew; g_step.sc = sc; g_step.zero = zero;
+}
 void db_launch_chol_solve(const double *A, int n, double mu, const double *b, double *x, double *ws,
                           int *info, cudaStream_t st) {
   CholArgs p;
   p.ts = g_ts;
+  p.st = g_step;
   p.A = A; p.b = b; p.x = x; p.ws = ws; p.info = info; p.mu = mu; p.n = n; p.nblk = (n + 31) / 32;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g_cluster);
@@ -906,6 +945,7 @@ int db_tri_available(int n) {
 void db_launch_tri_solve(const double *L, int n, const double *b, double *x, cudaStream_t st) {
   TriArgs p;
   p.L = L; p.b = b; p.x = x; p.n = n; p.nblk = (n + 31) / 32;
+  p.st = g_step;
   static bool configured = false;
   if (!configured) {
     size_t mx = tri_smem(16, g_cluster);

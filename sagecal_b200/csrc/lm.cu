@@ -272,6 +272,7 @@ static int enqueue_solve(dirac_b200_problem *pr, double mu, int linsolv, double 
                          d.stream);
     db_prof_end(d.stream);
     db_count_launch(1);
+    w.step_fused = w.step_armed;  // the kernel's epilogue formed the trial point (db_chol_set_step)
     return 1;
   }
   db_launch_copy_add_diag(w.jtj0_cur ? w.jtj0_cur : w.JTJ0, w.JTJ, n, mu, d.stream);
@@ -600,6 +601,12 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       while (1) {
         int issolved;
         bool skip_info = false;
+        // the cluster solvers form p + dp, |dp|^2, dp.J^T e themselves and clear the trial pass's
+        // accumulator (solution_epilogue, kernels_chol.cu); other solvers leave it to k_lm_step
+        w.step_fused = false;
+        w.step_armed = w.own_chol && linsolv == 0;
+        if (w.step_armed)
+          db_chol_set_step(pblk_dev, w.pnew, d.scal + 8, os ? nullptr : w.JTe_new);
         if (use_factor) {
           // (J^T J + mu0 I) = L L^T came out of the batch: only the two triangular solves remain
           use_factor = false;
@@ -608,6 +615,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
             // no status of its own: the factor's status came back with the batch
             skip_info = true;
             db_launch_tri_solve(w.LB + (size_t)slot * n * n, n, w.JTe, w.Dp, d.stream);
+            w.step_fused = w.step_armed;
           } else {
             DB_CHECK(cudaMemsetAsync(w.devinfo, 0, 2 * sizeof(int), d.stream));
             DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice,
@@ -622,11 +630,13 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           issolved = enqueue_solve(pr, mu, linsolv, eps1);
         }
         // p + dp, |dp|^2, dp.J^T e on the device; trial pass; everything back in one go
-        db_launch_lm_step(pblk_dev, w.Dp, w.JTe, w.pnew, d.scal + 8, os ? nullptr : w.JTe_new, n,
-                          d.stream);
+        if (w.step_armed) db_chol_set_step(nullptr, nullptr, nullptr, nullptr);
+        if (!w.step_fused)
+          db_launch_lm_step(pblk_dev, w.Dp, w.JTe, w.pnew, d.scal + 8, os ? nullptr : w.JTe_new, n,
+                            d.stream);
         db_cluster_pass(pr, k, w.pnew, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe_new, 1, t0, t1,
                         wt, 1.0, nullptr, true);
-        db_count_launch(1);
+        if (!w.step_fused) db_count_launch(1);  // k_lm_step
         int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
         DB_CHECK(cudaMemcpyAsync(d.h_scal, d.scal, sizeof(double) * (64 + 3 * n + 2),
                                  cudaMemcpyDeviceToHost, d.stream));

@@ -11,7 +11,10 @@ gradient passes).  Units per step = rows x clusters x (SAGE sweeps + LBFGS gradi
 actually performed): every baseline-visibility of every direction goes through predict + Jacobian
 once per sweep.  `value` = units / time on resident data, `e2e` = the same solve through the
 drop-in C entry point `sagefit_visibilities` with pinned HOST buffers (upload of coherencies and
-data, download of residual and Jones inside the timed region).
+data, download of residual and Jones inside the timed region).  The K timed steps run without any
+per-kernel instrumentation; the same K steps are then repeated with a CUDA-event pair around every
+kernel of the path, which is where `roofline` (dominant streaming kernel) and `roofline.solver` /
+`roofline.kernels` (shares of the step) come from.
 
 Prints ONE JSON line on rank 0.
 """

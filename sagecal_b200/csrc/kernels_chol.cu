@@ -263,12 +263,24 @@ __host__ __device__ inline size_t tri_tiles(int nblk, int cl) {
 __device__ __forceinline__ void load_rows_A(double (&a)[32], const CholArgs &p, int I, int K,
                                             int lane) {
   const int r = I * 32 + lane;
+  if (I * 32 + 32 <= p.n && K * 32 + 32 <= p.n) {
+    // interior block: 32 independent coalesced loads, no guards
+    const double *base = p.A + (size_t)(K * 32) * p.n + r;
+#pragma unroll
+    for (int c = 0; c < 32; c++) a[c] = __ldg(base + (size_t)c * p.n);
+    if (I == K) {
+#pragma unroll
+      for (int c = 0; c < 32; c++)
+        if (c == lane) a[c] += p.mu;
+    }
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 32; c++) {
     const int cc = K * 32 + c;
     double v;
     if (r < p.n && cc < p.n) {
-      v = p.A[(size_t)cc * p.n + r];
+      v = __ldg(p.A + (size_t)cc * p.n + r);
       if (r == cc) v += p.mu;
     } else {
       v = (r == cc) ? 1.0 : 0.0;
@@ -371,16 +383,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
   // identity padding), later panels from the workspace, so A is never copied as a whole.
   for (int j = -1; j < nblk - 1; j++) {
     const int nrem = nblk - 1 - j;
-    if (j >= 0) {
+    // j = -1: only block (0,0) is factored (by CTA 0, through the same code as every later diagonal
+    // block).  (A dry run of the block kernels on the idle CTAs during that time was tried to warm the
+    // instruction caches and measured no effect.)
+    const bool first = (j < 0);
+    const int jj = first ? 0 : j;
+    if (!first) {
       // ---- panel: L_Ij = A_Ij L_jj^-T
-      for (int t = g; t < nrem; t += G) {
+      const int ntr = nrem;
+      for (int t = g; t < ntr; t += G) {
         const int I = j + 1 + t;
         __syncwarp();
-        stage_block(Bs, ws + (size_t)(j * 32) * ld + j * 32, ld, lane);
-        rds[lane] = __ldcg(wrd + j * 32 + lane);
+        stage_block(Bs, ws + (size_t)(jj * 32) * ld + jj * 32, ld, lane);
+        rds[lane] = __ldcg(wrd + jj * 32 + lane);
         double x[32];
-        double *blk = ws + (size_t)(j * 32) * ld + I * 32;
-        if (j == 0) load_rows_A(x, p, I, 0, lane);
+        double *blk = ws + (size_t)(jj * 32) * ld + I * 32;
+        if (jj == 0) load_rows_A(x, p, I, 0, lane);
         else load_rows(x, blk, ld, lane);
         __syncwarp();
         trsm_warp(x, Bs, rds);
@@ -399,54 +417,56 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
       cluster_barrier();
       stamp(p, si);
     }
-    // ---- trailing update A_IK -= L_Ij L_Kj^T, j < K <= I; item 0 is block (j+1,j+1), factored at once
-    const int T = (j < 0) ? 1 : nrem * (nrem + 1) / 2;
-    if (crank == 0 && j >= 0) {
+    // ---- trailing update A_IK -= L_Ij L_Kj^T, j < K <= I; block (j+1,j+1) is factored at once
+    const int T = first ? 0 : nrem * (nrem + 1) / 2;
+    if (crank == 0) {
       // The diagonal block is on the critical path (its factorisation follows): the 8 warps of CTA 0
-      // update 4 columns each, warp 0 then factors it in registers.
+      // update 4 columns each, warp 0 then factors it in registers.  (j = -1: block (0,0), no update)
       double *coopA = sm + (size_t)CH_WARPS * (32 * 32 + 32);  // L_{j+1,j}, column-major
       double *coopC = coopA + 1024;
       const int J1 = j + 1;
-      const double *src = ws + (size_t)(j * 32) * ld + J1 * 32;
       double cv[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         const int k = 4 * w + i, r = J1 * 32 + lane, cc = J1 * 32 + k;
-        if (j == 0) {
+        if (jj == 0 && j <= 0) {
           cv[i] = (r < p.n && cc < p.n) ? p.A[(size_t)cc * p.n + r] + (r == cc ? p.mu : 0.0)
                                         : (r == cc ? 1.0 : 0.0);
         } else {
           cv[i] = __ldcg(ws + (size_t)cc * ld + r);
         }
       }
-      double yv = 0.0, bI = 0.0;
-      if (w == 1) {
-        const int r = J1 * 32 + lane;
-        yv = __ldcg(wy + j * 32 + lane);
-        bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
-      }
-      for (int e = threadIdx.x; e < 512; e += CH_THREADS) {
-        const int c = e >> 4, r2 = e & 15;
-        reinterpret_cast<double2 *>(coopA + c * 32)[r2] =
-            __ldcg(reinterpret_cast<const double2 *>(src + (size_t)c * ld) + r2);
-      }
-      if (w == 1) rds[lane] = yv;
-      __syncthreads();
-      double a[32];
+      if (!first) {
+        const double *src = ws + (size_t)(j * 32) * ld + J1 * 32;
+        double yv = 0.0, bI = 0.0;
+        if (w == 1) {
+          const int r = J1 * 32 + lane;
+          yv = __ldcg(wy + j * 32 + lane);
+          bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+        }
+        for (int e = threadIdx.x; e < 512; e += CH_THREADS) {
+          const int c = e >> 4, r2 = e & 15;
+          reinterpret_cast<double2 *>(coopA + c * 32)[r2] =
+              __ldcg(reinterpret_cast<const double2 *>(src + (size_t)c * ld) + r2);
+        }
+        if (w == 1) rds[lane] = yv;
+        __syncthreads();
+        double a[32];
 #pragma unroll
-      for (int m = 0; m < 32; m++) a[m] = coopA[m * 32 + lane];
+        for (int m = 0; m < 32; m++) a[m] = coopA[m * 32 + lane];
 #pragma unroll
-      for (int m = 0; m < 32; m++) {
-        const double2 b0 = lds_v2(reinterpret_cast<const double2 *>(coopA + m * 32 + 4 * w));
-        const double2 b1 = lds_v2(reinterpret_cast<const double2 *>(coopA + m * 32 + 4 * w + 2));
-        cv[0] = fma(-a[m], b0.x, cv[0]);
-        cv[1] = fma(-a[m], b0.y, cv[1]);
-        cv[2] = fma(-a[m], b1.x, cv[2]);
-        cv[3] = fma(-a[m], b1.y, cv[3]);
+        for (int m = 0; m < 32; m++) {
+          const double2 b0 = lds_v2(reinterpret_cast<const double2 *>(coopA + m * 32 + 4 * w));
+          const double2 b1 = lds_v2(reinterpret_cast<const double2 *>(coopA + m * 32 + 4 * w + 2));
+          cv[0] = fma(-a[m], b0.x, cv[0]);
+          cv[1] = fma(-a[m], b0.y, cv[1]);
+          cv[2] = fma(-a[m], b1.x, cv[2]);
+          cv[3] = fma(-a[m], b1.y, cv[3]);
+        }
+        if (w == 1) wb[J1 * 32 + lane] = bI - dot32(a, rds);  // b_{j+1} -= L_{j+1,j} y_j
       }
 #pragma unroll
       for (int i = 0; i < 4; i++) coopC[(4 * w + i) * 32 + lane] = cv[i];
-      if (w == 1) wb[J1 * 32 + lane] = bI - dot32(a, rds);  // b_{j+1} -= L_{j+1,j} y_j
       __syncthreads();
       if (w == 0) {
         double c[32], myrd = 0.0;
@@ -457,14 +477,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
         wrd[J1 * 32 + lane] = myrd;
         if (bad && lane == 0) atomicCAS(p.info, 0, J1 * 32 + bad);
         store_rows(c, ws + (size_t)(J1 * 32) * ld + J1 * 32, ld, lane);
-        }
+      }
     }
     // generic items: CTA 0 keeps its SM for the diagonal block (the other CL-1 CTAs share items 1..)
-    const bool solo = (j >= 0 && CL > 1);
+    const bool solo = (CL > 1);
     const int gu = solo ? (crank == 0 ? T : 1 + w * (CL - 1) + (crank - 1)) : g;
     const int Gu = solo ? (CL - 1) * CH_WARPS : G;
     for (int t = gu; t < T; t += Gu) {
-      if (t == 0 && j >= 0) continue;  // done above
+      if (t == 0) continue;  // the diagonal block, done above
       int u = 0;
       while ((u + 1) * (u + 2) / 2 <= t) u++;
       const int v = t - u * (u + 1) / 2;
@@ -472,32 +492,21 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
       double c[32];
       double *blk = ws + (size_t)(K * 32) * ld + I * 32;
       __syncwarp();
-      if (j >= 0) {
-        stage_block(Bs, ws + (size_t)(j * 32) * ld + K * 32, ld, lane);
-        double a[32];
-        load_rows(a, ws + (size_t)(j * 32) * ld + I * 32, ld, lane);
-        if (j == 0) load_rows_A(c, p, I, K, lane);
-        else load_rows(c, blk, ld, lane);
-        if (v == 0) {
-          // first trailing column: this warp holds row I of L_Ij, so b_I -= L_Ij y_j costs 32 FMAs
-          rds[lane] = __ldcg(wy + j * 32 + lane);
-          const int r = I * 32 + lane;
-          const double bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
-          __syncwarp();
-          wb[r] = bI - dot32(a, rds);
-        }
+      stage_block(Bs, ws + (size_t)(jj * 32) * ld + K * 32, ld, lane);
+      double a[32];
+      load_rows(a, ws + (size_t)(jj * 32) * ld + I * 32, ld, lane);
+      if (jj == 0) load_rows_A(c, p, I, K, lane);
+      else load_rows(c, blk, ld, lane);
+      if (v == 0) {
+        // first trailing column: this warp holds row I of L_Ij, so b_I -= L_Ij y_j costs 32 FMAs
+        rds[lane] = __ldcg(wy + j * 32 + lane);
+        const int r = I * 32 + lane;
+        const double bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
         __syncwarp();
-        update_warp(c, a, Bs);
-      } else {
-        load_rows_A(c, p, 0, 0, lane);
+        wb[r] = bI - dot32(a, rds);
       }
-      if (t == 0) {
-        double myrd = 0.0;
-        __syncwarp();
-        const int bad = potf2_warp(c, myrd, Bs, lane);
-        wrd[(j + 1) * 32 + lane] = myrd;
-        if (bad && lane == 0) atomicCAS(p.info, 0, (j + 1) * 32 + bad);
-      }
+      __syncwarp();
+      update_warp(c, a, Bs);
       store_rows(c, blk, ld, lane);
     }
     cluster_barrier();

@@ -268,6 +268,9 @@ struct ClusterPassArgs {
   int write_out;
   double beta;               // SAGE hidden-data weight: INIT d = beta*in + m ; SUB out = d - m + (1-beta)*in2
   const double2 *in2;        // mode 3 with beta != 1: the residual the hidden data was formed from
+  const short2 *blpq;        // [Nbase] (p,q) of baseline b (linear-mapped variant)
+  double *jte_part;          // [groups][slices][8N] per-CTA station sums (linear-mapped variant)
+  unsigned int *gcounter;    // [groups] arrival counters of the time slices of a baseline group
   const double2 *wt;         // [4][R] sqrt-weights (re,im) of the robust LM, or null.  With
                              // weights: cost = ||wt.e||^2 and J^T e -> J^T (wt^2 . e); the vector
                              // written for mode 1 stays the UNWEIGHTED e

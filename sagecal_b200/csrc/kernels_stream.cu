@@ -207,17 +207,11 @@ k_predict_full(PredictArgs a) {
 // station).  Gp belongs to station p (shared by the whole warp), Gq to station q (one per lane,
 // shared by the 8 warps of the CTA).  warp-shuffle reduction for p, smem transpose for q.
 // ------------------------------------------------------------------------------------------------
-__device__ int g_dbg_reduce = 0;  // tuning only: 1 = no atomics, 2 = no reduction at all
 __device__ __forceinline__ void tile_reduce_station_grad(const double2 *Gp, const double2 *Gq,
                                                           double *gblk, int p, int q, int N,
                                                           bool pvalid, double (*sq)[8][TILE_Q],
                                                           double scale) {
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int dbg = g_dbg_reduce;
-  if (dbg == 2) {
-    if (Gp[0].x == 1.2345e300) gblk[0] = Gq[0].x;  // keep the operands alive
-    return;
-  }
   // station p: butterfly over the 32 lanes
   double vp[8];
 #pragma unroll
@@ -229,7 +223,7 @@ __device__ __forceinline__ void tile_reduce_station_grad(const double2 *Gp, cons
     double v = vp[0];
 #pragma unroll
     for (int c = 1; c < 8; c++) v = (lane == c) ? vp[c] : v;
-    if (dbg == 0 || v == 1.2345e300) atomicAdd(gblk + 8 * (long long)p + lane, scale * v);
+    atomicAdd(gblk + 8 * (long long)p + lane, scale * v);
   }
   // station q: [warp][component][lane] in smem, warp c sums component c over the 8 warps
 #pragma unroll
@@ -242,7 +236,7 @@ __device__ __forceinline__ void tile_reduce_station_grad(const double2 *Gp, cons
     double s = 0.0;
 #pragma unroll
     for (int ww = 0; ww < TILE_P; ww++) s += sq[ww][w][lane];
-    if (q < N && s != 0.0 && (dbg == 0 || s == 1.2345e300)) atomicAdd(gblk + 8 * (long long)q + w, scale * s);
+    if (q < N && s != 0.0) atomicAdd(gblk + 8 * (long long)q + w, scale * s);
   }
   __syncthreads();
 }
@@ -926,6 +920,209 @@ k_cluster_pass_split(ClusterPassArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Gradient-carrying pass, linear mapping with CTA-wide TMA stages.  A CTA owns 256 CONSECUTIVE
+// baselines x a slice of timeslots; per timeslot the 4 coherency products and the 4 visibility
+// components of those baselines are 8 contiguous runs of 4 KB, fetched by 8 bulk copies of one elected
+// thread into a ring of NST stages (one mbarrier per stage, a CTA barrier frees a stage).  Compared
+// with the tile kernels: every lane is busy (the tile mapping idles 43 % of them at N = 62), NST-1
+// whole rows per CTA are in flight without costing registers, and the copy engine sees 16x fewer,
+// 8x larger requests.  Two threads per baseline as in k_cluster_pass_split (threadIdx.x = h*256 +
+// baseline).  Station sums are GATHERED through shared memory (no atomics: thread 8*s+comp adds up
+// what the CTA's baselines contribute to station s), written per CTA, and the last time slice of a
+// baseline group adds the group's total to J^T e (8 global atomics per entry instead of ~140).
+// ------------------------------------------------------------------------------------------------
+template <int NST>
+__global__ void __launch_bounds__(512)
+k_cluster_pass_lin(ClusterPassArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int BL = 256;
+  constexpr int STAGE_ELEMS = 8 * BL;  // double2: C00 C01 C10 C11 v0 v1 v2 v3
+  double2 *ring = reinterpret_cast<double2 *>(smem_raw);
+  double *acc = reinterpret_cast<double *>(ring + (size_t)NST * STAGE_ELEMS);  // [8N] station sums
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(acc + ((8 * a.N + 1) & ~1));
+  const int tid = threadIdx.x, h = tid >> 8, bl = tid & (BL - 1), lane = tid & 31;
+  const long long b0 = (long long)blockIdx.x * BL;
+  const int nvalid = (int)min((long long)BL, (long long)a.Nbase - b0);
+  const bool valid = bl < nvalid;
+  const int ts = a.t_begin + blockIdx.y * a.tslice;
+  const int te = min(ts + a.tslice, a.t_end);
+  const int nrow = te - ts;
+  for (int i = tid; i < 8 * a.N; i += 512) acc[i] = 0.0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int j, int s) {
+    const unsigned row_bytes = (unsigned)nvalid * 16u;
+    const long long row0 = (long long)(ts + j) * a.Nbase + b0;
+    double2 *dst = ring + (size_t)s * STAGE_ELEMS;
+    mbar_expect_tx(&bars[s], 8u * row_bytes);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      bulk_g2s(dst + c * BL, a.coh_k + (long long)c * a.R + row0, row_bytes, &bars[s]);
+      bulk_g2s(dst + (4 + c) * BL, a.in + (long long)c * a.R + row0, row_bytes, &bars[s]);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NST - 1; s++)
+      if (s < nrow) issue(s, s);
+  }
+  int p = 0, q = 0;
+  double2 Jr[2], Jq[4], W[8];
+#pragma unroll
+  for (int z = 0; z < 8; z++) W[z] = make_double2(0.0, 0.0);
+  Jr[0] = Jr[1] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) Jq[c] = make_double2(0.0, 0.0);
+  unsigned flagbits = 0;  // bit j: row ts+j flagged (slices are at most 32 rows, see the launcher)
+  const long long b = b0 + bl;
+  if (valid) {
+    const short2 pq = a.blpq[b];
+    p = pq.x;
+    q = pq.y;
+    const double2 *jp = reinterpret_cast<const double2 *>(a.pblk + 8 * (long long)p + 4 * h);
+    Jr[0] = __ldg(jp);
+    Jr[1] = __ldg(jp + 1);
+    load_jones(a.pblk, q, Jq);
+    for (int j = 0; j < nrow; j++)
+      flagbits |= (a.flag[(long long)(ts + j) * a.Nbase + b] != 0 ? 1u : 0u) << j;
+  }
+  const long long c0 = (long long)(2 * h) * a.R, c1 = c0 + a.R;
+  double cost = 0.0;
+  for (int j = 0; j < nrow; j++) {
+    const int s = j % NST;
+    // stage (j-1)%NST was released by the CTA barrier that closed iteration j-1
+    if (tid == 0 && j + NST - 1 < nrow) issue(j + NST - 1, (j + NST - 1) % NST);
+    mbar_wait(&bars[s], (unsigned)((j / NST) & 1));
+    if (valid) {
+      const double2 *st = ring + (size_t)s * STAGE_ELEMS + bl;
+      const long long row = (long long)(ts + j) * a.Nbase + b;
+      double2 C[4], v[2];
+#pragma unroll
+      for (int c = 0; c < 4; c++) C[c] = lds_v2(st + c * BL);
+      v[0] = lds_v2(st + (4 + 2 * h) * BL);
+      v[1] = lds_v2(st + (5 + 2 * h) * BL);
+      const bool fl = (flagbits >> j) & 1u;
+      const double2 T0 = cdot2(Jr[0], C[0], Jr[1], C[2]);
+      const double2 T1 = cdot2(Jr[0], C[1], Jr[1], C[3]);
+      double2 m[2];
+      m[0] = cdot2c(T0, Jq[0], T1, Jq[1]);
+      m[1] = cdot2c(T0, Jq[2], T1, Jq[3]);
+      if (fl) m[0] = m[1] = make_double2(0.0, 0.0);
+      double2 e[2];
+      if (a.mode == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const double2 d = cadd(make_double2(a.beta * v[jj].x, a.beta * v[jj].y), m[jj]);
+          if (a.write_out) st_stream(a.out + (jj ? c1 : c0) + row, d);
+          e[jj] = csub(d, m[jj]);
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          e[jj] = csub(v[jj], m[jj]);
+          if (a.write_out) st_stream(a.out + (jj ? c1 : c0) + row, e[jj]);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        cost = fma(e[jj].x, e[jj].x, cost);
+        cost = fma(e[jj].y, e[jj].y, cost);
+      }
+      if (!fl) {
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+          for (int lm = 0; lm < 4; lm++) cfmac(W[jj * 4 + lm], e[jj], C[lm]);
+      }
+    }
+    __syncthreads();  // every thread is done with stage s
+  }
+  // contraction with the Jones (see k_cluster_pass_split)
+  double2 Gp[2], Gq[4];
+  Gp[0] = Gp[1] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) Gq[c] = make_double2(0.0, 0.0);
+  if (valid) {
+#pragma unroll
+    for (int l = 0; l < 2; l++)
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+        for (int m = 0; m < 2; m++) cfma(Gp[l], Jq[2 * jj + m], W[jj * 4 + l * 2 + m]);
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++)
+#pragma unroll
+      for (int m = 0; m < 2; m++)
+#pragma unroll
+        for (int l = 0; l < 2; l++) cfmac(Gq[2 * jj + m], Jr[l], W[jj * 4 + l * 2 + m]);
+  }
+  // Station sums without atomics: every thread parks its 4 + 8 partial values in shared memory (the
+  // ring is free now), then thread i = 8*s + comp gathers what the CTA's baselines contribute to
+  // component comp of station s, as the q station of (p, s) for the p of this CTA and as the p
+  // station of (s, q).  (Shared-memory fp64 atomics for this cost more than the whole pass.)
+  double *gq = reinterpret_cast<double *>(ring);  // [512][8]
+  double *gp = gq + 512 * 8;                       // [512][4]
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    gq[tid * 8 + 2 * c] = Gq[c].x;
+    gq[tid * 8 + 2 * c + 1] = Gq[c].y;
+  }
+  gp[tid * 4 + 0] = Gp[0].x;
+  gp[tid * 4 + 1] = Gp[0].y;
+  gp[tid * 4 + 2] = Gp[1].x;
+  gp[tid * 4 + 3] = Gp[1].y;
+  __syncthreads();
+  const int pmin = a.blpq[b0].x, pmax = a.blpq[b0 + nvalid - 1].x;
+  for (int i = tid; i < 8 * a.N; i += 512) {
+    const int sidx = i >> 3, comp = i & 7;
+    double tot = 0.0;
+    // as station q of baselines (pp, sidx)
+    for (int pp = pmin; pp <= pmax && pp < sidx; pp++) {
+      const long long bb = baseline_index(pp, sidx, a.N) - b0;
+      if (bb >= 0 && bb < nvalid) tot += gq[bb * 8 + comp] + gq[(256 + bb) * 8 + comp];
+    }
+    // as station p of baselines (sidx, qq): components 4h..4h+3 come from half h
+    if (sidx >= pmin && sidx <= pmax) {
+      const int hh = comp >> 2, cc = comp & 3;
+      long long bb = baseline_index(sidx, sidx + 1, a.N) - b0;
+      long long be = bb + (a.N - 1 - sidx);
+      if (bb < 0) bb = 0;
+      if (be > nvalid) be = nvalid;
+      for (; bb < be; bb++) tot += gp[(hh * 256 + bb) * 4 + cc];
+    }
+    acc[i] = tot;
+  }
+  // Station sums of this CTA go out with plain stores; the LAST time slice of a baseline group to
+  // arrive adds the group's total to J^T e.  (One global atomic per entry and CTA instead: ~140 adds
+  // queue up on each of the 8N addresses and cost more than the pass itself.)
+  {
+    __shared__ bool last_of_group;
+    const int n8 = 8 * a.N;
+    double *grp = a.jte_part + (size_t)blockIdx.x * gridDim.y * n8;
+    double *mine = grp + (size_t)blockIdx.y * n8;
+    for (int i = tid; i < n8; i += 512) mine[i] = acc[i];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last_of_group = (atomicAdd(a.gcounter + blockIdx.x, 1u) == gridDim.y - 1);
+    __syncthreads();
+    if (last_of_group) {
+      __threadfence();
+      for (int i = tid; i < n8; i += 512) {
+        double sacc = 0.0;
+        for (unsigned c = 0; c < gridDim.y; c++) sacc += __ldcg(grp + (size_t)c * n8 + i);
+        if (sacc != 0.0) atomicAdd(a.jte + i, sacc);
+      }
+      if (tid == 0) a.gcounter[blockIdx.x] = 0;  // re-arm
+    }
+  }
+  grid_reduce_sum(cost, a.partials, a.cost, a.counter);
+}
+
+// ------------------------------------------------------------------------------------------------
 // time-summed Gram tensor of the coherencies of each baseline:
 //   T[b][16] = Hermitian 4x4  sum_t conj(c) c^T,  c = (C00,C01,C10,C11), unflagged rows only
 // stored as: 4 real diagonals, then the 6 complex upper off-diagonals (01,02,03,12,13,23)
@@ -1032,7 +1229,6 @@ void db_launch_grad_full(const GradArgs *a, int ntile, cudaStream_t st) {
   dim3 grid(ntile, (a->tilesz + PREDICT_TB - 1) / PREDICT_TB);
   k_grad_full<PREDICT_TB><<<grid, TILE_THREADS, 0, st>>>(*a);
 }
-void db_set_dbg_reduce(int v) { cudaMemcpyToSymbol(g_dbg_reduce, &v, sizeof(int)); }
 void db_launch_grad_tma(const GradArgs *a, int ntile, cudaStream_t st) {
   static int cfg = -1;
   static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
@@ -1058,11 +1254,33 @@ void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st
   dim3 grid(ntile, (nt + a->tslice - 1) / a->tslice);
   if (a->jte != nullptr && a->mode <= 1) {
     static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
-    // (a per-warp TMA ring was tried here and measured equal, 18.5 us: with 144 x 16 warps x 10 rows
-    //  x 6 runs of <= 512 B the pass is bound by the bulk-copy issue rate, ~1 per 32 clk per SM; see
-    //  DESIGN.md "what did not work")
-    if (unsplit) k_cluster_pass<true><<<grid, TILE_THREADS, 0, st>>>(*a);
-    else k_cluster_pass_split<<<grid, 2 * TILE_THREADS, 0, st>>>(*a);
+    // default: linear mapping with CTA-wide TMA stages; robust weights and DIRAC_B200_NO_TMA take the
+    // register-staged tile kernel
+    static const bool no_tma = getenv("DIRAC_B200_NO_TMA") != nullptr;
+    if (unsplit) {
+      k_cluster_pass<true><<<grid, TILE_THREADS, 0, st>>>(*a);
+    } else if (a->wt || no_tma) {
+      k_cluster_pass_split<<<grid, 2 * TILE_THREADS, 0, st>>>(*a);
+    } else {
+      // linear mapping: 256 baselines per CTA, time sliced to about one CTA per SM (<= 32 rows)
+      constexpr int NST = 5;
+      const int nbg = (a->Nbase + 255) / 256;
+      int nsl = (148 + nbg - 1) / nbg;
+      if (nsl > nt) nsl = nt;
+      ClusterPassArgs b = *a;
+      b.tslice = (nt + nsl - 1) / nsl;
+      if (b.tslice > 32) b.tslice = 32;
+      const size_t smem = (size_t)NST * 8 * 256 * sizeof(double2) +
+                          sizeof(double) * ((8 * a->N + 1) & ~1) + NST * 8;
+      static bool configured = false;
+      if (!configured) {
+        DB_CHECK(cudaFuncSetAttribute(k_cluster_pass_lin<NST>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+      dim3 glin(nbg, (nt + b.tslice - 1) / b.tslice);
+      k_cluster_pass_lin<NST><<<glin, 512, smem, st>>>(b);
+    }
   } else {
     k_cluster_pass<false><<<grid, TILE_THREADS, 0, st>>>(*a);
   }

@@ -82,6 +82,13 @@ void db_lm_init(dirac_b200_problem *pr) {
   for (int k = 0; k < d.M; k++) w.pref_slot[k] = -1;
   w.jtj0_cur = nullptr;
   w.jtj_spec = nullptr;
+  {
+    // linear-mapped gradient pass: (baseline groups of 256) x (time slices, about one CTA per SM)
+    const int nbg = (d.Nbase + 255) / 256;
+    int nsl = (148 + nbg - 1) / nbg;
+    if ((d.tilesz + 31) / 32 > nsl) nsl = (d.tilesz + 31) / 32;  // slices hold at most 32 rows
+    w.jte_part = dalloc<double>((size_t)nbg * (nsl + 1) * n8);
+  }
   DB_CHECK(cudaEventCreateWithFlags(&w.ev_mail, cudaEventDisableTiming));
   DB_CHECK(cudaMallocHost((void **)&w.h_vec, sizeof(double) * (5 * n8 + 4 * d.N + 64)));
   // library handles are process-wide (creating them costs tens of ms; the drop-in entry points
@@ -128,7 +135,7 @@ void db_lm_free(dirac_b200_problem *pr) {
   LMWork &w = pr->lm;
   if (!w.ready) return;
   db_free(w.T); db_free(w.Tsub); db_free(w.JTJ0); db_free(w.JTJ);
-  db_free(w.Hst); db_free(w.pnew); db_free(w.plast);
+  db_free(w.Hst); db_free(w.pnew); db_free(w.plast); db_free(w.jte_part);
   db_free(w.tau); db_free(w.cswork); db_free(w.dbuf);
   if (w.svdS) { db_free(w.svdS); db_free(w.svdU); db_free(w.svdVT); }
   if (w.wbuf) { db_free(w.wbuf); db_free(w.ebuf); db_free(w.HP); db_free(w.HQ); }
@@ -177,6 +184,7 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   ClusterPassArgs a;
   a.coh_k = d.coh + (size_t)k * 4 * d.R;
   a.in = in; a.flag = d.flag; a.pblk = pblk_dev; a.tiles = d.tiles; a.out = out; a.jte = jte_dev;
+  a.blpq = d.blpq; a.jte_part = pr->lm.jte_part; a.gcounter = d.counters + 16;
   a.partials = pr->partials; a.cost = d.scal + cost_slot; a.counter = d.counters; a.R = d.R;
   a.N = d.N; a.Nbase = d.Nbase; a.t_begin = t0; a.t_end = t1; a.tslice = pick_tslice(d, t1 - t0);
   a.mode = mode; a.write_out = write_out; a.wt = wt; a.beta = beta; a.in2 = in2;
@@ -954,13 +962,8 @@ extern "C" double dirac_b200_bench_predict(dirac_b200_problem *pr, int out_mode,
   return 1e3 * ms / reps;
 }
 
-extern "C" void db_set_dbg_reduce(int v);
 extern "C" double dirac_b200_bench_grad(dirac_b200_problem *pr, int reps) {
   DevProblem &d = pr->d;
-  if (reps < 0) {  // tuning: reps = -1-mode selects the reduction debug mode
-    db_set_dbg_reduce(-1 - reps);
-    return 0.0;
-  }
   cudaEvent_t e0, e1;
   DB_CHECK(cudaEventCreate(&e0));
   DB_CHECK(cudaEventCreate(&e1));

@@ -305,8 +305,8 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
   d.scal = dev_alloc<double>(64 + 3 * 8 * (size_t)N + 8);
   DB_CHECK(cudaMemset(d.scal, 0, sizeof(double) * (64 + 3 * 8 * (size_t)N + 8)));
   DB_CHECK(cudaMallocHost((void **)&d.h_scal, (64 + 3 * 8 * (size_t)N + 8) * sizeof(double)));
-  d.counters = dev_alloc<unsigned int>(16);
-  DB_CHECK(cudaMemset(d.counters, 0, 16 * sizeof(unsigned int)));
+  d.counters = dev_alloc<unsigned int>(16 + 1024);  // [0,16): grid reductions; then baseline groups
+  DB_CHECK(cudaMemset(d.counters, 0, (16 + 1024) * sizeof(unsigned int)));
   pr->res = dev_alloc<double2>((size_t)4 * R);
   pr->g = dev_alloc<double>((size_t)d.npar);
   DB_CHECK(cudaGetLastError());

@@ -207,12 +207,23 @@ void dirac_b200_set_stream(void *stream);
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 unsigned long long dirac_b200_launch_count(void);
 /* per-launch CUDA-event timing of the library's kernels on their launching stream.
- * kind: 0 k_predict_full, 1 k_grad_full, 2 k_cluster_pass, 3 k_coh_gram, 4 assemble, 5 damped solve
- * (cuSOLVER).  enable(1) clears the records; read returns the launch count and sums the elapsed
+ * kind: 0 full predict, 1 LBFGS gradient, 2 k_cluster_pass*, 3 k_coh_gram, 4 assembly, 5 damped solve
+ * (k_chol_solve / k_tri_solve / batched potrf), 6 k_weighted_jtj, 7 line setup.  enable(1) clears the
+ * records; read returns the launch count and sums the elapsed
  * milliseconds and the algorithmic bytes of the recorded launches of that kind. */
 unsigned long long dirac_b200_kernel_count(int kind); /* launches of `kind` since load */
 void dirac_b200_profile_enable(int on);
 int dirac_b200_profile_read(int kind, double *ms, double *bytes);
+
+/* ---- the dense solver of the LM step on its own (diagnostics, tests) ---------------------------
+ * (A + mu I) x = b for a symmetric positive definite A (n x n, column-major, only the lower triangle
+ * is read; n <= 512) on one thread-block cluster: blocked Cholesky, both substitutions, one kernel
+ * (replaces dpotrf + dpotrs of clmfit.c:373-395).  Host buffers.  *info as dpotrf (0, or the index
+ * of the first non-positive pivot).  Returns 0, or -1 if the device grants no 8/16-CTA cluster.
+ * dirac_b200_tri_solve: L L^T x = b for an existing factor L (column-major lower, ld = n), i.e.
+ * dpotrs; reps > 0 additionally times `reps` back-to-back solves (us per solve in *us). */
+int dirac_b200_spd_solve(int n, const double *A, const double *b, double mu, double *x, int *info);
+int dirac_b200_tri_solve(int n, const double *L, const double *b, double *x, int reps, double *us);
 
 #ifdef __cplusplus
 }

@@ -85,16 +85,6 @@ __device__ __forceinline__ void store_rows(const double (&a)[32], double *base, 
 #pragma unroll
   for (int c = 0; c < 32; c++) base[(size_t)c * ld + lane] = a[c];
 }
-// lane l <- column l of the block (32 contiguous doubles)
-__device__ __forceinline__ void load_cols(double (&a)[32], const double *base, int ld, int lane) {
-  const double2 *src = reinterpret_cast<const double2 *>(base + (size_t)lane * ld);
-#pragma unroll
-  for (int r = 0; r < 16; r++) {
-    const double2 v = __ldcg(src + r);
-    a[2 * r] = v.x;
-    a[2 * r + 1] = v.y;
-  }
-}
 // warp copy of a block into shared memory, column-major with ld 32
 __device__ __forceinline__ void stage_block(double *dst, const double *base, int ld, int lane) {
 #pragma unroll

@@ -693,7 +693,6 @@ k_cluster_pass(ClusterPassArgs a) {
   const bool valid = (q > p) && (q < a.N);
   const int ts = a.t_begin + blockIdx.y * a.tslice;
   const int te = min(ts + a.tslice, a.t_end);
-  constexpr bool want_grad = GRAD;
   double cost = 0.0;
   double2 Jp[4], Jq[4], W[GRAD ? 16 : 1];
 #pragma unroll
@@ -940,7 +939,7 @@ k_cluster_pass_lin(ClusterPassArgs a) {
   double2 *ring = reinterpret_cast<double2 *>(smem_raw);
   double *acc = reinterpret_cast<double *>(ring + (size_t)NST * STAGE_ELEMS);  // [8N] station sums
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(acc + ((8 * a.N + 1) & ~1));
-  const int tid = threadIdx.x, h = tid >> 8, bl = tid & (BL - 1), lane = tid & 31;
+  const int tid = threadIdx.x, h = tid >> 8, bl = tid & (BL - 1);
   const long long b0 = (long long)blockIdx.x * BL;
   const int nvalid = (int)min((long long)BL, (long long)a.Nbase - b0);
   const bool valid = bl < nvalid;

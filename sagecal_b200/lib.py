@@ -22,7 +22,7 @@ EXPORTED = [
     "dirac_b200_grad", "dirac_b200_normal_eq", "dirac_b200_launch_count", "dirac_b200_sagefit",
     "dirac_b200_set_stream", "dirac_b200_profile_enable", "dirac_b200_profile_read",
     "dirac_b200_kernel_count", "dirac_b200_normal_eq_weighted", "dirac_b200_create_shard",
-    "dirac_b200_set_comm",
+    "dirac_b200_set_comm", "dirac_b200_spd_solve", "dirac_b200_tri_solve",
 ]
 
 

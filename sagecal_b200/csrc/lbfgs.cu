@@ -44,9 +44,10 @@ static void line_alloc(dirac_b200_problem *pr) {
   if (pr->E0) return;
   DevProblem &d = pr->d;
   const size_t n = (size_t)4 * d.R;
-  pr->E0 = (decltype(pr->E0))db_malloc(sizeof(double2) * n);
-  pr->E1 = (decltype(pr->E1))db_malloc(sizeof(double2) * n);
-  pr->E2 = (decltype(pr->E2))db_malloc(sizeof(double2) * n);
+  // one allocation: the three parts of the line model travel in ONE all-reduce when sharded
+  pr->E0 = (decltype(pr->E0))db_malloc(sizeof(double2) * n * 3);
+  pr->E1 = pr->E0 + n;
+  pr->E2 = pr->E1 + n;
   pr->pk_dev = (decltype(pr->pk_dev))db_malloc(sizeof(double) * d.npar);
 }
 
@@ -78,9 +79,7 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
   db_count_launch(1);
   if (pr->world > 1) {
     // sum the model polynomials of all ranks, then E0 = x - V0
-    db_allreduce(pr, pr->E0, 8 * d.R);
-    db_allreduce(pr, pr->E1, 8 * d.R);
-    db_allreduce(pr, pr->E2, 8 * d.R);
+    db_allreduce(pr, pr->E0, 3 * 8 * d.R);  // E0 | E1 | E2 are contiguous
     db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);
     db_count_launch(1);
   }

@@ -322,7 +322,7 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   db_free(d.chunk_poff); db_free(d.tiles); db_free(d.blpq); db_free(d.scal); db_free(d.counters);
   db_free(pr->partials); db_free(pr->res); db_free(pr->g); db_free(pr->vis_stage);
   if (pr->pm) db_free(pr->pm);
-  if (pr->E0) { db_free(pr->E0); db_free(pr->E1); db_free(pr->E2); db_free(pr->pk_dev); }
+  if (pr->E0) { db_free(pr->E0); db_free(pr->pk_dev); }  // E1, E2 live inside E0's allocation
   cudaFreeHost(d.h_scal);
   free(d.h_clus); free(d.h_chunk_poff);
   if (pr->own_stream) cudaStreamDestroy(d.stream);

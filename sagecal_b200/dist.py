@@ -8,8 +8,8 @@ implemented here with `torch.distributed.all_reduce` (NCCL over NVLink / NVSwitc
 tensor view of the library's buffer, enqueued on the library's stream.
 
 Collectives per solve: ONE all-reduce of the residual delta (8*Nbase*tilesz doubles) per SAGE
-sweep, plus the Jones delta and two tiny bookkeeping vectors; in the LBFGS stage three all-reduces
-of the line model per iteration and one of the gradient.
+sweep, plus the Jones delta and two tiny bookkeeping vectors; in the LBFGS stage one all-reduce
+of the line model (three vectors, contiguous) per iteration and one of the gradient.
 """
 from __future__ import annotations
 
@@ -43,10 +43,18 @@ def make_allreduce(device="cuda"):
     import torch
     import torch.distributed as dist
 
+    views = {}  # (ptr, count) -> tensor view; (stream) -> ExternalStream: built once, the library
+    streams = {}  # calls with the same few buffers thousands of times
+
     def _cb(ptr, count, stream, user):
         if device == "cuda":
-            t = torch.as_tensor(_CudaView(ptr, count), device="cuda")
-            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+            t = views.get((ptr, count))
+            if t is None:
+                t = views[(ptr, count)] = torch.as_tensor(_CudaView(ptr, count), device="cuda")
+            st = streams.get(stream)
+            if st is None:
+                st = streams[stream] = torch.cuda.ExternalStream(int(stream))
+            with torch.cuda.stream(st):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
         else:
             a = np.ctypeslib.as_array(C.cast(ptr, c_double_p), shape=(int(count),))

@@ -114,3 +114,52 @@ def test_alternate_paths_agree(api, switch):
     alt = run({switch: "1"})
     assert relerr(np.array(alt["pp"]), np.array(base["pp"])) < 1e-7
     assert abs(alt["r"][3] - base["r"][3]) <= 1e-7 * base["r"][3]
+
+
+EDGE_CASES = [
+    # a third of the rows flagged, 2 % under the uv cut
+    ("heavy-flags", dict(N=10, M=2, tilesz=10, seed=51, flag_frac=0.3, uvcut_frac=0.02),
+     dict(solver_mode=1, max_iter=3)),
+    # a single timeslot
+    ("one-slot", dict(N=9, M=2, tilesz=1, seed=52, uvcut_frac=0.0), dict(solver_mode=1, max_iter=3)),
+    # 8N = 512: the largest system the cluster Cholesky takes
+    ("n512", dict(N=64, M=1, tilesz=2, seed=53), dict(solver_mode=1, max_iter=2, max_emiter=1,
+                                                     max_lbfgs=2)),
+    # 8N = 520: one station more, the damped solves fall back to cuSOLVER
+    ("n520", dict(N=65, M=1, tilesz=2, seed=54), dict(solver_mode=1, max_iter=2, max_emiter=1,
+                                                     max_lbfgs=2)),
+    # 8N not a multiple of the 32-wide blocks, several clusters
+    ("n264", dict(N=33, M=3, tilesz=4, seed=55, kmean=1.0), dict(solver_mode=1, max_iter=2)),
+]
+
+
+@pytest.mark.parametrize("name,prob,args", EDGE_CASES, ids=[c[0] for c in EDGE_CASES])
+def test_sagefit_edge_cases(api, ref, name, prob, args):
+    b = small_problem(**prob)
+    kw = dict(max_emiter=3, max_lbfgs=6, lbfgs_m=5, randomize=0)
+    kw.update(args)
+    (rr, xr, ppr), (rg, xg, ppg) = run_both(api, ref, b, **kw)
+    assert rr[0] == rg[0]
+    assert abs(rr[2] - rg[2]) <= 1e-10 * rr[2]          # res_0
+    assert relerr(ppg, ppr) < JONES_TOL, (name, relerr(ppg, ppr))
+    assert abs(rr[3] - rg[3]) <= 1e-5 * rr[3]           # res_1
+
+
+def test_sagefit_at_the_solution_stops_like_the_reference(api, ref):
+    """Noise-free data and the true Jones as the starting point: the residual is at rounding level,
+    every LM run stops on its entry tests (clmfit.c:300-340, applied after the fact by the deferred
+    path of lm_core) and the Jones come back unchanged in both libraries."""
+    b = small_problem(N=8, M=3, tilesz=6, seed=61, noise_rel=0.0, flag_frac=0.0, uvcut_frac=0.0)
+    pr = b.pr
+    out = []
+    for lib in (ref, api):
+        x = pr.x.copy()
+        pp = pr.jones_true.copy()
+        r = lib.sagefit_visibilities(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz, b.fresh_barr(),
+                                     b.sky, pr.coh, pp, max_emiter=2, max_iter=3, max_lbfgs=0,
+                                     lbfgs_m=5, solver_mode=1, randomize=0)
+        out.append((r, pp))
+    (rr, ppr), (rg, ppg) = out
+    assert np.max(np.abs(ppr - pr.jones_true)) < 1e-9
+    assert np.max(np.abs(ppg - pr.jones_true)) < 1e-9
+    assert rg[2] < 1e-12 and rr[2] < 1e-12

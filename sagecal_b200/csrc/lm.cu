@@ -7,7 +7,9 @@
 //   e, ||e||^2, J^T e   one streaming pass over (hidden data, coh_k)          k_cluster_pass
 //   J^T J               assembled from the per-baseline Gram tensors           k_coh_gram/k_assemble
 //                       (weighted, robust LM: one streaming pass)              k_weighted_jtj
-//   (J^T J + mu I) dp   cuSOLVER potrf/potrs | geqrf+ormqr+trsm | gesvd        (library, not HBM bound)
+//   (J^T J + mu I) dp   linsolv 0: k_chol_solve / k_tri_solve on one thread-block cluster
+//                       (kernels_chol.cu; cuSOLVER potrf/potrs when 8N > 512 or no cluster)
+//                       linsolv 1, 2: cuSOLVER geqrf+ormqr+trsm | gesvd
 // The dense n x 8N Jacobian of the reference (7.2 GB per cluster at N=62, T=120) never exists.
 #include <float.h>
 #include <math.h>

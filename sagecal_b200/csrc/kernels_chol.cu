@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
   const int ld = p.nblk * 32, nblk = p.nblk;
   double *ws = p.ws;
   double *wrd = p.ws + (size_t)ld * ld;
-  double *winv = wrd + ld;  // per diagonal block: L_jj^-1 (1024) then its transpose (1024)
+  double *winv = wrd + ld;  // per diagonal block 2048 doubles: [1024, 2048) holds L_jj^-T
   double *wb = winv + (size_t)nblk * 2048;  // running right-hand side (forward solve rides along)
   double *wy = wb + ld;                     // y = L^-1 b
   double *Bs = sm + (size_t)w * (32 * 32 + 32);  // per-warp staging block + 32 reciprocals
@@ -514,13 +514,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
     for (int c = 0; c < 32; c++) x[c] = (c == lane) ? 1.0 : 0.0;
     __syncwarp();
     trsm_warp(x, Bs, rds);  // x[c] = (L^-1)[c][lane]
+    // T[m*32 + l] = Linv[m][l]: what the back substitution multiplies with (the forward solve has
+    // already happened along the factorisation, so L_jj^-1 itself is not stored)
     double *inv = winv + (size_t)t * 2048;
-    // inv[m*32 + l] = Linv[l][m] (row l per lane for the forward solve); the transpose behind it
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
-      inv[lane * 32 + c] = x[c];         // (l = c, m = lane)
-      inv[1024 + c * 32 + lane] = x[c];  // T[l = lane][m = c] = Linv[c][lane]
-    }
+    for (int c = 0; c < 32; c++) inv[1024 + c * 32 + lane] = x[c];
   }
   if (g == G - 1) {
     const int j = nblk - 1;

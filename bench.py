@@ -56,12 +56,45 @@ def parse():
     return ap.parse_args()
 
 
+def solve_args(name):
+    """solver settings of a workload: C3 is the robust configuration (robust LM in the last sweep +
+    Student's-t LBFGS); everything else plain LM + LBFGS"""
+    a = dict(SOLVE)
+    if name == "C3":
+        a["solver_mode"] = 2
+    elif name == "C3os":
+        a["solver_mode"] = 3
+    return a
+
+
+def golden_parity(name, pr, pp, res):
+    """solved Jones of one step against the committed golden of the CPU restatement at the FULL
+    shape (tests/golden/full/*.npz, generator tests/golden/make_golden_full.py; the restatement is
+    pinned to the compiled reference at the reduced shape).  Checker only, outside every timed region."""
+    path = os.path.join(ROOT, "tests", "golden", "full", name + ".npz")
+    if not os.path.exists(path):
+        return {"checked": False, "why": "no golden for workload %s" % name}
+    g = np.load(path)
+    fp = np.array([np.sum(pr.x), np.sum(np.abs(pr.x)), np.sum(pr.coh.real), np.sum(pr.coh.imag),
+                   np.sum(np.abs(pr.coh)), float(np.sum(pr.flag)), np.sum(pr.u), np.sum(pr.w)])
+    same_inputs = bool(np.allclose(fp, g["fingerprint"], rtol=1e-10, atol=0))
+    want = g["out_scalars"]
+    err = float(np.max(np.abs(pp - g["out_pp"])) / np.max(np.abs(g["out_pp"])))
+    return {"checked": True, "against": "oracle/liboracle.so golden tests/golden/full/%s.npz" % name,
+            "same_inputs": same_inputs, "jones_max_relerr": err, "tolerance": 1e-5,
+            "ok": bool(same_inputs and err < 1e-5),
+            "res_0": [res[2], float(want[2])], "res_1": [res[3], float(want[3])],
+            "mean_nu": [res[1], float(want[1])]}
+
+
 def workload_shape(name):
     from sagecal_b200 import synth
+    if name == "C3os":
+        name = "C3"
     if name in synth.CONFIGS:
         c = synth.CONFIGS[name]
         return dict(N=c["N"], M=c["M"], tilesz=c["tilesz"], radius=c["radius"], seed=c["seed"],
-                    kmean=c["kmean"])
+                    kmean=c["kmean"], outliers=c.get("outliers", 0.0))
     N, M, T = (int(v) for v in name.split(","))
     return dict(N=N, M=M, tilesz=T, radius=40e3, seed=20260921 + 2, kmean=2.0)
 
@@ -244,6 +277,7 @@ def main():
 
     from sagecal_b200 import synth
     shape = dict(workload_shape(args.workload))
+    SOLVE_W = solve_args(args.workload)
 
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -294,9 +328,12 @@ def main():
     with torch.cuda.stream(stream):
         dp = make_resident()
         res = None
-        for _ in range(W):
+        parity = None
+        for it in range(W):
             pp = pr.pp0.copy()
-            res = dp.sagefit(pp, None, **SOLVE)
+            res = dp.sagefit(pp, None, **SOLVE_W)
+            if it == 0 and world == 1 and rank == 0:
+                parity = golden_parity(args.workload, pr, pp, res)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -308,7 +345,7 @@ def main():
         e0.record(stream)
         for _ in range(K):
             pp = pr.pp0.copy()
-            res = dp.sagefit(pp, None, **SOLVE)
+            res = dp.sagefit(pp, None, **SOLVE_W)
         e1.record(stream)
         torch.cuda.synchronize()
         if world > 1:
@@ -325,13 +362,13 @@ def main():
         p0.record(stream)
         for _ in range(K):
             pp = pr.pp0.copy()
-            res = dp.sagefit(pp, None, **SOLVE)
+            res = dp.sagefit(pp, None, **SOLVE_W)
         p1.record(stream)
         torch.cuda.synchronize()
         ms_profiled = p0.elapsed_time(p1) / K
         prof = {k: api.profile_read(k) for k in range(8)}
         api.profile_enable(False)
-    sweeps = SOLVE["max_emiter"] + ngrad
+    sweeps = SOLVE_W["max_emiter"] + ngrad
     units_step = R * M * sweeps
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -353,11 +390,11 @@ def main():
                 pp_h[:] = pr.pp0
                 if world == 1:
                     return api.sagefit_visibilities(pr.u, pr.v, pr.w, x_h, pr.N, pr.Nbase,
-                                                    pr.tilesz, barr, sky, coh_h, pp_h, **SOLVE)
+                                                    pr.tilesz, barr, sky, coh_h, pp_h, **SOLVE_W)
                 # sharded public path: upload this rank's shard, solve, download, free
                 sp = make_resident()
                 xo = np.empty_like(x_keep)
-                rr = sp.sagefit(pp_h, xo, **SOLVE)
+                rr = sp.sagefit(pp_h, xo, **SOLVE_W)
                 sp.close()
                 return rr
             one()
@@ -430,7 +467,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: N=%d stations, %d baselines, M=%d clusters, tilesz=%d, "
                                "rows=%d per GPU" % (args.workload, pr.N, pr.Nbase, M, pr.tilesz, R),
-                   "solve": SOLVE, "sweeps_per_step": sweeps,
+                   "solve": SOLVE_W, "sweeps_per_step": sweeps,
                    "units_per_step": "rows*clusters*(em_sweeps+lbfgs_grad_evals)",
                    "l2": "inputs (%.0f MB coherencies) larger than the 126 MB L2, no flush needed"
                          % (coh_h.nbytes / 1e6),
@@ -439,7 +476,7 @@ def main():
                    else "1 GPU",
                    "final_res": [res[2], res[3]] if res else None},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:

@@ -199,10 +199,35 @@ dirac_b200_problem *dirac_b200_create_shard(int N, int Nbase, int tilesz, const 
 void dirac_b200_set_comm(dirac_b200_problem *pr, int rank, int world,
                          void (*allreduce)(void *dev, long long count, void *stream, void *user),
                          void *user, int m_global, int k_global0, double beta);
+/* The collective itself: with allreduce == NULL in dirac_b200_set_comm the library calls
+ * ncclAllReduce (fp64, sum, in place) on its own stream through a process-wide communicator:
+ *   rank 0:     dirac_b200_nccl_unique_id(id)         (128 bytes; the host distributes them: MPI_Bcast,
+ *   every rank: dirac_b200_nccl_init(rank, world, id)   a file, a TCP store ...)  [collective call]
+ * NCCL is bound at run time (an already loaded libnccl.so.2, $DIRAC_B200_NCCL_LIB, libnccl.so.2).
+ * A C host (the reference driver) needs nothing else for the multi-GPU path; the callback remains
+ * for hosts that bring their own collective.  All return 0 on success. */
+int dirac_b200_nccl_unique_id(char *id128);
+int dirac_b200_nccl_init(int rank, int world, const char *id128);
+void dirac_b200_nccl_finalize(void);
+int dirac_b200_nccl_ready(void);
+/* collectives issued since the last reset: calls, bytes, host seconds spent enqueueing them */
+void dirac_b200_comm_stats(unsigned long long *calls, unsigned long long *bytes,
+                           double *enqueue_seconds, int reset);
 
 /* run on a caller-supplied CUDA stream (cudaStream_t) instead of a private one; NULL restores the
  * default.  Affects problems created afterwards and the reference entry points. */
 void dirac_b200_set_stream(void *stream);
+
+/* test / tuning switches; returns 0, or -1 for an unknown name.
+ *   "cp_rows"   timeslots per CTA of the gradient-carrying cluster pass (0: one wave over the SMs);
+ *               the parity tests use it to drive the multi-row TMA ring on small problems */
+int dirac_b200_set_option(const char *name, int value);
+
+/* LM accept/reject decisions that were taken at rounding level (|dF| <= 1e-11 ||e||^2) since the last
+ * reset: on such runs (typical for the ordered-subsets modes 0 and 3 once trial steps get rejected
+ * down to ~1e-15 |p|) the iterates of two correct implementations diverge, the reference's own CPU
+ * path included; parity of the solved Jones is defined for runs where this stays 0. */
+long dirac_b200_noise_decisions(int reset);
 
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 unsigned long long dirac_b200_launch_count(void);

@@ -42,6 +42,8 @@ int orc_rlm_chunk(const orc_problem *P, int k, int t0, int ntiles, double *pblk,
                   double *info);
 double orc_update_w_and_nu(double nu0, double *w, const double *ed, int n, double nulow,
                            double nuhigh);
+/* LM accept/reject decisions taken at rounding level since the last reset (see dirac_oracle.c) */
+long orc_noise_decisions(int reset);
 void orc_lbfgs(const orc_problem *P, double *pp, const double *x, int itmax, int M, int robust,
                double nu);
 int orc_sagefit(const orc_problem *P, double *x, double *pp, int max_emiter, int max_iter,

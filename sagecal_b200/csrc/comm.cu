@@ -1,0 +1,136 @@
+// Collectives of the cluster-sharded solve, called from C on the library's stream.
+//
+// NCCL is bound at run time (dlopen/dlsym), not at link time: a host that never shards never needs
+// it, and inside a PyTorch process the library must use the NCCL that process already carries
+// (torch bundles its own libnccl.so.2) instead of pulling a second copy in.  Resolution order:
+// an already loaded libnccl.so.2, $DIRAC_B200_NCCL_LIB, libnccl.so.2, libnccl.so.
+//
+// The reference merges its two GPUs' results on the host under a pthread barrier
+// (lmfit_cuda.c:1544-1580,1801-1950); here every exchange is one ncclAllReduce(sum, fp64, in place)
+// over NVLink / NVSwitch, enqueued behind the kernels that produced the buffer.
+#include <dlfcn.h>
+#include <string.h>
+#include <time.h>
+
+#include "../../include/dirac_b200.h"
+#include "problem.h"
+
+typedef struct { char internal[128]; } db_ncclUniqueId;  // ncclUniqueId, nccl.h
+typedef void *db_ncclComm_t;
+enum { DB_NCCL_DOUBLE = 8, DB_NCCL_SUM = 0 };            // ncclFloat64, ncclSum
+
+static struct {
+  void *lib;
+  int (*GetUniqueId)(db_ncclUniqueId *);
+  int (*CommInitRank)(db_ncclComm_t *, int, db_ncclUniqueId, int);
+  int (*CommDestroy)(db_ncclComm_t);
+  int (*AllReduce)(const void *, void *, size_t, int, int, db_ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(int);
+  db_ncclComm_t comm;
+  int rank, world;
+} g_nccl;
+
+static double g_comm_seconds = 0.0;   // host time spent enqueueing collectives
+static unsigned long long g_comm_calls = 0, g_comm_bytes = 0;
+
+static int nccl_bind() {
+  if (g_nccl.lib) return 0;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  const char *env = getenv("DIRAC_B200_NCCL_LIB");
+  if (!h && env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    fprintf(stderr, "dirac_b200: cannot load NCCL (%s); set DIRAC_B200_NCCL_LIB\n", dlerror());
+    return -1;
+  }
+  *(void **)&g_nccl.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+  *(void **)&g_nccl.CommInitRank = dlsym(h, "ncclCommInitRank");
+  *(void **)&g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+  *(void **)&g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
+  *(void **)&g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce) {
+    fprintf(stderr, "dirac_b200: the NCCL library lacks a required symbol\n");
+    return -1;
+  }
+  g_nccl.lib = h;
+  return 0;
+}
+
+#define NCCL_CHECK(call)                                                                     \
+  do {                                                                                       \
+    int r__ = (call);                                                                        \
+    if (r__ != 0) {                                                                          \
+      fprintf(stderr, "dirac_b200: NCCL error %d (%s) at %s:%d\n", r__,                      \
+              g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?", __FILE__, __LINE__); \
+      exit(1);                                                                               \
+    }                                                                                        \
+  } while (0)
+
+// rank 0 draws the 128-byte id; the host hands it to every rank (MPI_Bcast, a file, a TCP store)
+extern "C" int dirac_b200_nccl_unique_id(char *id128) {
+  if (nccl_bind()) return -1;
+  db_ncclUniqueId id;
+  NCCL_CHECK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+
+// collective over all ranks: binds the current CUDA device of the calling process to `rank`
+extern "C" int dirac_b200_nccl_init(int rank, int world, const char *id128) {
+  if (nccl_bind()) return -1;
+  if (g_nccl.comm) {
+    g_nccl.CommDestroy(g_nccl.comm);
+    g_nccl.comm = nullptr;
+  }
+  db_ncclUniqueId id;
+  memcpy(id.internal, id128, 128);
+  NCCL_CHECK(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank));
+  g_nccl.rank = rank;
+  g_nccl.world = world;
+  return 0;
+}
+
+extern "C" void dirac_b200_nccl_finalize(void) {
+  if (g_nccl.comm) {
+    cudaDeviceSynchronize();
+    g_nccl.CommDestroy(g_nccl.comm);
+    g_nccl.comm = nullptr;
+  }
+}
+
+extern "C" int dirac_b200_nccl_ready(void) { return g_nccl.comm != nullptr; }
+
+// sum a device buffer of doubles over the ranks (no-op for a single rank); enqueued on the stream
+void db_allreduce(dirac_b200_problem *pr, void *dev, long long count) {
+  if (pr->world <= 1 || count <= 0) return;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (pr->allreduce) {
+    pr->allreduce(dev, count, (void *)pr->d.stream, pr->comm_user);
+  } else {
+    if (!g_nccl.comm || g_nccl.world != pr->world) {
+      fprintf(stderr, "dirac_b200: sharded problem (world %d) without a communicator: call "
+                      "dirac_b200_nccl_init or supply a callback to dirac_b200_set_comm\n", pr->world);
+      exit(1);
+    }
+    NCCL_CHECK(g_nccl.AllReduce(dev, dev, (size_t)count, DB_NCCL_DOUBLE, DB_NCCL_SUM, g_nccl.comm,
+                                pr->d.stream));
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  g_comm_seconds += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  g_comm_calls++;
+  g_comm_bytes += (unsigned long long)count * 8ull;
+}
+
+// host-side accounting of the collectives since the last reset: calls, bytes, seconds spent enqueueing
+extern "C" void dirac_b200_comm_stats(unsigned long long *calls, unsigned long long *bytes,
+                                      double *enqueue_seconds, int reset) {
+  if (calls) *calls = g_comm_calls;
+  if (bytes) *bytes = g_comm_bytes;
+  if (enqueue_seconds) *enqueue_seconds = g_comm_seconds;
+  if (reset) {
+    g_comm_calls = g_comm_bytes = 0;
+    g_comm_seconds = 0.0;
+  }
+}

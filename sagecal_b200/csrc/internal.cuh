@@ -363,6 +363,18 @@ struct BatchAssembleArgs {
   int N, Nbase;
 };
 
+// test / tuning options (dirac_b200_set_option): 0 = default
+enum { DB_OPT_CP_ROWS = 0, DB_OPT_COUNT = 8 };
+int db_opt(int id);
+int db_sm_count();  // SMs of the current device
+// slices of the time axis the linear-mapped gradient pass may use (sizes LMWork::jte_part)
+static inline int db_cp_max_slices(int Nbase, int tilesz) {
+  const int nbg = (Nbase + 255) / 256;
+  int nsl = (db_sm_count() + nbg - 1) / nbg;
+  if ((tilesz + 31) / 32 > nsl) nsl = (tilesz + 31) / 32;  // slices hold at most 32 rows
+  return nsl;
+}
+
 extern "C" {
 void db_launch_coh_to_planar(const double2 *src, double2 *dst, long long r0, int nr, int M,
                              long long R, cudaStream_t st);

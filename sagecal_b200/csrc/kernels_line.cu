@@ -234,6 +234,49 @@ k_axpby(const double2 *__restrict__ x, double2 *__restrict__ y, long long n4, do
   }
 }
 
+// out = beta*in + model_k (sign > 0) or in - model_k + (1-beta)*in2 (sign < 0) for ONE cluster whose
+// hybrid chunk of a row is the ROW-based map px = row / ceil(R/nchunk) of mylm_fit_single_pth
+// (lmfit.c:86): the hidden-data add / subtract of lmfit.c:890-891,980-981 when nchunk does not divide
+// tilesz, i.e. when that map differs from the timeslot ranges the per-chunk LM fits run over.
+__global__ void __launch_bounds__(256)
+k_cluster_rowmap(const double2 *__restrict__ coh_k, const double2 *__restrict__ in,
+                 const double2 *__restrict__ in2, double2 *__restrict__ out,
+                 const unsigned char *__restrict__ flag, const double *__restrict__ pp,
+                 const int *__restrict__ chunk_poff, int nchunk, const short2 *__restrict__ blpq,
+                 long long R, int Nbase, int sign, double beta) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R;
+       r += (long long)gridDim.x * blockDim.x) {
+    const short2 pq = blpq[r % Nbase];
+    const int off = chunk_poff[row_chunk(r, R, nchunk)];
+    double2 Jp[4], Jq[4], C[4], A[4], m[4];
+    load_jones(pp + off, pq.x, Jp);
+    load_jones(pp + off, pq.y, Jq);
+#pragma unroll
+    for (int c = 0; c < 4; c++) C[c] = coh_k[(long long)c * R + r];
+    mat_ab(Jp, C, A);
+    mat_abh(A, Jq, m);
+    const bool fl = flag[r] != 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const long long ix = (long long)c * R + r;
+      const double2 mm = fl ? make_double2(0.0, 0.0) : m[c];
+      const double2 v = in[ix];
+      double2 o;
+      if (sign > 0) {
+        o = make_double2(beta * v.x + mm.x, beta * v.y + mm.y);
+      } else {
+        o = make_double2(v.x - mm.x, v.y - mm.y);
+        if (in2) {
+          const double2 w = in2[ix];
+          o.x += (1.0 - beta) * w.x;
+          o.y += (1.0 - beta) * w.y;
+        }
+      }
+      out[ix] = o;
+    }
+  }
+}
+
 extern "C" {
 #define LINE_TB 2
 void db_launch_line_setup(const LineSetupArgs *a, int ntile, cudaStream_t st) {
@@ -256,6 +299,13 @@ void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, 
 void db_launch_axpby(const double2 *x, double2 *y, long long n4, double a, double b,
                      cudaStream_t st) {
   k_axpby<<<592, 256, 0, st>>>(x, y, n4, a, b);
+}
+void db_launch_cluster_rowmap(const double2 *coh_k, const double2 *in, const double2 *in2,
+                               double2 *out, const unsigned char *flag, const double *pp,
+                               const int *chunk_poff, int nchunk, const short2 *blpq, long long R,
+                               int Nbase, int sign, double beta, cudaStream_t st) {
+  k_cluster_rowmap<<<592, 256, 0, st>>>(coh_k, in, in2, out, flag, pp, chunk_poff, nchunk, blpq, R,
+                                        Nbase, sign, beta);
 }
 void db_launch_line_poly(const double2 *E0, const double2 *E1, const double2 *E2, long long n4,
                          double *partials, double *out, unsigned int *counter, cudaStream_t st) {

@@ -1256,18 +1256,27 @@ void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st
     // default: linear mapping with CTA-wide TMA stages; robust weights and DIRAC_B200_NO_TMA take the
     // register-staged tile kernel
     static const bool no_tma = getenv("DIRAC_B200_NO_TMA") != nullptr;
+    // the linear-mapped kernel keeps 8N station sums in shared memory next to its ring and one
+    // arrival counter per 256-baseline group: arrays too large for either take the tile kernel
+    const bool lin_fits = (size_t)5 * 8 * 256 * sizeof(double2) + sizeof(double) * ((8 * a->N + 1) & ~1) + 40 <=
+                              (size_t)200 * 1024 && (a->Nbase + 255) / 256 <= 1024;
     if (unsplit) {
       k_cluster_pass<true><<<grid, TILE_THREADS, 0, st>>>(*a);
-    } else if (a->wt || no_tma) {
+    } else if (a->wt || no_tma || !lin_fits) {
       k_cluster_pass_split<<<grid, 2 * TILE_THREADS, 0, st>>>(*a);
     } else {
       // linear mapping: 256 baselines per CTA, time sliced to about one CTA per SM (<= 32 rows)
       constexpr int NST = 5;
       const int nbg = (a->Nbase + 255) / 256;
-      int nsl = (148 + nbg - 1) / nbg;
+      int nsl = (db_sm_count() + nbg - 1) / nbg;
       if (nsl > nt) nsl = nt;
       ClusterPassArgs b = *a;
       b.tslice = (nt + nsl - 1) / nsl;
+      // test hook: rows per CTA forced (drives the multi-row ring on small problems), as long as
+      // the slices still fit the per-CTA partial buffer
+      const int forced = db_opt(DB_OPT_CP_ROWS);
+      if (forced > 0 && (nt + forced - 1) / forced <= db_cp_max_slices(a->Nbase, nt)) b.tslice = forced;
+      if (b.tslice > nt) b.tslice = nt;
       if (b.tslice > 32) b.tslice = 32;
       const size_t smem = (size_t)NST * 8 * 256 * sizeof(double2) +
                           sizeof(double) * ((8 * a->N + 1) & ~1) + NST * 8;

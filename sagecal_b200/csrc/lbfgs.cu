@@ -13,6 +13,11 @@
 // instead of a full predict over all clusters, and the residual at the accepted step feeds the
 // gradient pass (k_grad_full) directly.  Per iteration: 2 passes over the coherencies instead of
 // ~30 (cost_func / robust_cost_func, robust_lbfgs.c:674-726; func_grad(_robust), :569-669,322-416).
+//
+// The iterate, the gradient, the search direction and the (s, y) history live on the device; the
+// two-loop recursion is one cluster kernel (kernels_lbfgs.cu).  The host keeps what is scalar: the
+// line search's decisions on costs that come back as a quartic's coefficients (Gaussian) or one
+// number per evaluation (Student's t), and ||g|| for the stopping test.
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -21,6 +26,13 @@
 #include "problem.h"
 
 extern "C" {
+void db_launch_lbfgs_direction(double *pk, const double *gk, const double *s, const double *y,
+                               const double *rho, int m, int npairs, int next, cudaStream_t st);
+void db_launch_lbfgs_nrm2(const double *g, int m, double *out, cudaStream_t st);
+void db_launch_lbfgs_step(const double *xk, const double *pk, const double *gk, double *xk1,
+                          double *sk, double *yk, int m, double alpha, cudaStream_t st);
+void db_launch_lbfgs_update(const double *gk, const double *sk, double *yk, const double *xk1,
+                            double *xk, int m, double *rho_slot, double *out, cudaStream_t st);
 void db_launch_line_setup(const LineSetupArgs *a, int ntile, cudaStream_t st);
 void db_launch_line_eval(const double2 *E0, const double2 *E1, const double2 *E2, long long n4,
                          double alpha, int mode, double inv_nu, double *partials, double *out,
@@ -48,19 +60,15 @@ static void line_alloc(dirac_b200_problem *pr) {
   pr->E0 = (decltype(pr->E0))db_malloc(sizeof(double2) * n * 3);
   pr->E1 = pr->E0 + n;
   pr->E2 = pr->E1 + n;
-  pr->pk_dev = (decltype(pr->pk_dev))db_malloc(sizeof(double) * d.npar);
 }
 
-// line model along pk from xk (both host vectors)
+// line model along pk from xk (both device vectors)
 static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
   dirac_b200_problem *pr = c->pr;
   DevProblem &d = pr->d;
   line_alloc(pr);
-  DB_CHECK(cudaMemcpyAsync(d.pp, xk, sizeof(double) * c->m, cudaMemcpyHostToDevice, d.stream));
-  DB_CHECK(cudaMemcpyAsync(pr->pk_dev, pk, sizeof(double) * c->m, cudaMemcpyHostToDevice,
-                           d.stream));
   LineSetupArgs a;
-  a.coh = d.coh; a.x = d.x; a.flag = d.flag; a.xk = d.pp; a.pk = pr->pk_dev; a.clus = d.clus;
+  a.coh = d.coh; a.x = d.x; a.flag = d.flag; a.xk = xk; a.pk = pk; a.clus = d.clus;
   a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.E0 = pr->E0; a.E1 = pr->E1; a.E2 = pr->E2;
   a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.tilesz = d.tilesz; a.M = d.M;
   a.partial = (pr->world > 1) ? 1 : 0;
@@ -112,60 +120,19 @@ static double line_cost(LbfgsCtx *c, double alpha) {
   return db_read_scalar(pr, 0);
 }
 
-// gradient at p (host); if from_line, the residual is taken from the line model at alpha
+// gradient at p (device) into g (device); if from_line, the residual is taken from the line model at
+// alpha instead of a fresh predict
 static void grad_eval(LbfgsCtx *c, const double *p, double *g, bool from_line, double alpha) {
   dirac_b200_problem *pr = c->pr;
   DevProblem &d = pr->d;
-  DB_CHECK(cudaMemcpyAsync(d.pp, p, sizeof(double) * c->m, cudaMemcpyHostToDevice, d.stream));
   if (from_line) {
     db_launch_line_residual(pr->E0, pr->E1, pr->E2, pr->res, 4 * d.R, alpha, d.stream);
     db_count_launch(1);
   } else {
-    db_predict_dev(pr, d.pp, pr->res, 1, 0, 0.0, 0);
+    db_predict_dev(pr, p, pr->res, 1, 0, 0.0, 0);
   }
-  db_grad_dev(pr, d.pp, pr->g, c->robust, c->nu);
-  DB_CHECK(cudaMemcpyAsync(g, pr->g, sizeof(double) * c->m, cudaMemcpyDeviceToHost, d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_grad_dev(pr, p, g, c->robust, c->nu);
   c->ngrad++;
-}
-
-static inline double vdot(const double *a, const double *b, int m) {
-  double s = 0.0;
-  for (int i = 0; i < m; i++) s += a[i] * b[i];
-  return s;
-}
-static inline void vaxpy(double *y, const double *x, double a, int m) {  // y += a x
-  for (int i = 0; i < m; i++) y[i] += a * x[i];
-}
-static inline double vnrm2(const double *a, int m) { return sqrt(vdot(a, a, m)); }
-
-// pk = H_k gk by the two-loop recursion; M = number of valid pairs, ii = slot to be written next
-static void mult_hessian(int m, double *pk, const double *gk, const double *s, const double *y,
-                         const double *rho, int M, int ii) {
-  std::vector<double> alphai(M > 0 ? M : 1);
-  std::vector<int> idx(M > 0 ? M : 1);
-  if (M > 0) {
-    ii = (ii > 0) ? ii - 1 : M - 1;
-    for (int ci = 0; ci < M - ii - 1; ci++) idx[ci] = ii + ci + 1;
-    for (int ci = M - ii - 1; ci < M; ci++) idx[ci] = ci - M + ii + 1;
-  }
-  memcpy(pk, gk, sizeof(double) * m);
-  for (int ci = 0; ci < M; ci++) {
-    int j = idx[M - ci - 1];
-    alphai[M - ci - 1] = rho[j] * vdot(&s[(size_t)m * j], pk, m);
-    vaxpy(pk, &y[(size_t)m * j], -alphai[M - ci - 1], m);
-  }
-  if (M > 0) {
-    int j = idx[M - 1];
-    double gamma = vdot(&s[(size_t)m * j], &y[(size_t)m * j], m);
-    gamma /= vdot(&y[(size_t)m * j], &y[(size_t)m * j], m);
-    for (int i = 0; i < m; i++) pk[i] *= gamma;
-  }
-  for (int ci = 0; ci < M; ci++) {
-    int j = idx[ci];
-    double beta = rho[j] * vdot(&y[(size_t)m * j], pk, m);
-    vaxpy(pk, &s[(size_t)m * j], alphai[ci] - beta, m);
-  }
 }
 
 // In the three functions below `xa` is the position of the reference's scratch vector xp along
@@ -307,8 +274,10 @@ static double linesearch(LbfgsCtx *c, double alpha1, double sigma, double rho, d
 }
 
 // p: m x 1 in/out (host).  robust != 0 -> Student's-t cost with nu.
+// Iteration logic of lbfgs_fit_fullbatch (lbfgs.c:479-640); vectors on the device.
 void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, int robust,
                   double nu) {
+  DevProblem &d = pr->d;
   LbfgsCtx ctx;
   ctx.pr = pr;
   ctx.robust = robust;
@@ -316,12 +285,19 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
   ctx.m = m;
   ctx.ncost = ctx.ngrad = 0;
   if (M < 1) M = 1;
-  std::vector<double> gk(m), xk1(m), xk(m), pk(m), s((size_t)m * M), y((size_t)m * M), rho(M);
+  if (M > 64) M = 64;  // k_lbfgs_direction keeps the alpha_i of one recursion in shared memory
+  // one allocation: xk | xk1 | gk | pk | s[M] | y[M] | rho[M]
+  double *ws = (double *)db_malloc(sizeof(double) * ((size_t)m * (4 + 2 * (size_t)M) + M + 8));
+  double *xk = ws, *xk1 = xk + m, *gk = xk1 + m, *pk = gk + m, *s = pk + m,
+         *y = s + (size_t)m * M, *rho = y + (size_t)m * M;
+  double *nrm_dev = d.scal + 24;
   double step, alphak;
   int ck, ci, cm;
-  memcpy(xk.data(), p, sizeof(double) * m);
-  grad_eval(&ctx, xk.data(), gk.data(), false, 0.0);
-  double gradnrm = vnrm2(gk.data(), m);
+  DB_CHECK(cudaMemcpyAsync(xk, p, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
+  grad_eval(&ctx, xk, gk, false, 0.0);
+  db_launch_lbfgs_nrm2(gk, m, nrm_dev, d.stream);
+  db_count_launch(1);
+  double gradnrm = sqrt(db_read_scalar(pr, 24));
   const double STOP = 1e-17;  // CLM_STOP_THRESH, Dirac_common.h:43
   if (gradnrm < STOP) {
     ck = itmax;
@@ -335,24 +311,18 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
   cm = 0;
   ci = 0;
   while (ck < itmax && isnormal(gradnrm) && gradnrm > STOP) {
-    mult_hessian(m, pk.data(), gk.data(), s.data(), y.data(), rho.data(), ck < M ? ck : M, ci);
-    for (int i = 0; i < m; i++) pk[i] = -pk[i];
-    line_setup(&ctx, xk.data(), pk.data());
+    db_launch_lbfgs_direction(pk, gk, s, y, rho, m, ck < M ? ck : M, ci, d.stream);
+    db_count_launch(1);
+    line_setup(&ctx, xk, pk);
     alphak = linesearch(&ctx, 10.0, 0.1, 0.01, 9, 0.1, 0.5, step);
     if (!isnormal(alphak) || fabs(alphak) < 1e-12) break;  // CLM_EPSILON
-    memcpy(xk1.data(), xk.data(), sizeof(double) * m);
-    vaxpy(xk1.data(), pk.data(), alphak, m);
-    double *sk = &s[(size_t)cm];
-    double *yk = &y[(size_t)cm];
-    for (int i = 0; i < m; i++) {
-      sk[i] = xk1[i] - xk[i];
-      yk[i] = -gk[i];
-    }
-    grad_eval(&ctx, xk1.data(), gk.data(), true, alphak);
-    gradnrm = vnrm2(gk.data(), m);
-    vaxpy(yk, gk.data(), 1.0, m);
-    rho[ci] = 1.0 / vdot(yk, sk, m);
-    memcpy(xk.data(), xk1.data(), sizeof(double) * m);
+    double *sk = s + (size_t)cm;
+    double *yk = y + (size_t)cm;
+    db_launch_lbfgs_step(xk, pk, gk, xk1, sk, yk, m, alphak, d.stream);
+    grad_eval(&ctx, xk1, gk, true, alphak);
+    db_launch_lbfgs_update(gk, sk, yk, xk1, xk, m, rho + ci, nrm_dev, d.stream);
+    db_count_launch(2);
+    gradnrm = sqrt(db_read_scalar(pr, 24));
     ck++;
     if (cm < (M - 1) * m) {
       cm += m;
@@ -361,5 +331,7 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
       cm = ci = 0;
     }
   }
-  memcpy(p, xk.data(), sizeof(double) * m);
+  DB_CHECK(cudaMemcpyAsync(p, xk, sizeof(double) * m, cudaMemcpyDeviceToHost, d.stream));
+  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_free(ws);
 }

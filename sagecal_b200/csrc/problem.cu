@@ -69,6 +69,26 @@ cudaStream_t db_new_stream(int *owned) {
   return st;
 }
 
+// ---- test / tuning options ------------------------------------------------------------------------
+static int g_opt[DB_OPT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+int db_opt(int id) { return (id >= 0 && id < DB_OPT_COUNT) ? g_opt[id] : 0; }
+extern "C" int dirac_b200_set_option(const char *name, int value) {
+  if (!strcmp(name, "cp_rows")) { g_opt[DB_OPT_CP_ROWS] = value; return 0; }
+  return -1;
+}
+// SMs of the current device (grids of the one-wave kernels are sized from it)
+int db_sm_count() {
+  static int n[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!n[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev] = v;
+  }
+  return n[dev];
+}
+
 static void require_gpu() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -185,10 +205,6 @@ extern "C" void dirac_b200_set_comm(dirac_b200_problem *pr, int rank, int world,
   pr->beta = (beta > 0.0) ? beta : 1.0 / (double)(world > 0 ? world : 1);
 }
 
-// sum a device buffer of doubles over the ranks (no-op for a single rank)
-void db_allreduce(dirac_b200_problem *pr, void *dev, long long count) {
-  if (pr->world > 1) pr->allreduce(dev, count, (void *)pr->d.stream, pr->comm_user);
-}
 
 static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const baseline_t *barr,
                                        const clus_source_t *carr, int M, int Mt, const double *coh,
@@ -322,7 +338,8 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   db_free(d.chunk_poff); db_free(d.tiles); db_free(d.blpq); db_free(d.scal); db_free(d.counters);
   db_free(pr->partials); db_free(pr->res); db_free(pr->g); db_free(pr->vis_stage);
   if (pr->pm) db_free(pr->pm);
-  if (pr->E0) { db_free(pr->E0); db_free(pr->pk_dev); }  // E1, E2 live inside E0's allocation
+  if (pr->xb) { db_free(pr->xb); db_free(pr->pp_start); }
+  if (pr->E0) db_free(pr->E0);  // E1, E2 live inside E0's allocation
   cudaFreeHost(d.h_scal);
   free(d.h_clus); free(d.h_chunk_poff);
   if (pr->own_stream) cudaStreamDestroy(d.stream);

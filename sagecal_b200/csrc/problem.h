@@ -65,10 +65,11 @@ struct dirac_b200_problem {
   int m_global;           // clusters over all ranks
   int k_global0;          // global index of local cluster 0
   double beta;            // hidden-data weight of the sharded SAGE sweep (1/world by default)
-  double2 *pm;            // [4][R] partial model / residual-delta staging
+  double2 *pm;            // [4][R] partial model / residual at the start of a sharded sweep
+  double *xb;             // [8R + npar + m_global] sweep exchange message (sharded)
+  double *pp_start;       // [npar] Jones at the start of a sharded sweep
   // LBFGS line model (allocated on first use)
   double2 *E0, *E1, *E2;  // [4][R] each
-  double *pk_dev;         // [8*N*Mt] search direction
 };
 
 void *db_malloc(size_t bytes);
@@ -94,5 +95,10 @@ void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, 
                              double *cost, unsigned int *counter, cudaStream_t st);
 void db_launch_axpby(const double2 *x, double2 *y, long long n4, double a, double b,
                      cudaStream_t st);
+void db_launch_cluster_rowmap(const double2 *coh_k, const double2 *in, const double2 *in2,
+                              double2 *out, const unsigned char *flag, const double *pp,
+                              const int *chunk_poff, int nchunk, const short2 *blpq, long long R,
+                              int Nbase, int sign, double beta, cudaStream_t st);
 }
+
 void db_lm_free(dirac_b200_problem *pr);

@@ -12,10 +12,13 @@
 #include "problem.h"
 
 void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
-                 const double *opts, int linsolv, int os, int randomize, double *info);
+                 const double *opts, int linsolv, int os, int randomize, double *info,
+                 bool hidden_ready);
 void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
                   int linsolv, int os, int randomize, double nulow, double nuhigh,
-                  double *robust_nu, double *info);
+                  double *robust_nu, double *info, bool hidden_ready);
+bool db_cluster_needs_rowmap(const dirac_b200_problem *pr, int k);
+void db_cluster_hidden(dirac_b200_problem *pr, int k, double2 *r, int sign);
 void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, int robust,
                   double nu);
 
@@ -30,18 +33,28 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
                                   int max_emiter, int max_iter, int max_lbfgs, int lbfgs_m,
                                   int linsolv, int solver_mode, double nulow, double nuhigh,
                                   int randomize, double *mean_nu, double *res_0, double *res_1) {
-  if (solver_mode == SM_RTR_OSLM_LBFGS || solver_mode == SM_RTR_OSRLM_RLBFGS ||
-      solver_mode == SM_NSD_RLBFGS) {
-    fprintf(stderr, "dirac_b200: solver_mode %d (RTR/NSD) is outside this library's scope; use "
-                    "0-3 (LM / OS-LM / robust LM + LBFGS)\n", solver_mode);
-    exit(1);
-  }
   if (solver_mode < 0 || solver_mode > 6) {
     fprintf(stderr, "%s: %d: undefined solver mode\n", __FILE__, __LINE__);  // lmfit.c:957-962
     exit(1);
   }
+  if (solver_mode == SM_RTR_OSLM_LBFGS || solver_mode == SM_RTR_OSRLM_RLBFGS ||
+      solver_mode == SM_NSD_RLBFGS) {
+    // The Riemannian trust-region / nested-SD solvers (rtr_solve*.c; the driver's default -j 5,
+    // src/MS/data.cpp:69) are not part of this library.  A host linked against it
+    // must not die on its default settings: solve with the LM-family mode of the same noise model
+    // (4 -> OS-LM + LBFGS, 5 and 6 -> OS-LM / OS robust LM + robust LBFGS) and say so once.
+    static bool warned = false;
+    const int mapped = (solver_mode == SM_RTR_OSLM_LBFGS) ? SM_OSLM_LBFGS : SM_OSLM_OSRLM_RLBFGS;
+    if (!warned) {
+      fprintf(stderr, "dirac_b200: solver_mode %d (RTR/NSD) is not implemented; solving with "
+                      "solver_mode %d (same noise model, LM family). Use -j 0..3 to silence this.\n",
+              solver_mode, mapped);
+      warned = true;
+    }
+    solver_mode = mapped;
+  }
   DevProblem &d = pr->d;
-  const int N = d.N, M = d.M, Mt = d.Mt;
+  const int M = d.M;
   const int m = (int)pr->d.npar;
   const long long n = (long long)d.Nbase * d.tilesz * 8;
   const ClusterDesc *hc = d.h_clus;
@@ -57,13 +70,18 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
   const bool sharded = pr->world > 1;
   const int MG = sharded ? pr->m_global : M;
   const int k0 = sharded ? pr->k_global0 : 0;
-  std::vector<double> nerr(MG, 0.0), robust_nuM(MG, 0.0), pp_start, hsum;
+  std::vector<double> nerr(MG, 0.0), robust_nuM(MG, 0.0);
   const bool robust = is_robust_mode(solver_mode);
+  // Sharded sweep exchange: ONE message per sweep, [residual delta | Jones delta | nerr], formed on
+  // the device, summed over the ranks by one all-reduce on the library's stream
+  const size_t xb_len = (size_t)8 * d.R + (size_t)m + (size_t)MG;
   if (sharded) {
     db_lm_init(pr);
     if (!pr->pm) pr->pm = (decltype(pr->pm))db_malloc(sizeof(double2) * 4 * d.R);
-    pp_start.resize(m);
-    hsum.resize(m > MG ? m : MG);
+    if (!pr->xb) {
+      pr->xb = (double *)db_malloc(sizeof(double) * (xb_len + 8));
+      pr->pp_start = (double *)db_malloc(sizeof(double) * ((size_t)m + 8));
+    }
   }
   // sum a small host vector over the ranks through the device scratch pr->g
   auto allreduce_host = [&](double *v, int cnt) {
@@ -87,9 +105,8 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
       // remember the state every rank starts the sweep from
       DB_CHECK(cudaMemcpyAsync(pr->pm, r, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice,
                                d.stream));
-      DB_CHECK(cudaMemcpyAsync(pp_start.data(), d.pp, sizeof(double) * m, cudaMemcpyDeviceToHost,
+      DB_CHECK(cudaMemcpyAsync(pr->pp_start, d.pp, sizeof(double) * m, cudaMemcpyDeviceToDevice,
                                d.stream));
-      DB_CHECK(cudaStreamSynchronize(d.stream));
       for (int g = 0; g < MG; g++)
         if (g < k0 || g >= k0 + M) nerr[g] = 0.0;  // other ranks' entries come back by the sum
     }
@@ -110,36 +127,41 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
       }
       if (this_itermax > 0) {
         double init_res = 0.0, final_res = 0.0;
+        // hybrid chunks that do not tile the interval evenly: hidden data and residual of the whole
+        // cluster with the reference's row-based chunk map, the LM fits in between
+        const bool hr = db_cluster_needs_rowmap(pr, cj);
+        if (hr) db_cluster_hidden(pr, cj, r, +1);
         for (int ck = 0; ck < hc[cj].nchunk; ck++) {
           double *pblk = d.pp + d.h_chunk_poff[hc[cj].chunk0 + ck];
           const bool last = (ci == max_emiter - 1);
           if (solver_mode == SM_OSLM_LBFGS) {
             db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, last ? 0 : 1, randomize,
-                        info);
+                        info, hr);
           } else if (solver_mode == SM_LM_LBFGS) {
-            db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 0, randomize, info);
+            db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 0, randomize, info, hr);
           } else if (solver_mode == SM_RLM_RLBFGS) {
             if (last) {
               double nu = robust_nu0;
               db_rlm_chunk(pr, cj, ck, pblk, r, this_itermax, linsolv, 0, randomize, nulow, nuhigh,
-                           &nu, info);
+                           &nu, info, hr);
               robust_nuM[cg] += nu;
             } else {
-              db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info);
+              db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info, hr);
             }
           } else {  // SM_OSLM_OSRLM_RLBFGS
             if (last) {
               double nu = robust_nu0;
               db_rlm_chunk(pr, cj, ck, pblk, r, this_itermax, linsolv, 1, randomize, nulow, nuhigh,
-                           &nu, info);
+                           &nu, info, hr);
               robust_nuM[cg] += nu;
             } else {
-              db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info);
+              db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info, hr);
             }
           }
           init_res += info[0];
           final_res += info[1];
         }
+        if (hr) db_cluster_hidden(pr, cj, r, -1);
         if (init_res > 0.0) {
           nerr[cg] = (init_res - final_res) / init_res;
           if (nerr[cg] < 0.0) nerr[cg] = 0.0;
@@ -150,26 +172,28 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
       }
     }
     if (sharded) {
-      // ONE all-reduce of the residual delta per sweep: r <- r_start + sum_ranks (r_local - r_start)
-      LMWork &w = pr->lm;
-      DB_CHECK(cudaMemcpyAsync(w.dbuf, r, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice,
-                               d.stream));
-      db_launch_axpby(pr->pm, w.dbuf, 4 * d.R, -1.0, 1.0, d.stream);   // dbuf = r - r_start
-      db_allreduce(pr, w.dbuf, 8 * d.R);
+      // r <- r_start + sum_ranks (r_local - r_start), pp <- pp_start + sum_ranks (pp_local - pp_start)
+      // (every rank changed only its own clusters' Jones blocks), nerr <- sum of the local entries
+      double *xb = pr->xb;
+      double2 *xr = reinterpret_cast<double2 *>(xb);
+      double2 *xp = reinterpret_cast<double2 *>(xb + (size_t)8 * d.R);
+      DB_CHECK(cudaMemcpyAsync(xr, r, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice, d.stream));
+      db_launch_axpby(pr->pm, xr, 4 * d.R, -1.0, 1.0, d.stream);
+      DB_CHECK(cudaMemcpyAsync(xp, d.pp, sizeof(double) * m, cudaMemcpyDeviceToDevice, d.stream));
+      db_launch_axpby(reinterpret_cast<double2 *>(pr->pp_start), xp, m / 2, -1.0, 1.0, d.stream);
+      DB_CHECK(cudaMemcpyAsync(xb + (size_t)8 * d.R + m, nerr.data(), sizeof(double) * MG,
+                               cudaMemcpyHostToDevice, d.stream));
+      db_allreduce(pr, xb, (long long)xb_len);
+      DB_CHECK(cudaMemcpyAsync(nerr.data(), xb + (size_t)8 * d.R + m, sizeof(double) * MG,
+                               cudaMemcpyDeviceToHost, d.stream));
       DB_CHECK(cudaMemcpyAsync(r, pr->pm, sizeof(double2) * 4 * d.R, cudaMemcpyDeviceToDevice,
                                d.stream));
-      db_launch_axpby(w.dbuf, r, 4 * d.R, 1.0, 1.0, d.stream);         // r = r_start + sum delta
-      // Jones: every rank changed only its own clusters' blocks
-      DB_CHECK(cudaMemcpyAsync(hsum.data(), d.pp, sizeof(double) * m, cudaMemcpyDeviceToHost,
+      db_launch_axpby(xr, r, 4 * d.R, 1.0, 1.0, d.stream);
+      DB_CHECK(cudaMemcpyAsync(d.pp, pr->pp_start, sizeof(double) * m, cudaMemcpyDeviceToDevice,
                                d.stream));
-      DB_CHECK(cudaStreamSynchronize(d.stream));
-      for (int i = 0; i < m; i++) hsum[i] -= pp_start[i];
-      allreduce_host(hsum.data(), m);
-      for (int i = 0; i < m; i++) hsum[i] += pp_start[i];
-      DB_CHECK(cudaMemcpyAsync(d.pp, hsum.data(), sizeof(double) * m, cudaMemcpyHostToDevice,
-                               d.stream));
-      DB_CHECK(cudaStreamSynchronize(d.stream));
-      allreduce_host(nerr.data(), MG);
+      db_launch_axpby(xp, reinterpret_cast<double2 *>(d.pp), m / 2, 1.0, 1.0, d.stream);
+      db_count_launch(4);
+      DB_CHECK(cudaStreamSynchronize(d.stream));  // nerr steers the next sweep's iteration budgets
     }
     double total_err = 0.0;
     for (int cj = 0; cj < MG; cj++) total_err += fabs(nerr[cj]);

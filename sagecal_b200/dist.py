@@ -1,15 +1,16 @@
 """Cluster-sharded calibration over the GPUs of one box.
 
-One process per GPU (`torch.distributed`, backend nccl).  Each rank owns a contiguous block of
-clusters — its slice of the coherencies, by far the largest array — while the data, the residual
-and the Jones vector are replicated.  All solver logic stays in the C library; the only thing the
-host supplies is the collective: a C callback that sums a device buffer of doubles over the ranks,
-implemented here with `torch.distributed.all_reduce` (NCCL over NVLink / NVSwitch) on a zero-copy
-tensor view of the library's buffer, enqueued on the library's stream.
+One process per GPU.  Each rank owns a contiguous block of clusters — its slice of the
+coherencies, by far the largest array — while the data, the residual and the Jones vector are
+replicated.  All solver logic AND the collectives live in the C library: it calls ncclAllReduce on
+its own stream through a communicator it owns (`dirac_b200_nccl_init`, csrc/comm.cu).  The host only
+has to carry the 128-byte NCCL id from rank 0 to the others; here `torch.distributed` does that
+(`init_nccl`).  A host-supplied callback (`make_allreduce`) is still accepted — the gloo CPU tests of
+the plumbing use it.
 
-Collectives per solve: ONE all-reduce of the residual delta (8*Nbase*tilesz doubles) per SAGE
-sweep, plus the Jones delta and two tiny bookkeeping vectors; in the LBFGS stage one all-reduce
-of the line model (three vectors, contiguous) per iteration and one of the gradient.
+Collectives per solve: ONE all-reduce per SAGE sweep ([residual delta | Jones delta | nerr] in one
+message); in the LBFGS stage one all-reduce of the line model (three vectors, contiguous) per
+iteration and one of the gradient.
 """
 from __future__ import annotations
 
@@ -65,10 +66,29 @@ def make_allreduce(device="cuda"):
     return cb
 
 
+def init_nccl(api, rank: int, world: int):
+    """create the library's own NCCL communicator; the id travels over the default process group"""
+    import torch
+    import torch.distributed as dist
+    L = api.lib
+    L.dirac_b200_nccl_unique_id.argtypes = [C.c_char_p]
+    L.dirac_b200_nccl_init.argtypes = [C.c_int, C.c_int, C.c_char_p]
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        if L.dirac_b200_nccl_unique_id(buf) != 0:
+            raise RuntimeError("dirac_b200_nccl_unique_id failed")
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    ident = bytes(t.cpu().tolist())
+    if L.dirac_b200_nccl_init(rank, world, ident) != 0:
+        raise RuntimeError("dirac_b200_nccl_init failed")
+
+
 class ShardedProblem:
     """this rank's shard of a solve interval, resident on its GPU"""
 
-    def __init__(self, api, pr, barr, rank, world, beta=0.0, coh_local=None):
+    def __init__(self, api, pr, barr, rank, world, beta=0.0, coh_local=None, use_callback=False):
         """pr: sagecal_b200.synth.Problem with ALL clusters (coh may be None when coh_local is
         given or generated on the device)"""
         self.api = api
@@ -93,7 +113,13 @@ class ShardedProblem:
                                            self.sky.Mt, self.npar,
                                            cptr(coh_local) if coh_local is not None else None,
                                            dptr(pr.x))
-        self._cb = make_allreduce("cuda")
+        L.dirac_b200_nccl_ready.restype = C.c_int
+        if use_callback:
+            self._cb = make_allreduce("cuda")
+        else:
+            if not L.dirac_b200_nccl_ready():
+                init_nccl(api, rank, world)
+            self._cb = None  # NULL: the library's own ncclAllReduce
         L.dirac_b200_set_comm(self.h, rank, world, self._cb, None, pr.M, self.k0, float(beta))
 
     def sagefit(self, pp, x_out=None, max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, linsolv=0,

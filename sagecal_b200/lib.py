@@ -23,6 +23,9 @@ EXPORTED = [
     "dirac_b200_set_stream", "dirac_b200_profile_enable", "dirac_b200_profile_read",
     "dirac_b200_kernel_count", "dirac_b200_normal_eq_weighted", "dirac_b200_create_shard",
     "dirac_b200_set_comm", "dirac_b200_spd_solve", "dirac_b200_tri_solve",
+    "dirac_b200_set_option", "dirac_b200_nccl_unique_id", "dirac_b200_nccl_init",
+    "dirac_b200_nccl_finalize", "dirac_b200_nccl_ready", "dirac_b200_comm_stats",
+    "dirac_b200_noise_decisions",
 ]
 
 
@@ -65,6 +68,16 @@ class DiracB200(DiracAPI):
         L.dirac_b200_profile_enable.argtypes = [i]
         L.dirac_b200_profile_read.restype = i
         L.dirac_b200_profile_read.argtypes = [i, dp, dp]
+        L.dirac_b200_set_option.restype = i
+        L.dirac_b200_set_option.argtypes = [C.c_char_p, i]
+
+    def set_option(self, name: str, value: int):
+        if self.lib.dirac_b200_set_option(name.encode(), int(value)) != 0:
+            raise KeyError(name)
+
+    def noise_decisions(self, reset=False) -> int:
+        self.lib.dirac_b200_noise_decisions.restype = C.c_long
+        return int(self.lib.dirac_b200_noise_decisions(1 if reset else 0))
 
     def launch_count(self) -> int:
         return int(self.lib.dirac_b200_launch_count())

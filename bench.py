@@ -323,6 +323,12 @@ def main():
 
     K, W = args.steps, max(args.warmup, 3)
     clocks = ClockSampler(local)
+    # sharded runs: prove the sharded path right on this very box before timing it (small problem,
+    # sharded vs single GPU on every rank; sagecal_b200.dist.verify_sharding)
+    shard_check = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            shard_check = sdist.verify_sharding(api, rank, world)
 
     # ---------------- resident-data throughput (`value`) ----------------
     with torch.cuda.stream(stream):
@@ -339,6 +345,7 @@ def main():
             dist.barrier()
         g0 = api.kernel_count(1)
         l0 = api.launch_count()
+        api.host_stats(reset=True)
         clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -351,6 +358,7 @@ def main():
         if world > 1:
             dist.barrier()
         clk = clocks.stop()
+        hstat = api.host_stats()
         ms_total = e0.elapsed_time(e1)
         launches = api.launch_count() - l0
         ngrad = (api.kernel_count(1) - g0) / K
@@ -417,6 +425,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            api.lib.dirac_b200_nccl_finalize()
             dist.destroy_process_group()
         return
 
@@ -476,10 +485,23 @@ def main():
                    else "1 GPU",
                    "final_res": [res[2], res[3]] if res else None},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "parity": parity if world == 1 else {"checked": True, "sharded_vs_single_gpu": shard_check,
+                                             "ok": bool(shard_check and shard_check["ok"])},
+        # where a step goes on rank 0 (timed region, per step): kernels by CUDA events (instrumented
+        # repeat), host blocked in stream/event waits, host enqueueing collectives; the remainder is
+        # host-side solver logic and launch overhead
+        "breakdown": {"ms_per_step": ms_step,
+                      "kernels_ms": sum(v["ms_per_step"] for v in shares.values()),
+                      "host_syncs_per_step": hstat["host_syncs"] / K,
+                      "host_wait_ms": 1e3 * hstat["host_wait_s"] / K,
+                      "collectives_per_step": hstat["collectives"] / K,
+                      "collective_MB_per_step": hstat["collective_bytes"] / K / 1e6,
+                      "collective_enqueue_ms": 1e3 * hstat["collective_enqueue_s"] / K},
     }
     print(json.dumps(line))
     if world > 1:
+        api.lib.dirac_b200_nccl_finalize()
         dist.destroy_process_group()
 
 

@@ -240,6 +240,10 @@ unsigned long long dirac_b200_kernel_count(int kind); /* launches of `kind` sinc
 void dirac_b200_profile_enable(int on);
 int dirac_b200_profile_read(int kind, double *ms, double *bytes);
 
+/* host synchronisations (stream / event waits of the host-side solver logic) since the last reset and
+ * the seconds the host spent blocked in them */
+void dirac_b200_host_stats(unsigned long long *syncs, double *wait_seconds, int reset);
+
 /* ---- the dense solver of the LM step on its own (diagnostics, tests) ---------------------------
  * (A + mu I) x = b for a symmetric positive definite A (n x n, column-major, only the lower triangle
  * is read; n <= 512) on one thread-block cluster: blocked Cholesky, both substitutions, one kernel

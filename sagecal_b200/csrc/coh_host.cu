@@ -70,7 +70,7 @@ static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream
                            cudaMemcpyHostToDevice, st));
   DB_CHECK(cudaMemcpyAsync(sky->segs, segs.data(), sizeof(CohSegment) * segs.size(),
                            cudaMemcpyHostToDevice, st));
-  DB_CHECK(cudaStreamSynchronize(st));  // the vectors go out of scope
+  db_stream_sync(st);  // the vectors go out of scope
   sky->nseg = (int)segs.size();
 }
 
@@ -107,10 +107,10 @@ extern "C" void dirac_b200_precalculate(dirac_b200_problem *pr, const double *u,
   if (barr) {
     std::vector<unsigned char> hf(d.R);
     DB_CHECK(cudaMemcpyAsync(hf.data(), d.flag, d.R, cudaMemcpyDeviceToHost, d.stream));
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    db_stream_sync(d.stream);
     for (long long r = 0; r < d.R; r++) barr[r].flag = hf[r];
   }
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
   DB_CHECK(cudaGetLastError());
   cudaFree(du); cudaFree(dv); cudaFree(dw); cudaFree(df);
   sky_free(&sky);
@@ -165,7 +165,7 @@ extern "C" int precalculate_coherencies(double *u, double *v, double *w, double 
                              cudaMemcpyDeviceToHost, st));
   }
   DB_CHECK(cudaMemcpyAsync(hf.data(), dflag, R, cudaMemcpyDeviceToHost, st));
-  DB_CHECK(cudaStreamSynchronize(st));
+  db_stream_sync(st);
   DB_CHECK(cudaGetLastError());
   for (long long r = 0; r < R; r++) barr[r].flag = hf[r];
   cudaFree(stage); cudaFree(dcoh); cudaFree(dflag);
@@ -212,7 +212,7 @@ extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, d
   db_launch_predict_multifreq(&a, st);
   db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(x, dx, sizeof(double2) * nx, cudaMemcpyDeviceToHost, st));
-  DB_CHECK(cudaStreamSynchronize(st));
+  db_stream_sync(st);
   DB_CHECK(cudaGetLastError());
   cudaFree(dx); cudaFree(du); cudaFree(dv); cudaFree(dw); cudaFree(df);
   sky_free(&sky);

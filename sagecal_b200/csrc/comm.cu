@@ -134,3 +134,33 @@ extern "C" void dirac_b200_comm_stats(unsigned long long *calls, unsigned long l
     g_comm_seconds = 0.0;
   }
 }
+
+// ---- host waits ------------------------------------------------------------------------------------
+static double g_wait_seconds = 0.0;
+static unsigned long long g_wait_calls = 0;
+static inline double now_s() {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+void db_stream_sync(cudaStream_t st) {
+  const double t0 = now_s();
+  DB_CHECK(cudaStreamSynchronize(st));
+  g_wait_seconds += now_s() - t0;
+  g_wait_calls++;
+}
+void db_event_sync(cudaEvent_t ev) {
+  const double t0 = now_s();
+  DB_CHECK(cudaEventSynchronize(ev));
+  g_wait_seconds += now_s() - t0;
+  g_wait_calls++;
+}
+// host synchronisations since the last reset and the seconds the host spent blocked in them
+extern "C" void dirac_b200_host_stats(unsigned long long *syncs, double *wait_seconds, int reset) {
+  if (syncs) *syncs = g_wait_calls;
+  if (wait_seconds) *wait_seconds = g_wait_seconds;
+  if (reset) {
+    g_wait_calls = 0;
+    g_wait_seconds = 0.0;
+  }
+}

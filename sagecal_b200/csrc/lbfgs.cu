@@ -91,7 +91,7 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
     db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);
     db_count_launch(1);
   }
-  if (!c->robust) {
+  if (!c->robust && !db_opt(DB_OPT_LINE_DIRECT)) {
     // the Gaussian cost along the line is a quartic in alpha: five reductions, then every cost
     // evaluation of the line search is arithmetic on the host
     db_launch_line_poly(pr->E0, pr->E1, pr->E2, 4 * d.R, pr->partials, d.scal + 16, d.counters,
@@ -99,7 +99,7 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
     db_count_launch(1);
     DB_CHECK(cudaMemcpyAsync(d.h_scal + 16, d.scal + 16, 5 * sizeof(double), cudaMemcpyDeviceToHost,
                              d.stream));
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    db_stream_sync(d.stream);
     for (int j = 0; j < 5; j++) c->poly[j] = d.h_scal[16 + j];
   }
 }
@@ -108,7 +108,7 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
 static double line_cost(LbfgsCtx *c, double alpha) {
   dirac_b200_problem *pr = c->pr;
   DevProblem &d = pr->d;
-  if (!c->robust) {
+  if (!c->robust && !db_opt(DB_OPT_LINE_DIRECT)) {
     c->ncost++;
     const double *q = c->poly;
     return q[0] + alpha * (q[1] + alpha * (q[2] + alpha * (q[3] + alpha * q[4])));
@@ -332,6 +332,6 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
     }
   }
   DB_CHECK(cudaMemcpyAsync(p, xk, sizeof(double) * m, cudaMemcpyDeviceToHost, d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
   db_free(ws);
 }

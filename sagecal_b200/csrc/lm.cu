@@ -319,14 +319,14 @@ static int enqueue_solve(dirac_b200_problem *pr, double mu, int linsolv, double 
     CB_CHECK(cublasDgemv(w.cb, CUBLAS_OP_T, n, n, &one, w.svdU, n, w.JTe, 1, &zero, w.Dp, 1));
     DB_CHECK(cudaMemcpyAsync(hS, w.svdS, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
     DB_CHECK(cudaMemcpyAsync(hb, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    db_stream_sync(d.stream);
     for (int i = 0; i < n; i++) hb[i] = (hS[i] > eps1) ? hb[i] / hS[i] : 0.0;
     DB_CHECK(cudaMemcpyAsync(w.pnew, hb, sizeof(double) * n, cudaMemcpyHostToDevice, d.stream));
     CB_CHECK(cublasDgemv(w.cb, CUBLAS_OP_T, n, n, &one, w.svdVT, n, w.pnew, 1, &zero, w.Dp, 1));
     db_prof_end(d.stream);
     DB_CHECK(cudaMemcpyAsync(w.h_vec + 2 * n, w.Dp, sizeof(double) * n, cudaMemcpyDeviceToHost,
                              d.stream));
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    db_stream_sync(d.stream);
     free(hS);
     free(hb);
     db_count_launch(2);
@@ -430,7 +430,7 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   DB_CHECK(cudaMemcpyAsync(w.h_mu, w.mu_dev, sizeof(double) * nb, cudaMemcpyDeviceToHost, d.stream));
   DB_CHECK(cudaMemcpyAsync(w.h_binfo, w.binfo_dev, sizeof(int) * nb, cudaMemcpyDeviceToHost,
                            d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));  // list goes out of scope; mu0 is needed on the host
+  db_stream_sync(d.stream);  // list goes out of scope; mu0 is needed on the host
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -493,7 +493,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       if (std::isnan(first_cost))
         DB_CHECK(cudaMemcpyAsync(d.h_scal + 2, d.scal + 2, sizeof(double), cudaMemcpyDeviceToHost,
                                  d.stream));
-      DB_CHECK(cudaStreamSynchronize(d.stream));
+      db_stream_sync(d.stream);
       if (std::isnan(first_cost)) p_eL2 = d.h_scal[2];
     } else {
       p_eL2 = 1.0;  // placeholder: J^T e and ||e||^2 (slot 2) come back with the first trial
@@ -590,7 +590,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           DB_CHECK(cudaMemcpyAsync(hH, w.Hst, sizeof(double) * 4 * d.N, cudaMemcpyDeviceToHost,
                                    d.stream));
       }
-      if (need_mx || os) DB_CHECK(cudaStreamSynchronize(d.stream));
+      if (need_mx || os) db_stream_sync(d.stream);
       if (need_mx) {
         if (wt) {
           for (int i = 0; i < n; i++)
@@ -674,9 +674,9 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           spec_buf = (cur == w.JTJ0) ? w.JTJ : w.JTJ0;
           DB_CHECK(cudaEventRecord(w.ev_mail, d.stream));
           assemble(pr, Tfull, w.pnew, spec_buf);
-          DB_CHECK(cudaEventSynchronize(w.ev_mail));
+          db_event_sync(w.ev_mail);
         } else {
-          DB_CHECK(cudaStreamSynchronize(d.stream));
+          db_stream_sync(d.stream);
         }
         {
           const double *hm = d.h_scal + 64;
@@ -937,7 +937,7 @@ void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, doubl
       db_count_launch(2);
       DB_CHECK(cudaMemcpyAsync(d.h_scal + 3, d.scal + 3, 2 * sizeof(double),
                                cudaMemcpyDeviceToHost, d.stream));
-      DB_CHECK(cudaStreamSynchronize(d.stream));
+      db_stream_sync(d.stream);
       const double lambda = d.h_scal[3];
       const double sumq = d.h_scal[4] / ndata;
       nu_t = pick_nu(sumq, nulow, nuhigh);
@@ -1013,7 +1013,7 @@ extern "C" double dirac_b200_bench_predict(dirac_b200_problem *pr, int out_mode,
   DB_CHECK(cudaEventRecord(e0, d.stream));
   for (int i = 0; i < reps; i++) db_predict_dev(pr, d.pp, pr->res, out_mode, 1, 0.0, 0);
   DB_CHECK(cudaEventRecord(e1, d.stream));
-  DB_CHECK(cudaEventSynchronize(e1));
+  db_event_sync(e1);
   float ms = 0.f;
   DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
@@ -1031,7 +1031,7 @@ extern "C" double dirac_b200_bench_grad(dirac_b200_problem *pr, int reps) {
   DB_CHECK(cudaEventRecord(e0, d.stream));
   for (int i = 0; i < reps; i++) db_grad_dev(pr, d.pp, pr->g, 0, 0.0);
   DB_CHECK(cudaEventRecord(e1, d.stream));
-  DB_CHECK(cudaEventSynchronize(e1));
+  db_event_sync(e1);
   float ms = 0.f;
   DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);
@@ -1061,7 +1061,7 @@ extern "C" double dirac_b200_bench_cluster_pass(dirac_b200_problem *pr, int clus
     db_cluster_pass(pr, (clus + i) % d.M, pblk, pr->res, w.dbuf, mode, write_out,
                     with_grad ? w.JTe : nullptr, 1, 0, d.tilesz, nullptr);
   DB_CHECK(cudaEventRecord(e1, d.stream));
-  DB_CHECK(cudaEventSynchronize(e1));
+  db_event_sync(e1);
   float ms = 0.f;
   DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0);

@@ -74,6 +74,7 @@ static int g_opt[DB_OPT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
 int db_opt(int id) { return (id >= 0 && id < DB_OPT_COUNT) ? g_opt[id] : 0; }
 extern "C" int dirac_b200_set_option(const char *name, int value) {
   if (!strcmp(name, "cp_rows")) { g_opt[DB_OPT_CP_ROWS] = value; return 0; }
+  if (!strcmp(name, "line_direct")) { g_opt[DB_OPT_LINE_DIRECT] = value; return 0; }
   return -1;
 }
 // SMs of the current device (grids of the one-wave kernels are sized from it)
@@ -306,7 +307,7 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
       db_launch_coh_to_planar(stage, d.coh, r0, nr, M, R, d.stream);
       db_count_launch(1);
     }
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    db_stream_sync(d.stream);
     db_free(stage);
   }
 
@@ -359,12 +360,12 @@ void db_download_vis(dirac_b200_problem *pr, const double2 *src, double *h) {
   db_launch_vis_from_planar(src, pr->vis_stage, d.R, d.stream);
   db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(h, pr->vis_stage, (size_t)d.R * 64, cudaMemcpyDeviceToHost, d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
 }
 
 extern "C" void dirac_b200_set_data(dirac_b200_problem *pr, const double *x) {
   db_upload_vis(pr, x, pr->d.x);
-  DB_CHECK(cudaStreamSynchronize(pr->d.stream));
+  db_stream_sync(pr->d.stream);
 }
 
 extern "C" void dirac_b200_get_coherencies(dirac_b200_problem *pr, double *coh) {
@@ -380,7 +381,7 @@ extern "C" void dirac_b200_get_coherencies(dirac_b200_problem *pr, double *coh) 
     DB_CHECK(cudaMemcpyAsync(coh + (size_t)r0 * d.M * 8, stage, (size_t)nr * d.M * 64,
                              cudaMemcpyDeviceToHost, d.stream));
   }
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
   db_free(stage);
 }
 
@@ -445,7 +446,7 @@ double db_read_scalar(dirac_b200_problem *pr, int slot) {
   DevProblem &d = pr->d;
   DB_CHECK(cudaMemcpyAsync(d.h_scal + slot, d.scal + slot, sizeof(double), cudaMemcpyDeviceToHost,
                            d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
   return d.h_scal[slot];
 }
 
@@ -483,7 +484,7 @@ extern "C" double dirac_b200_predict(dirac_b200_problem *pr, const double *pp, d
   double c = 0.0;
   if (cost_mode) c = db_read_scalar(pr, 0);
   if (out_mode) db_download_vis(pr, pr->res, out);
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
   DB_CHECK(cudaGetLastError());
   return c;
 }
@@ -497,6 +498,6 @@ extern "C" void dirac_b200_grad(dirac_b200_problem *pr, const double *pp, double
   db_grad_dev(pr, d.pp, pr->g, robust, nu);
   DB_CHECK(cudaMemcpyAsync(g, pr->g, sizeof(double) * d.npar, cudaMemcpyDeviceToHost,
                            d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
   DB_CHECK(cudaGetLastError());
 }

@@ -88,7 +88,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
     DB_CHECK(cudaMemcpyAsync(pr->g, v, sizeof(double) * cnt, cudaMemcpyHostToDevice, d.stream));
     db_allreduce(pr, pr->g, cnt);
     DB_CHECK(cudaMemcpyAsync(v, pr->g, sizeof(double) * cnt, cudaMemcpyDeviceToHost, d.stream));
-    DB_CHECK(cudaStreamSynchronize(d.stream));
+    db_stream_sync(d.stream);
   };
 
   DB_CHECK(cudaMemcpyAsync(d.pp, pp, sizeof(double) * m, cudaMemcpyHostToDevice, d.stream));
@@ -193,7 +193,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
                                d.stream));
       db_launch_axpby(xp, reinterpret_cast<double2 *>(d.pp), m / 2, 1.0, 1.0, d.stream);
       db_count_launch(4);
-      DB_CHECK(cudaStreamSynchronize(d.stream));  // nerr steers the next sweep's iteration budgets
+      db_stream_sync(d.stream);  // nerr steers the next sweep's iteration budgets
     }
     double total_err = 0.0;
     for (int cj = 0; cj < MG; cj++) total_err += fabs(nerr[cj]);
@@ -210,7 +210,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
     else if (robust_nu0 > nuhigh) robust_nu0 = nuhigh;
   }
   DB_CHECK(cudaMemcpyAsync(pp, d.pp, sizeof(double) * m, cudaMemcpyDeviceToHost, d.stream));
-  DB_CHECK(cudaStreamSynchronize(d.stream));
+  db_stream_sync(d.stream);
 
   if (max_lbfgs > 0) {
     if (robust) {

@@ -25,7 +25,7 @@ EXPORTED = [
     "dirac_b200_set_comm", "dirac_b200_spd_solve", "dirac_b200_tri_solve",
     "dirac_b200_set_option", "dirac_b200_nccl_unique_id", "dirac_b200_nccl_init",
     "dirac_b200_nccl_finalize", "dirac_b200_nccl_ready", "dirac_b200_comm_stats",
-    "dirac_b200_noise_decisions",
+    "dirac_b200_noise_decisions", "dirac_b200_host_stats",
 ]
 
 
@@ -74,6 +74,15 @@ class DiracB200(DiracAPI):
     def set_option(self, name: str, value: int):
         if self.lib.dirac_b200_set_option(name.encode(), int(value)) != 0:
             raise KeyError(name)
+
+    def host_stats(self, reset=False):
+        """(host syncs, seconds blocked in them, collectives, collective bytes, seconds enqueueing them)"""
+        n, c, b = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+        w, e = C.c_double(0.0), C.c_double(0.0)
+        self.lib.dirac_b200_host_stats(C.byref(n), C.byref(w), 1 if reset else 0)
+        self.lib.dirac_b200_comm_stats(C.byref(c), C.byref(b), C.byref(e), 1 if reset else 0)
+        return dict(host_syncs=n.value, host_wait_s=w.value, collectives=c.value,
+                    collective_bytes=b.value, collective_enqueue_s=e.value)
 
     def noise_decisions(self, reset=False) -> int:
         self.lib.dirac_b200_noise_decisions.restype = C.c_long

@@ -49,8 +49,14 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", help="C2 (62 st, 64 clusters, 120 slots) | C1 | "
-                    "custom N,M,T e.g. 62,16,30")
+    ap.add_argument("--workload", default="C4",
+                    help="C4 (512 stations, 32 clusters per GPU, 120 slots: the workload BASELINE.json's "
+                         "metric is quoted on, 256 clusters on 8 GPUs) | C2 (62 st, 64 clusters) | C3 "
+                         "(robust) | C1 | custom N,M,T e.g. 62,16,30")
+    ap.add_argument("--only", action="store_true", help="one GPU: do not append the C2 and C3 lines")
+    ap.add_argument("--devgen", action="store_true", help="generate the coherencies on the device "
+                    "(always for C4)")
+    ap.add_argument("--c4-clusters-per-gpu", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -161,12 +167,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
+def ncu_traffic(workload="C2"):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("k_cluster_pass_dram_bytes_per_launch")
+            t = json.load(f)
+        return t.get("k_cluster_pass_dram_bytes_per_launch_" + workload,
+                     t.get("k_cluster_pass_dram_bytes_per_launch") if workload == "C2" else None)
     return None
 
 
@@ -211,6 +219,68 @@ def cpu_reference_run(steps, warmup, seed):
     return units / sec, sec, desc
 
 
+def cpu_stage_timings(seed):
+    """the reference's own CPU stages timed beside the GPU ones, at the largest shape
+    its dense Jacobian allows (62 stations, 8 clusters, 10 timeslots): P1 full predict
+    (minimize_viz_full_pth), one cost + one gradient (the LBFGS callbacks), one LM iteration of one
+    cluster (clevmar_der_single_nocuda, itmax=1: dense J + dgemm, that IS the reference's cost).
+    OpenBLAS pinned to 1 thread as the reference driver does (fullbatch_mode.cpp:85) and with all
+    threads; Nt = cores pthreads in both."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import refdirac
+    from sagecal_b200 import synth
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+    if not refdirac.available():
+        return None
+    ref = refdirac.load()
+    cores = min(os.cpu_count() or 1, 32)
+    pr = synth.make_problem(N=62, M=8, tilesz=10, radius=40e3, seed=seed, kmean=2.0)
+    barr = make_barr(pr.sta1, pr.sta2, pr.flag)
+    sky = SkyModel(pr.clusters, pr.N)
+    n = 8 * pr.Nbase1
+    rows = pr.Nbase1
+    out = {"shape": "N=62, M=8, tilesz=10 (%d rows)" % rows, "Nt": cores, "unit": UNIT}
+    rng = np.random.default_rng(1)
+    pp = pr.pp0 + 0.05 * rng.normal(0, 1, pr.pp0.shape)
+
+    def timed(f, reps=1):
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            f()
+        return (time.perf_counter() - t0) / reps
+
+    for label, nth in (("openblas_1_thread", 1), ("openblas_all_threads", cores)):
+        try:
+            ref.lib.openblas_set_num_threads(nth)
+        except AttributeError:
+            pass
+        md = ref.me_data(pr.N, pr.Nbase, pr.tilesz, barr, sky, pr.coh, Nt=cores)
+        md0 = ref.me_data(pr.N, pr.Nbase, pr.tilesz, barr, sky, pr.coh, clus=0, Nt=cores)
+        t_p1 = timed(lambda: ref.predict_full(pp, md, n), 5)
+        t_cost = timed(lambda: ref.cost(pp, pr.x, md), 3)
+        t_grad = timed(lambda: ref.grad(pp, pr.x, md), 1)
+        t_lm = timed(lambda: ref.clevmar(pp[:8 * pr.N], pr.x, md0, 1), 1)
+        out[label] = {
+            "P1_full_predict": {"seconds": t_p1, "value": rows * pr.M / t_p1},
+            "cost_plus_grad": {"seconds": t_cost + t_grad, "value": rows * pr.M / (t_cost + t_grad)},
+            "one_LM_iteration_one_cluster": {"seconds": t_lm, "value": rows / t_lm},
+        }
+    return out
+
+
+def cpu_baseline_object(seed):
+    v, sec, desc = cpu_reference_run(1, 0, seed)
+    cores = min(os.cpu_count() or 1, 32)
+    cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": desc}
+    if v is not None:
+        cpu["seconds_per_step"] = sec
+        try:
+            cpu["stages"] = cpu_stage_timings(seed)
+        except Exception as e:  # the stage timings are a report, never a reason to lose the line
+            cpu["stages"] = {"error": repr(e)}
+    return cpu
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -241,50 +311,58 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
-def build_workload(api, shape, rank, world):
-    """synthetic MS of the workload shape; coherencies by the numpy generator (independent of the
-    product), data = true-Jones model + noise"""
-    from sagecal_b200 import synth
-    pr = synth.make_problem(**shape)
-    return pr
+def n512_parity(api):
+    """reduced-interval problem at the station count of C4 (512 stations, 2 timeslots, 2 clusters)
+    against the committed golden of the CPU restatement (tests/golden/n512): the parity evidence for
+    the 8N = 4096 code paths next to a C4 bench line (no CPU code can produce a full-shape C4 golden)"""
+    path = os.path.join(ROOT, "tests", "golden", "n512", "lm.npz")
+    if not os.path.exists(path):
+        return {"checked": False, "why": "tests/golden/n512/lm.npz missing"}
+    import ast
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_n512 as gen
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+    g = np.load(path)
+    pr = gen.build()
+    same_inputs = bool(np.allclose(gen.fingerprint(pr), g["fingerprint"], rtol=1e-10, atol=0))
+    kw = ast.literal_eval(str(g["args"]))
+    x, pp = pr.x.copy(), pr.pp0.copy()
+    out = api.sagefit_visibilities(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz,
+                                   make_barr(pr.sta1, pr.sta2, pr.flag), SkyModel(pr.clusters, pr.N),
+                                   pr.coh, pp, **kw)
+    want = g["out_scalars"]
+    err = float(np.max(np.abs(pp - g["out_pp"])) / np.max(np.abs(g["out_pp"])))
+    return {"checked": True, "against": "oracle/liboracle.so golden tests/golden/n512/lm.npz "
+                                        "(N=512, 2 clusters, 2 timeslots)",
+            "same_inputs": same_inputs, "jones_max_relerr": err, "tolerance": 1e-5,
+            "ok": bool(same_inputs and err < 1e-5), "res_1": [out[3], float(want[3])]}
 
 
-def main():
-    args = parse()
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
+def run_workload(name, args, ctx, with_cpu=True):
+    """one workload through the own arm; returns the JSON line (dict) on rank 0, None elsewhere"""
     import torch
     import torch.distributed as dist
     from sagecal_b200 import lib as blib
     from sagecal_b200 import dist as sdist
-    from sagecal_b200.dirac_api import SkyModel, make_barr
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there otherwise
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    api = blib.load()
-    stream = torch.cuda.Stream()
-    api.set_stream(stream.cuda_stream)
-
     from sagecal_b200 import synth
-    shape = dict(workload_shape(args.workload))
-    SOLVE_W = solve_args(args.workload)
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+    api, stream, rank, world, local = ctx["api"], ctx["stream"], ctx["rank"], ctx["world"], ctx["local"]
+    shape = dict(workload_shape(name))
+    SOLVE_W = solve_args(name)
 
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
 
-    if world == 1:
-        pr = build_workload(api, shape, rank, world)
+    # C4 (512 stations): the coherencies of one GPU's 32 clusters are 32 GB (257 GB for all 256
+    # clusters) and never exist on the host: they are generated on the device from the sky model
+    # (dirac_b200_precalculate, the device-side precalculate_coherencies), as SURVEY.md 8e prescribes
+    devgen = name == "C4" or args.devgen
+    if name == "C4":
+        shape["M"] = args.c4_clusters_per_gpu
+    coh_h = None
+    if world == 1 and not devgen:
+        pr = synth.make_problem(**shape)
         barr = make_barr(pr.sta1, pr.sta2, pr.flag)
         sky = SkyModel(pr.clusters, pr.N)
         coh_t, coh_h = pinned(pr.coh.view(np.float64))
@@ -296,39 +374,44 @@ def main():
         shape["M"] = shape["M"] * world
         pr = synth.make_problem(with_data=False, **shape)
         barr = make_barr(pr.sta1, pr.sta2, pr.flag)
-        sky = None
+        sky = SkyModel(pr.clusters, pr.N) if world == 1 else None
         k0, k1 = sdist.partition_clusters(pr.M, world)[rank]
-        coh_local = synth.coherencies(pr.u, pr.v, pr.w, pr.clusters[k0:k1], pr.freq0, pr.fdelta)
-        coh_t, coh_h = pinned(coh_local.view(np.float64))
-        coh_h = coh_h.view(np.complex128)
+        if not devgen:
+            coh_local = synth.coherencies(pr.u, pr.v, pr.w, pr.clusters[k0:k1], pr.freq0, pr.fdelta)
+            coh_t, coh_h = pinned(coh_local.view(np.float64))
+            coh_h = coh_h.view(np.complex128)
         pr.x = np.zeros(8 * pr.Nbase1)
+
+    def make_resident():
+        if world == 1:
+            dpx = blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, barr, sky, coh_h, pr.x)
+            if devgen:
+                dpx.precalculate(pr.u, pr.v, pr.w, pr.freq0, pr.fdelta)
+            return dpx
+        spx = sdist.ShardedProblem(api, pr, barr, rank, world, coh_local=coh_h)
+        if devgen:
+            spx.precalculate(pr.u, pr.v, pr.w, pr.freq0, pr.fdelta)
+        return spx
+
+    if world > 1 or devgen:
         with torch.cuda.stream(stream):
-            sp0 = sdist.ShardedProblem(api, pr, barr, rank, world, coh_local=coh_h)
+            sp0 = make_resident()
             model = np.zeros(8 * pr.Nbase1)
             api.lib.dirac_b200_predict(sp0.h, blib.dptr(pr.jones_true), blib.dptr(model), 2, 0, 0.0)
             sp0.close()
         rng = np.random.default_rng(shape["seed"] + 17)
-        sigma = 1e-2 * np.median(np.abs(model))
+        sigma = 1e-2 * np.median(np.abs(model[:: max(1, len(model) // 4000000)]))
         pr.x = model + rng.normal(0, sigma, model.shape)
+        del model
         pr.x.reshape(pr.Nbase1, 8)[pr.flag == 1] = 0.0
     R, M = pr.Nbase1, pr.M
     x_t, x_h = pinned(pr.x)
+    pr.x = x_h
     pp_t, pp_h = pinned(pr.pp0)
-
-    def make_resident():
-        if world == 1:
-            return blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, barr, sky, coh_h, x_h)
-        pr.x = x_h
-        return sdist.ShardedProblem(api, pr, barr, rank, world, coh_local=coh_h)
+    coh_bytes = coh_h.nbytes if coh_h is not None else 64 * R * (M // world)
 
     K, W = args.steps, max(args.warmup, 3)
     clocks = ClockSampler(local)
-    # sharded runs: prove the sharded path right on this very box before timing it (small problem,
-    # sharded vs single GPU on every rank; sagecal_b200.dist.verify_sharding)
-    shard_check = None
-    if world > 1:
-        with torch.cuda.stream(stream):
-            shard_check = sdist.verify_sharding(api, rank, world)
 
     # ---------------- resident-data throughput (`value`) ----------------
     with torch.cuda.stream(stream):
@@ -338,8 +421,8 @@ def main():
         for it in range(W):
             pp = pr.pp0.copy()
             res = dp.sagefit(pp, None, **SOLVE_W)
-            if it == 0 and world == 1 and rank == 0:
-                parity = golden_parity(args.workload, pr, pp, res)
+            if it == 0 and world == 1 and rank == 0 and name != "C4":
+                parity = golden_parity(name, pr, pp, res)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -386,9 +469,13 @@ def main():
 
     # ---------------- end to end through the drop-in C entry point (`e2e`) ----------------
     e2e = None
+    dp.close()
     if not args.no_e2e:
-        dp.close()
-        h2d = coh_h.nbytes + x_h.nbytes + pp_h.nbytes + R  # coherencies, data, Jones, flags
+        if devgen:
+            # u, v, w, data, Jones, flags up; the coherencies are generated on the device
+            h2d = 3 * 8 * R + x_h.nbytes + pp_h.nbytes + R
+        else:
+            h2d = coh_h.nbytes + x_h.nbytes + pp_h.nbytes + R  # coherencies, data, Jones, flags
         d2h = x_h.nbytes + pp_h.nbytes
         with torch.cuda.stream(stream):
             x_keep = np.array(x_h)
@@ -396,10 +483,11 @@ def main():
             def one():
                 x_h[:] = x_keep
                 pp_h[:] = pr.pp0
-                if world == 1:
+                if world == 1 and not devgen:
                     return api.sagefit_visibilities(pr.u, pr.v, pr.w, x_h, pr.N, pr.Nbase,
                                                     pr.tilesz, barr, sky, coh_h, pp_h, **SOLVE_W)
-                # sharded public path: upload this rank's shard, solve, download, free
+                # sharded / device-generated public path: upload (or generate) this rank's shard,
+                # solve, download, free
                 sp = make_resident()
                 xo = np.empty_like(x_keep)
                 rr = sp.sagefit(pp_h, xo, **SOLVE_W)
@@ -415,19 +503,20 @@ def main():
                 one()
             f1.record(stream)
             torch.cuda.synchronize()
+            x_h[:] = x_keep
         te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ms_e2e = float(te.item()) / K
         e2e = {"value": units_step / (ms_e2e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": ms_e2e}
+               "ms_per_step": ms_e2e,
+               "path": ("dirac_b200_create + dirac_b200_precalculate (device) + dirac_b200_sagefit + "
+                        "destroy, host buffers" if (devgen or world > 1) else
+                        "sagefit_visibilities (drop-in entry point), host buffers")}
 
     if rank != 0:
-        if world > 1:
-            api.lib.dirac_b200_nccl_finalize()
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---------------- roofline of the dominant own kernel ----------------
     peak, peak_src = measured_peaks()
@@ -439,55 +528,66 @@ def main():
         shares[names[k]] = {"launches_per_step": n / K, "ms_per_step": ms / K,
                             "share_of_step": (ms / K) / ms_profiled if ms_profiled else None,
                             "GBps": (by / (ms * 1e-3)) / 1e9 if ms > 0 and by > 0 else None}
-    # `roofline` is quoted for the dominant HBM-streaming kernel.  The damped solves (k_chol_solve /
-    # k_tri_solve: one 496x496 Cholesky per LM iteration on a 16-CTA cluster) take the largest share
-    # of the step but are a dependency chain of 496 pivots, bounded by latency, not by HBM or the
-    # tensor cores: they are reported next to it with their share and achieved FLOP rate.
+    # `roofline` is quoted for the dominant HBM-streaming kernel.  The damped solves take a large
+    # share of the step, are latency (N=62: a chain of 496 pivots on a 16-CTA cluster) or FP64 bound
+    # (N=512: 23 GFLOP per factorisation), not HBM or tensor bound: reported next to it.
     own = {k: v for k, v in shares.items() if not k.startswith("damped")}
     dom = max(own, key=lambda k: own[k]["ms_per_step"])
     n8 = 8 * pr.N
     sv = shares["damped_solve"]
-    solver = {"kernels": "k_chol_solve (factor+solve), k_tri_solve (solve on batch-prefactored systems), "
-                         "cusolverDnDpotrfBatched (one batch per sweep)",
-              "bound": "latency (pivot chain)", "launches_per_step": sv["launches_per_step"],
+    flop = n8 ** 3 / 3.0 + 2.0 * n8 * n8
+    solver = {"kernels": ("k_chol_solve (factor+solve), k_tri_solve (solve on batch-prefactored "
+                          "systems), cusolverDnDpotrfBatched (one batch per sweep)") if n8 <= 512 else
+                         "cusolverDnDpotrf + Dpotrs (8N > 512)",
+              "bound": "latency (pivot chain)" if n8 <= 512 else "fp64",
+              "launches_per_step": sv["launches_per_step"],
               "ms_per_step": sv["ms_per_step"], "share_of_step": sv["share_of_step"],
-              "flop_per_factor_solve": n8 ** 3 / 3.0 + 2.0 * n8 * n8}
+              "flop_per_factor_solve": flop,
+              "TFLOPs": (flop * sv["launches_per_step"] / (sv["ms_per_step"] * 1e-3) / 1e12)
+              if sv["ms_per_step"] else None}
     n, ms, by = prof[names.index(dom)]
     achieved = (by / (ms * 1e-3)) / 1e9 if ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(name), "peak_source": peak_src,
                 "launches_in_timed_region": n, "avg_launch_us": 1e3 * ms / n if n else None,
-                "profiled_ms_per_step": ms_profiled, "dominant_by_time": max(shares, key=lambda k: shares[k]["ms_per_step"]),
+                "algorithmic_bytes_per_launch": by / n if n else None,
+                "profiled_ms_per_step": ms_profiled,
+                "dominant_by_time": max(shares, key=lambda k: shares[k]["ms_per_step"]),
                 "solver": solver, "kernels": shares}
 
     cpu = None
-    if not args.no_cpu_baseline:
-        v, sec, desc = cpu_reference_run(1, 0, shape["seed"])
-        if v is not None:
-            cpu = {"value": v, "unit": UNIT, "cores": min(os.cpu_count() or 1, 32), "kind": "reference",
-                   "sample": desc, "seconds_per_step": sec}
-        else:
-            cpu = {"value": None, "unit": UNIT, "cores": min(os.cpu_count() or 1, 32), "kind": "reference",
-                   "sample": desc}
+    if with_cpu and not args.no_cpu_baseline:
+        cpu = cpu_baseline_object(shape["seed"])
 
+    if world > 1:
+        par = {"checked": True, "sharded_vs_single_gpu": ctx.get("shard_check"),
+               "ok": bool(ctx.get("shard_check") and ctx["shard_check"]["ok"])}
+        if name == "C4":
+            par["n512_reduced"] = ctx.get("n512")
+            par["ok"] = bool(par["ok"] and ctx.get("n512", {}).get("ok"))
+    elif name == "C4":
+        par = ctx.get("n512")
+    else:
+        par = parity
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: N=%d stations, %d baselines, M=%d clusters, tilesz=%d, "
-                               "rows=%d per GPU" % (args.workload, pr.N, pr.Nbase, M, pr.tilesz, R),
+        "config": {"workload": "%s: N=%d stations, %d baselines, M=%d clusters (%d per GPU), "
+                               "tilesz=%d, rows=%d per GPU" % (name, pr.N, pr.Nbase, M, M // world,
+                                                              pr.tilesz, R),
                    "solve": SOLVE_W, "sweeps_per_step": sweeps,
                    "units_per_step": "rows*clusters*(em_sweeps+lbfgs_grad_evals)",
-                   "l2": "inputs (%.0f MB coherencies) larger than the 126 MB L2, no flush needed"
-                         % (coh_h.nbytes / 1e6),
-                   "parallelism": ("clusters sharded over %d GPUs (%d per GPU), NCCL all-reduce of the "
-                                   "residual delta per SAGE sweep" % (world, M // world)) if world > 1
-                   else "1 GPU",
+                   "l2": "inputs (%.0f MB coherencies per GPU) larger than the 126 MB L2, no flush needed"
+                         % (coh_bytes / 1e6),
+                   "coherencies": "generated on the device (dirac_b200_precalculate)" if devgen
+                                  else "host array uploaded",
+                   "parallelism": ("clusters sharded over %d GPUs (%d per GPU), ONE NCCL all-reduce "
+                                   "(residual delta | Jones delta | nerr) per SAGE sweep, called from "
+                                   "C" % (world, M // world)) if world > 1 else "1 GPU",
                    "final_res": [res[2], res[3]] if res else None},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": roofline, "cpu_baseline": cpu,
-        "parity": parity if world == 1 else {"checked": True, "sharded_vs_single_gpu": shard_check,
-                                             "ok": bool(shard_check and shard_check["ok"])},
+        "roofline": roofline, "cpu_baseline": cpu, "parity": par,
         # where a step goes on rank 0 (timed region, per step): kernels by CUDA events (instrumented
         # repeat), host blocked in stream/event waits, host enqueueing collectives; the remainder is
         # host-side solver logic and launch overhead
@@ -499,7 +599,60 @@ def main():
                       "collective_MB_per_step": hstat["collective_bytes"] / K / 1e6,
                       "collective_enqueue_ms": 1e3 * hstat["collective_enqueue_s"] / K},
     }
-    print(json.dumps(line))
+    return line
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from sagecal_b200 import lib as blib
+    from sagecal_b200 import dist as sdist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there otherwise
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api = blib.load()
+    stream = torch.cuda.Stream()
+    api.set_stream(stream.cuda_stream)
+    ctx = dict(api=api, stream=stream, rank=rank, world=world, local=local)
+    # checks that run before anything is timed
+    with torch.cuda.stream(stream):
+        if world > 1:
+            # prove the sharded path right on this very box (small problem, sharded vs single GPU
+            # on every rank; sagecal_b200.dist.verify_sharding)
+            ctx["shard_check"] = sdist.verify_sharding(api, rank, world)
+        if args.workload == "C4" and rank == 0:
+            ctx["n512"] = n512_parity(api)
+    if world > 1:
+        dist.barrier()
+
+    line = run_workload(args.workload, args, ctx)
+    # one GPU: the two 62-station configurations of BASELINE.json ride along (their own parity
+    # against the full-shape goldens, value, roofline), so that one driver run covers C2, C3 and C4
+    if world == 1 and rank == 0 and args.workload == "C4" and not args.only:
+        others = {}
+        for w in ("C2", "C3"):
+            o = run_workload(w, args, ctx, with_cpu=False)
+            others[w] = {k: o[k] for k in ("value", "ms_per_step", "config", "e2e", "gpu_launches",
+                                           "parity", "breakdown")}
+            others[w]["roofline"] = {k: o["roofline"][k] for k in
+                                     ("kernel", "achieved", "peak", "frac", "avg_launch_us", "solver")}
+            others[w]["kernels"] = o["roofline"]["kernels"]
+        line["other_workloads"] = others
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         api.lib.dirac_b200_nccl_finalize()
         dist.destroy_process_group()

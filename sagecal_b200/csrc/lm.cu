@@ -357,6 +357,8 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   const int n = w.n8;
   const size_t nn = (size_t)n * n;
   if ((double)d.M * nn * 16.0 > 24e9) return;  // keep the two batch buffers within 24 GB
+  if (n > 1024) return;  // the batched factorisation is a small-matrix routine; large systems are
+                         // assembled and factorised inside their visit
   if (!w.JB) {
     w.JB = dalloc<double>(nn * d.M);
     w.LB = dalloc<double>(nn * d.M);
@@ -449,6 +451,13 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
 // its CPU restatement part ways on such runs (tests/golden/make_golden_c2r.py), so parity of the
 // solved Jones is only defined when this stays 0.
 static long g_noise_decisions = 0;
+static long g_lm_stat[4] = {0, 0, 0, 0};  // accepted, accepted with mu/3, rejected, -
+extern "C" void dirac_b200_lm_stats(long *out4, int reset) {
+  for (int i = 0; i < 4; i++) {
+    if (out4) out4[i] = g_lm_stat[i];
+    if (reset) g_lm_stat[i] = 0;
+  }
+}
 extern "C" long dirac_b200_noise_decisions(int reset) {
   const long v = g_noise_decisions;
   if (reset) g_noise_decisions = 0;
@@ -744,6 +753,8 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
             double tmp = (2.0 * dF / dL - 1.0);
             tmp = 1.0 - tmp * tmp * tmp;
             mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);  // CLM_ONE_THIRD
+            g_lm_stat[0]++;                                // accepted steps
+            if (!(tmp >= 0.3333333334)) g_lm_stat[1]++;    // ... that shrink mu by exactly 1/3
             nu = 2;
             for (int i = 0; i < n; i++) hp[i] += hDp[i];
             DB_CHECK(cudaMemcpyAsync(pblk_dev, w.pnew, sizeof(double) * n,
@@ -757,6 +768,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
             break;
           }
         }
+        g_lm_stat[2]++;
         mu *= (double)nu;
         nu2 = nu << 1;
         if (nu2 <= nu) {

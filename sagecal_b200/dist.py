@@ -122,6 +122,15 @@ class ShardedProblem:
             self._cb = C.cast(None, ALLREDUCE_FN)  # NULL: the library's own ncclAllReduce
         L.dirac_b200_set_comm(self.h, rank, world, self._cb, None, pr.M, self.k0, float(beta))
 
+    def precalculate(self, u, v, w, freq0, fdelta, uvmin=0.0, uvmax=1e9):
+        """coherencies of this rank's clusters generated on the device (dirac_b200_precalculate)"""
+        L = self.api.lib
+        L.dirac_b200_precalculate.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p,
+                                              C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_void_p]
+        L.dirac_b200_precalculate(self.h, dptr(u), dptr(v), dptr(w), C.cast(self.sky.arr, C.c_void_p),
+                                  freq0, fdelta, uvmin, uvmax, None)
+
     def sagefit(self, pp, x_out=None, max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, linsolv=0,
                 solver_mode=1, nulow=2.0, nuhigh=30.0, randomize=0):
         nu, r0, r1 = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)

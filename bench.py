@@ -457,7 +457,7 @@ def run_workload(name, args, ctx, with_cpu=True):
         p1.record(stream)
         torch.cuda.synchronize()
         ms_profiled = p0.elapsed_time(p1) / K
-        prof = {k: api.profile_read(k) for k in range(8)}
+        prof = {k: api.profile_read(k) for k in range(9)}
         api.profile_enable(False)
     sweeps = SOLVE_W["max_emiter"] + ngrad
     units_step = R * M * sweeps
@@ -521,9 +521,9 @@ def run_workload(name, args, ctx, with_cpu=True):
     # ---------------- roofline of the dominant own kernel ----------------
     peak, peak_src = measured_peaks()
     names = ["k_predict_full", "k_grad_full", "k_cluster_pass", "k_coh_gram", "assemble",
-             "damped_solve", "k_weighted_jtj", "k_line_setup"]
+             "damped_solve", "k_weighted_jtj", "k_line_setup", "k_cluster_pass_addsub"]
     shares = {}
-    for k in range(8):
+    for k in range(9):
         n, ms, by = prof[k]
         shares[names[k]] = {"launches_per_step": n / K, "ms_per_step": ms / K,
                             "share_of_step": (ms / K) / ms_profiled if ms_profiled else None,

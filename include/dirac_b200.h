@@ -233,7 +233,8 @@ long dirac_b200_noise_decisions(int reset);
 unsigned long long dirac_b200_launch_count(void);
 /* per-launch CUDA-event timing of the library's kernels on their launching stream.
  * kind: 0 full predict, 1 LBFGS gradient, 2 k_cluster_pass*, 3 k_coh_gram, 4 assembly, 5 damped solve
- * (k_chol_solve / k_tri_solve / batched potrf), 6 k_weighted_jtj, 7 line setup.  enable(1) clears the
+ * (k_chol_solve / k_tri_solve / batched potrf), 6 k_weighted_jtj, 7 line setup, 8 k_cluster_pass
+ * without gradient (ADD / SUB / cost-only; kind 2 then counts the gradient-carrying INIT / TRIAL passes).  enable(1) clears the
  * records; read returns the launch count and sums the elapsed
  * milliseconds and the algorithmic bytes of the recorded launches of that kind. */
 unsigned long long dirac_b200_kernel_count(int kind); /* launches of `kind` since load */

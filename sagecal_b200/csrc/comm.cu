@@ -123,6 +123,43 @@ void db_allreduce(dirac_b200_problem *pr, void *dev, long long count) {
   g_comm_bytes += (unsigned long long)count * 8ull;
 }
 
+// ---- overlapped exchange: all-reduces on a communication stream of the library, grouped ----------
+// Used where a streaming kernel is followed by a large all-reduce of what it wrote (the LBFGS line
+// model: three visibility-sized vectors per iteration): the kernel is launched in time chunks and
+// every chunk's slices are summed over the ranks on a second stream while the next chunk is computed,
+// so the NVLink transfer runs behind the math instead of after it.
+static cudaStream_t g_comm_stream = nullptr;
+int db_overlap_available(const dirac_b200_problem *pr) {
+  return pr->world > 1 && !pr->allreduce && g_nccl.comm && g_nccl.world == pr->world &&
+         !getenv("DIRAC_B200_NO_OVERLAP");
+}
+cudaStream_t db_comm_stream() {
+  if (!g_comm_stream) DB_CHECK(cudaStreamCreateWithFlags(&g_comm_stream, cudaStreamNonBlocking));
+  return g_comm_stream;
+}
+static int (*p_GroupStart)() = nullptr;
+static int (*p_GroupEnd)() = nullptr;
+// sums `nseg` device segments (ptr[i], count[i] doubles) over the ranks as ONE grouped NCCL operation
+void db_allreduce_segments(dirac_b200_problem *pr, double **ptr, const long long *count, int nseg,
+                           cudaStream_t st) {
+  if (!p_GroupStart) {
+    *(void **)&p_GroupStart = dlsym(g_nccl.lib, "ncclGroupStart");
+    *(void **)&p_GroupEnd = dlsym(g_nccl.lib, "ncclGroupEnd");
+  }
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (p_GroupStart && p_GroupEnd) NCCL_CHECK(p_GroupStart());
+  for (int i = 0; i < nseg; i++) {
+    NCCL_CHECK(g_nccl.AllReduce(ptr[i], ptr[i], (size_t)count[i], DB_NCCL_DOUBLE, DB_NCCL_SUM,
+                                g_nccl.comm, st));
+    g_comm_bytes += (unsigned long long)count[i] * 8ull;
+  }
+  if (p_GroupStart && p_GroupEnd) NCCL_CHECK(p_GroupEnd());
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  g_comm_seconds += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  g_comm_calls++;
+}
+
 // host-side accounting of the collectives since the last reset: calls, bytes, seconds spent enqueueing
 extern "C" void dirac_b200_comm_stats(unsigned long long *calls, unsigned long long *bytes,
                                       double *enqueue_seconds, int reset) {

@@ -268,6 +268,9 @@ struct ClusterPassArgs {
   int write_out;
   double beta;               // SAGE hidden-data weight: INIT d = beta*in + m ; SUB out = d - m + (1-beta)*in2
   const double2 *in2;        // mode 3 with beta != 1: the residual the hidden data was formed from
+  const double *pblk_old;    // mode 3 with beta != 1, instead of in2: the Jones the hidden data was
+                             // formed with; the old residual is recovered as (d - f(p_old))/beta, so
+                             // out = d - f(p) + (1-beta)/beta (d - f(p_old)) costs no extra traffic
   const short2 *blpq;        // [Nbase] (p,q) of baseline b (linear-mapped variant)
   double *jte_part;          // [groups][slices][8N] per-CTA station sums (linear-mapped variant)
   unsigned int *gcounter;    // [groups] arrival counters of the time slices of a baseline group
@@ -310,6 +313,8 @@ struct StreamAllArgs {
   int out_mode, cost_mode;
   double inv_nu;
   int partial;
+  long long row0;            // absolute row of the first row the pointers address (time-chunked
+                             // launches shift the base pointers; hybrid chunk maps need the row)
 };
 
 // line model of the LBFGS line search: e(alpha) = E0 - alpha E1 - alpha^2 E2 (kernels_line.cu)

@@ -702,6 +702,13 @@ k_cluster_pass(ClusterPassArgs a) {
   if (valid) {
     load_jones(a.pblk, p, Jp);
     load_jones(a.pblk, q, Jq);
+    double2 Jpo[4], Jqo[4];
+    const bool recover = (!GRAD) && a.mode == 3 && a.pblk_old != nullptr;
+    const double gamma = recover ? (1.0 - a.beta) / a.beta : 0.0;
+    if (recover) {
+      load_jones(a.pblk_old, p, Jpo);
+      load_jones(a.pblk_old, q, Jqo);
+    }
     const long long b = baseline_index(p, q, a.N);
 #pragma unroll 2
     for (int t = ts; t < te; t++) {
@@ -733,11 +740,25 @@ k_cluster_pass(ClusterPassArgs a) {
           st_stream(a.out + (long long)c * a.R + row,
                     cadd(make_double2(a.beta * v[c].x, a.beta * v[c].y), m[c]));
       } else {
+        double2 mo[4];
+        if (recover) {
+          double2 T2[4];
+          mat_ab(Jpo, C, T2);
+          mat_abh(T2, Jqo, mo);
+          if (fl) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) mo[c] = make_double2(0.0, 0.0);
+          }
+        }
 #pragma unroll
         for (int c = 0; c < 4; c++) {
           e[c] = csub(v[c], m[c]);
           double2 o = e[c];
-          if (a.mode == 3 && a.in2) {
+          if (recover) {
+            // + (1-beta) r_old with r_old = (d - f(p_old)) / beta
+            o.x = fma(gamma, v[c].x - mo[c].x, o.x);
+            o.y = fma(gamma, v[c].y - mo[c].y, o.y);
+          } else if (a.mode == 3 && a.in2) {
             const double2 r2 = a.in2[(long long)c * a.R + row];  // may alias out: plain load
             o.x = fma(1.0 - a.beta, r2.x, o.x);
             o.y = fma(1.0 - a.beta, r2.y, o.y);
@@ -930,7 +951,7 @@ k_cluster_pass_split(ClusterPassArgs a) {
 // what the CTA's baselines contribute to station s), written per CTA, and the last time slice of a
 // baseline group adds the group's total to J^T e (8 global atomics per entry instead of ~140).
 // ------------------------------------------------------------------------------------------------
-template <int NST>
+template <int NST, bool GRAD>
 __global__ void __launch_bounds__(512)
 k_cluster_pass_lin(ClusterPassArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -946,7 +967,8 @@ k_cluster_pass_lin(ClusterPassArgs a) {
   const int ts = a.t_begin + blockIdx.y * a.tslice;
   const int te = min(ts + a.tslice, a.t_end);
   const int nrow = te - ts;
-  for (int i = tid; i < 8 * a.N; i += 512) acc[i] = 0.0;
+  if (GRAD)
+    for (int i = tid; i < 8 * a.N; i += 512) acc[i] = 0.0;
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NST; s++) mbar_init(&bars[s], 1);
@@ -978,6 +1000,14 @@ k_cluster_pass_lin(ClusterPassArgs a) {
   for (int c = 0; c < 4; c++) Jq[c] = make_double2(0.0, 0.0);
   unsigned flagbits = 0;  // bit j: row ts+j flagged (slices are at most 32 rows, see the launcher)
   const long long b = b0 + bl;
+  // closing pass of a sharded visit: the old residual is recovered from the Jones the visit started
+  // with, out = d - f(p) + (1-beta)/beta (d - f(p_old))
+  const bool recover = (!GRAD) && a.mode == 3 && a.pblk_old != nullptr;
+  const double gamma = recover ? (1.0 - a.beta) / a.beta : 0.0;
+  double2 Jro[2], Jqo[4];
+  Jro[0] = Jro[1] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) Jqo[c] = make_double2(0.0, 0.0);
   if (valid) {
     const short2 pq = a.blpq[b];
     p = pq.x;
@@ -986,6 +1016,12 @@ k_cluster_pass_lin(ClusterPassArgs a) {
     Jr[0] = __ldg(jp);
     Jr[1] = __ldg(jp + 1);
     load_jones(a.pblk, q, Jq);
+    if (recover) {
+      const double2 *jo = reinterpret_cast<const double2 *>(a.pblk_old + 8 * (long long)p + 4 * h);
+      Jro[0] = __ldg(jo);
+      Jro[1] = __ldg(jo + 1);
+      load_jones(a.pblk_old, q, Jqo);
+    }
     for (int j = 0; j < nrow; j++)
       flagbits |= (a.flag[(long long)(ts + j) * a.Nbase + b] != 0 ? 1u : 0u) << j;
   }
@@ -1012,7 +1048,7 @@ k_cluster_pass_lin(ClusterPassArgs a) {
       m[1] = cdot2c(T0, Jq[2], T1, Jq[3]);
       if (fl) m[0] = m[1] = make_double2(0.0, 0.0);
       double2 e[2];
-      if (a.mode == 0) {
+      if (a.mode == 0 || a.mode == 2) {
 #pragma unroll
         for (int jj = 0; jj < 2; jj++) {
           const double2 d = cadd(make_double2(a.beta * v[jj].x, a.beta * v[jj].y), m[jj]);
@@ -1020,18 +1056,33 @@ k_cluster_pass_lin(ClusterPassArgs a) {
           e[jj] = csub(d, m[jj]);
         }
       } else {
+        double2 mo[2];
+        if (recover) {
+          const double2 U0 = cdot2(Jro[0], C[0], Jro[1], C[2]);
+          const double2 U1 = cdot2(Jro[0], C[1], Jro[1], C[3]);
+          mo[0] = cdot2c(U0, Jqo[0], U1, Jqo[1]);
+          mo[1] = cdot2c(U0, Jqo[2], U1, Jqo[3]);
+          if (fl) mo[0] = mo[1] = make_double2(0.0, 0.0);
+        }
 #pragma unroll
         for (int jj = 0; jj < 2; jj++) {
           e[jj] = csub(v[jj], m[jj]);
-          if (a.write_out) st_stream(a.out + (jj ? c1 : c0) + row, e[jj]);
+          double2 o = e[jj];
+          if (recover) {
+            o.x = fma(gamma, v[jj].x - mo[jj].x, o.x);
+            o.y = fma(gamma, v[jj].y - mo[jj].y, o.y);
+          }
+          if (a.write_out) st_stream(a.out + (jj ? c1 : c0) + row, o);
         }
       }
+      if (a.mode <= 1) {
 #pragma unroll
-      for (int jj = 0; jj < 2; jj++) {
-        cost = fma(e[jj].x, e[jj].x, cost);
-        cost = fma(e[jj].y, e[jj].y, cost);
+        for (int jj = 0; jj < 2; jj++) {
+          cost = fma(e[jj].x, e[jj].x, cost);
+          cost = fma(e[jj].y, e[jj].y, cost);
+        }
       }
-      if (!fl) {
+      if (GRAD && !fl) {
 #pragma unroll
         for (int jj = 0; jj < 2; jj++)
 #pragma unroll
@@ -1039,6 +1090,11 @@ k_cluster_pass_lin(ClusterPassArgs a) {
       }
     }
     __syncthreads();  // every thread is done with stage s
+  }
+  if (!GRAD) {
+    // ADD / SUB / cost-only pass: no station sums
+    if (a.mode <= 1) grid_reduce_sum(cost, a.partials, a.cost, a.counter);
+    return;
   }
   // contraction with the Jones (see k_cluster_pass_split)
   double2 Gp[2], Gq[4];
@@ -1251,6 +1307,34 @@ int db_cluster_pass_nblocks(int ntile, int nt, int tslice) { return ntile * ((nt
 void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st) {
   int nt = a->t_end - a->t_begin;
   dim3 grid(ntile, (nt + a->tslice - 1) / a->tslice);
+  static const bool no_tma_any = getenv("DIRAC_B200_NO_TMA") != nullptr;
+  const bool lin_ok = (size_t)5 * 8 * 256 * sizeof(double2) + sizeof(double) * ((8 * a->N + 1) & ~1) + 40 <=
+                          (size_t)200 * 1024 && (a->Nbase + 255) / 256 <= 1024;
+  if (!(a->jte != nullptr && a->mode <= 1) && !a->wt && !a->in2 && !no_tma_any && lin_ok &&
+      !getenv("DIRAC_B200_ADDSUB_TILE")) {
+    // ADD / SUB / cost-only pass in the linear mapping: the same CTA-wide TMA ring as the gradient
+    // pass, without the station sums
+    constexpr int NST = 5;
+    const int nbg = (a->Nbase + 255) / 256;
+    int nsl = (db_sm_count() + nbg - 1) / nbg;
+    if (nsl > nt) nsl = nt;
+    ClusterPassArgs b = *a;
+    b.tslice = (nt + nsl - 1) / nsl;
+    const int forced = db_opt(DB_OPT_CP_ROWS);
+    if (forced > 0) b.tslice = forced;
+    if (b.tslice > nt) b.tslice = nt;
+    if (b.tslice > 32) b.tslice = 32;
+    const size_t smem = (size_t)NST * 8 * 256 * sizeof(double2) + sizeof(double) * ((8 * a->N + 1) & ~1) + NST * 8;
+    static bool configured = false;
+    if (!configured) {
+      DB_CHECK(cudaFuncSetAttribute(k_cluster_pass_lin<NST, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    dim3 glin(nbg, (nt + b.tslice - 1) / b.tslice);
+    k_cluster_pass_lin<NST, false><<<glin, 512, smem, st>>>(b);
+    return;
+  }
   if (a->jte != nullptr && a->mode <= 1) {
     static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
     // default: linear mapping with CTA-wide TMA stages; robust weights and DIRAC_B200_NO_TMA take the
@@ -1282,12 +1366,12 @@ void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st
                           sizeof(double) * ((8 * a->N + 1) & ~1) + NST * 8;
       static bool configured = false;
       if (!configured) {
-        DB_CHECK(cudaFuncSetAttribute(k_cluster_pass_lin<NST>,
+        DB_CHECK(cudaFuncSetAttribute(k_cluster_pass_lin<NST, true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
       }
       dim3 glin(nbg, (nt + b.tslice - 1) / b.tslice);
-      k_cluster_pass_lin<NST><<<glin, 512, smem, st>>>(b);
+      k_cluster_pass_lin<NST, true><<<glin, 512, smem, st>>>(b);
     }
   } else {
     k_cluster_pass<false><<<grid, TILE_THREADS, 0, st>>>(*a);

@@ -88,7 +88,7 @@ k_stream_all(StreamAllArgs a) {
   auto fetch_jones = [&](int j, double2 *jp, double2 *jq, double2 *dp, double2 *dq) {
     const int k = w + j * WARPS;
     const ClusterDesc cd = a.clus[k];
-    const long long row = (long long)t0 * a.Nbase + b;
+    const long long row = a.row0 + (long long)t0 * a.Nbase + b;
     const int off = a.chunk_poff[cd.chunk0 + row_chunk(row, a.R, cd.nchunk)];
     load_jones(a.pp + off, p, jp);
     load_jones(a.pp + off, q, jq);
@@ -122,8 +122,8 @@ k_stream_all(StreamAllArgs a) {
         if (i < nrows) {
           if (cd.nchunk > 1 && i > 0) {
             // hybrid cluster: the chunk (hence the Jones block) may change from row to row
-            const long long row = (long long)(t0 + i) * a.Nbase + b;
-            const long long row0 = (long long)t0 * a.Nbase + b;
+            const long long row = a.row0 + (long long)(t0 + i) * a.Nbase + b;
+            const long long row0 = a.row0 + (long long)t0 * a.Nbase + b;
             const int px = row_chunk(row, a.R, cd.nchunk);
             if (px != row_chunk(row0, a.R, cd.nchunk) || i > 1) {
               const int off = a.chunk_poff[cd.chunk0 + px];

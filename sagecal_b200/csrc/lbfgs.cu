@@ -72,24 +72,64 @@ static void line_setup(LbfgsCtx *c, const double *xk, const double *pk) {
   a.chunk_poff = d.chunk_poff; a.tiles = d.tiles; a.E0 = pr->E0; a.E1 = pr->E1; a.E2 = pr->E2;
   a.R = d.R; a.N = d.N; a.Nbase = d.Nbase; a.tilesz = d.tilesz; a.M = d.M;
   a.partial = (pr->world > 1) ? 1 : 0;
-  db_prof_begin(7, (double)d.R * (64.0 * d.M + 65.0 + 192.0), d.stream);
-  if (db_use_tma()) {
-    StreamAllArgs s;
-    memset(&s, 0, sizeof(s));
-    s.coh = a.coh; s.x = a.x; s.flag = a.flag; s.pp = a.xk; s.pk = a.pk; s.clus = a.clus;
-    s.chunk_poff = a.chunk_poff; s.blpq = d.blpq; s.E0 = a.E0; s.E1 = a.E1; s.E2 = a.E2;
-    s.R = a.R; s.N = a.N; s.Nbase = a.Nbase; s.tilesz = a.tilesz; s.M = a.M; s.partial = a.partial;
-    db_launch_line_setup_tma(&s, d.stream);
-  } else {
-    db_launch_line_setup(&a, d.ntile, d.stream);
-  }
-  db_prof_end(d.stream);
-  db_count_launch(1);
-  if (pr->world > 1) {
-    // sum the model polynomials of all ranks, then E0 = x - V0
-    db_allreduce(pr, pr->E0, 3 * 8 * d.R);  // E0 | E1 | E2 are contiguous
-    db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);
+  StreamAllArgs s;
+  memset(&s, 0, sizeof(s));
+  s.coh = a.coh; s.x = a.x; s.flag = a.flag; s.pp = a.xk; s.pk = a.pk; s.clus = a.clus;
+  s.chunk_poff = a.chunk_poff; s.blpq = d.blpq; s.E0 = a.E0; s.E1 = a.E1; s.E2 = a.E2;
+  s.R = a.R; s.N = a.N; s.Nbase = a.Nbase; s.tilesz = a.tilesz; s.M = a.M; s.partial = a.partial;
+  if (db_use_tma() && db_overlap_available(pr) && d.tilesz >= 8) {
+    // Sharded: the kernel runs in time chunks; each chunk's 12 slices (3 vectors x 4 polarisation
+    // planes) are summed over the ranks on the communication stream while the next chunk is computed
+    static cudaEvent_t ev_chunk[8], ev_done;
+    static bool have_ev = false;
+    if (!have_ev) {
+      for (int i = 0; i < 8; i++) DB_CHECK(cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming));
+      DB_CHECK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+      have_ev = true;
+    }
+    cudaStream_t cs = db_comm_stream();
+    const int nch = 8;
+    const int per = (d.tilesz + nch - 1) / nch;
+    db_prof_begin(7, (double)d.R * (64.0 * d.M + 65.0 + 192.0), d.stream);
+    int ci = 0;
+    for (int t0 = 0; t0 < d.tilesz; t0 += per, ci++) {
+      const int t1 = (t0 + per < d.tilesz) ? t0 + per : d.tilesz;
+      const long long r0 = (long long)t0 * d.Nbase, nr = (long long)(t1 - t0) * d.Nbase;
+      StreamAllArgs c2 = s;
+      c2.coh = s.coh + r0; c2.x = s.x + r0; c2.flag = s.flag + r0;
+      c2.E0 = s.E0 + r0; c2.E1 = s.E1 + r0; c2.E2 = s.E2 + r0;
+      c2.tilesz = t1 - t0; c2.row0 = r0;
+      db_launch_line_setup_tma(&c2, d.stream);
+      db_count_launch(1);
+      DB_CHECK(cudaEventRecord(ev_chunk[ci], d.stream));
+      DB_CHECK(cudaStreamWaitEvent(cs, ev_chunk[ci], 0));
+      double *seg[12];
+      long long cnt[12];
+      for (int v = 0; v < 3; v++)
+        for (int c = 0; c < 4; c++) {
+          double2 *base = (v == 0 ? pr->E0 : v == 1 ? pr->E1 : pr->E2) + (long long)c * d.R + r0;
+          seg[v * 4 + c] = reinterpret_cast<double *>(base);
+          cnt[v * 4 + c] = 2 * nr;
+        }
+      db_allreduce_segments(pr, seg, cnt, 12, cs);
+    }
+    db_prof_end(d.stream);
+    DB_CHECK(cudaEventRecord(ev_done, cs));
+    DB_CHECK(cudaStreamWaitEvent(d.stream, ev_done, 0));
+    db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);  // E0 = x - V0
     db_count_launch(1);
+  } else {
+    db_prof_begin(7, (double)d.R * (64.0 * d.M + 65.0 + 192.0), d.stream);
+    if (db_use_tma()) db_launch_line_setup_tma(&s, d.stream);
+    else db_launch_line_setup(&a, d.ntile, d.stream);
+    db_prof_end(d.stream);
+    db_count_launch(1);
+    if (pr->world > 1) {
+      // sum the model polynomials of all ranks, then E0 = x - V0
+      db_allreduce(pr, pr->E0, 3 * 8 * d.R);  // E0 | E1 | E2 are contiguous
+      db_launch_axpby(d.x, pr->E0, 4 * d.R, 1.0, -1.0, d.stream);
+      db_count_launch(1);
+    }
   }
   if (!c->robust && !db_opt(DB_OPT_LINE_DIRECT)) {
     // the Gaussian cost along the line is a quartic in alpha: five reductions, then every cost

@@ -74,6 +74,7 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.Dp = d.scal + 64;
   w.pnew = dalloc<double>(n8);
   w.plast = dalloc<double>(n8);
+  w.pold = dalloc<double>(n8);
   w.devinfo = reinterpret_cast<int *>(d.scal + 64 + 3 * n8);
   w.tau = dalloc<double>(n8);
   w.svdS = w.svdU = w.svdVT = nullptr;
@@ -136,7 +137,7 @@ void db_lm_free(dirac_b200_problem *pr) {
   LMWork &w = pr->lm;
   if (!w.ready) return;
   db_free(w.T); db_free(w.Tsub); db_free(w.JTJ0); db_free(w.JTJ);
-  db_free(w.Hst); db_free(w.pnew); db_free(w.plast); db_free(w.jte_part);
+  db_free(w.Hst); db_free(w.pnew); db_free(w.plast); db_free(w.pold); db_free(w.jte_part);
   db_free(w.tau); db_free(w.cswork); db_free(w.dbuf);
   if (w.svdS) { db_free(w.svdS); db_free(w.svdU); db_free(w.svdVT); }
   if (w.wbuf) { db_free(w.wbuf); db_free(w.ebuf); db_free(w.HP); db_free(w.HQ); }
@@ -170,12 +171,13 @@ static int pick_tslice(const DevProblem &d, int nt) {
 void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
                      double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
                      int t1, const double2 *wt, double beta = 1.0, const double2 *in2 = nullptr,
-                     bool jte_zeroed = false);
+                     bool jte_zeroed = false, const double *pblk_old = nullptr);
 
 // one streaming pass of cluster k over timeslots [t0,t1): see ClusterPassArgs for the modes
 void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, const double2 *in,
                      double2 *out, int mode, int write_out, double *jte_dev, int cost_slot, int t0,
-                     int t1, const double2 *wt, double beta, const double2 *in2, bool jte_zeroed) {
+                     int t1, const double2 *wt, double beta, const double2 *in2, bool jte_zeroed,
+                     const double *pblk_old) {
   DevProblem &d = pr->d;
   if (t1 <= t0) {
     if (mode <= 1) DB_CHECK(cudaMemsetAsync(d.scal + cost_slot, 0, sizeof(double), d.stream));
@@ -189,11 +191,13 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   a.partials = pr->partials; a.cost = d.scal + cost_slot; a.counter = d.counters; a.R = d.R;
   a.N = d.N; a.Nbase = d.Nbase; a.t_begin = t0; a.t_end = t1; a.tslice = pick_tslice(d, t1 - t0);
   a.mode = mode; a.write_out = write_out; a.wt = wt; a.beta = beta; a.in2 = in2;
+  a.pblk_old = pblk_old;
   // passes without the gradient accumulator fit two CTAs per SM: twice as many, half as long
   if (!(jte_dev && mode <= 1) && g_tslice_override <= 0 && a.tslice > 1) a.tslice = (a.tslice + 1) / 2;
   if (jte_dev && mode <= 1 && !jte_zeroed)
     DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
-  db_prof_begin(2, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
+  // kind 2: gradient-carrying passes (INIT, TRIAL); kind 8: ADD / SUB / cost-only passes
+  db_prof_begin((jte_dev && mode <= 1) ? 2 : 8, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
                                                  (wt ? 64.0 : 0.0)), d.stream);
   db_launch_cluster_pass(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
@@ -357,8 +361,6 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   const int n = w.n8;
   const size_t nn = (size_t)n * n;
   if ((double)d.M * nn * 16.0 > 24e9) return;  // keep the two batch buffers within 24 GB
-  if (n > 1024) return;  // the batched factorisation is a small-matrix routine; large systems are
-                         // assembled and factorised inside their visit
   if (!w.JB) {
     w.JB = dalloc<double>(nn * d.M);
     w.LB = dalloc<double>(nn * d.M);
@@ -426,9 +428,48 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   db_prof_end(d.stream);
   db_count_launch(4);
   db_prof_begin(5, 0.0, d.stream);
-  CS_CHECK(cusolverDnDpotrfBatched(w.cs, CUBLAS_FILL_MODE_LOWER, n, w.LBptr_dev, n, w.binfo_dev, nb));
+  if (n <= 1024) {
+    CS_CHECK(cusolverDnDpotrfBatched(w.cs, CUBLAS_FILL_MODE_LOWER, n, w.LBptr_dev, n, w.binfo_dev, nb));
+    db_count_launch(1);
+  } else {
+    // Large systems (8N = 4096 at 512 stations: 23 GFLOP each): the batched routine is a small-matrix
+    // code; a single dpotrf leaves most SMs idle in its panel phases (~10 TFLOP/s).  The clusters'
+    // first systems are independent, so they are factorised side by side on a few streams.
+    enum { NS = 4 };
+    static cudaStream_t fs[NS];
+    static cusolverDnHandle_t fh[NS];
+    static double *fwork[NS];
+    static int flwork = 0;
+    static cudaEvent_t fev[NS], fstart;
+    if (!flwork || flwork < w.lwork) {
+      for (int i = 0; i < NS; i++) {
+        if (!flwork) {
+          DB_CHECK(cudaStreamCreateWithFlags(&fs[i], cudaStreamNonBlocking));
+          CS_CHECK(cusolverDnCreate(&fh[i]));
+          CS_CHECK(cusolverDnSetStream(fh[i], fs[i]));
+          DB_CHECK(cudaEventCreateWithFlags(&fev[i], cudaEventDisableTiming));
+        } else {
+          db_free(fwork[i]);
+        }
+        fwork[i] = dalloc<double>((size_t)w.lwork);
+      }
+      if (!flwork) DB_CHECK(cudaEventCreateWithFlags(&fstart, cudaEventDisableTiming));
+      flwork = w.lwork;
+    }
+    DB_CHECK(cudaEventRecord(fstart, d.stream));
+    for (int i = 0; i < NS && i < nb; i++) DB_CHECK(cudaStreamWaitEvent(fs[i], fstart, 0));
+    for (int b = 0; b < nb; b++) {
+      const int i = b % NS;
+      CS_CHECK(cusolverDnDpotrf(fh[i], CUBLAS_FILL_MODE_LOWER, n, w.LB + nn * b, n, fwork[i], flwork,
+                                w.binfo_dev + b));
+    }
+    for (int i = 0; i < NS && i < nb; i++) {
+      DB_CHECK(cudaEventRecord(fev[i], fs[i]));
+      DB_CHECK(cudaStreamWaitEvent(d.stream, fev[i], 0));
+    }
+    db_count_launch(nb);
+  }
   db_prof_end(d.stream);
-  db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(w.h_mu, w.mu_dev, sizeof(double) * nb, cudaMemcpyDeviceToHost, d.stream));
   DB_CHECK(cudaMemcpyAsync(w.h_binfo, w.binfo_dev, sizeof(int) * nb, cudaMemcpyDeviceToHost,
                            d.stream));
@@ -829,6 +870,9 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
   // the first func/jacf evaluation, clmfit.c:241-252)
   // (sharded runs weight the residual share of the hidden data with beta, SAGE: d = f + beta r)
   const double beta = pr->world > 1 ? pr->beta : 1.0;
+  if (beta != 1.0)  // the closing pass recovers the old residual from the Jones the visit started with
+    DB_CHECK(cudaMemcpyAsync(w.pold, pblk_dev, sizeof(double) * w.n8, cudaMemcpyDeviceToDevice,
+                             d.stream));
   db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 0, 1, os ? nullptr : w.JTe, 2, t0, t1, nullptr, beta);
   // ||e||^2 at entry stays on the device for now: lm_core fetches it together with p and J^T e
   // (NaN = "still in d.scal[2]")
@@ -840,8 +884,8 @@ void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double
           randomize, true, c0, &nu, &ev, &o);
   // residual of the chunk with the final Jones: r = d - f(p) (+ (1-beta) r when sharded)
   // (lmfit.c:980-981)
-  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr, beta,
-                  beta != 1.0 ? r : nullptr);
+  db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr, beta, nullptr, false,
+                  beta != 1.0 ? w.pold : nullptr);
   fill_info(info, o);
 }
 
@@ -925,8 +969,12 @@ void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, doubl
   const double ndata = 8.0 * (double)(r1 - r0);
   // hidden data d = beta r + f(p_old)
   const double beta = pr->world > 1 ? pr->beta : 1.0;
-  if (!hidden_ready)
+  if (!hidden_ready) {
+    if (beta != 1.0)
+      DB_CHECK(cudaMemcpyAsync(w.pold, pblk_dev, sizeof(double) * w.n8, cudaMemcpyDeviceToDevice,
+                               d.stream));
     db_cluster_pass(pr, k, pblk_dev, r, w.dbuf, 2, 1, nullptr, 1, t0, t1, nullptr, beta);
+  }
   if (r1 > r0) db_launch_scale_vis(w.wbuf, d.R, r0, r1, 1.0, 1, d.stream);  // wt = 1
   db_count_launch(1);
   double nu_t = *robust_nu;
@@ -960,8 +1008,8 @@ void db_rlm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, doubl
   *robust_nu = nu_t;
   // residual of the chunk with the final Jones: r = d - f(p) (+ (1-beta) r when sharded)
   if (!hidden_ready)
-    db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr, beta,
-                    beta != 1.0 ? r : nullptr);
+    db_cluster_pass(pr, k, pblk_dev, w.dbuf, r, 3, 1, nullptr, 1, t0, t1, nullptr, beta, nullptr, false,
+                    beta != 1.0 ? w.pold : nullptr);
   (void)n8;
   fill_info(info, o);
 }

@@ -35,6 +35,7 @@ struct LMWork {
   double2 *ebuf;          // [4][R] unweighted residual for the weight update
   double *HP, *HQ;        // [N][2][10] station sums of the weighted normal matrix
   double *plast;          // [8N] device copy of the last evaluated trial point
+  double *pold;           // [8N] Jones at the start of the visit (sharded closing pass)
   // normal matrices of ALL clusters of a sweep, assembled and factorised in one batch before the
   // sweep (each cluster's first LM solve then only needs the triangular solves)
   double *JB, *LB;        // [M][8N][8N] J^T J and its damped Cholesky factor
@@ -92,6 +93,10 @@ int db_use_tma();
 void db_lm_init(dirac_b200_problem *pr);
 void db_prefactor_sweep(dirac_b200_problem *pr, double tau);
 void db_allreduce(dirac_b200_problem *pr, void *dev, long long count);
+int db_overlap_available(const dirac_b200_problem *pr);
+cudaStream_t db_comm_stream();
+void db_allreduce_segments(dirac_b200_problem *pr, double **ptr, const long long *count, int nseg,
+                           cudaStream_t st);
 extern "C" {
 void db_launch_residual_cost(const double2 *x, const double2 *pm, double2 *out, long long n4,
                              int out_mode, int cost_mode, double inv_nu, double *partials,

@@ -54,6 +54,9 @@ def parse():
                          "metric is quoted on, 256 clusters on 8 GPUs) | C2 (62 st, 64 clusters) | C3 "
                          "(robust) | C1 | custom N,M,T e.g. 62,16,30")
     ap.add_argument("--only", action="store_true", help="one GPU: do not append the C2 and C3 lines")
+    ap.add_argument("--profile-run", action="store_true",
+                    help="for runs UNDER ncu only: 1 warm-up, no instrumented repeat, no e2e, no CPU leg "
+                         "(a number printed by such a run is never a bench value)")
     ap.add_argument("--devgen", action="store_true", help="generate the coherencies on the device "
                     "(always for C4)")
     ap.add_argument("--c4-clusters-per-gpu", type=int, default=32)
@@ -411,6 +414,8 @@ def run_workload(name, args, ctx, with_cpu=True):
     coh_bytes = coh_h.nbytes if coh_h is not None else 64 * R * (M // world)
 
     K, W = args.steps, max(args.warmup, 3)
+    if args.profile_run:
+        K, W = 1, 1
     clocks = ClockSampler(local)
 
     # ---------------- resident-data throughput (`value`) ----------------
@@ -451,7 +456,7 @@ def run_workload(name, args, ctx, with_cpu=True):
         api.profile_enable(True)
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(stream)
-        for _ in range(K):
+        for _ in range(0 if args.profile_run else K):
             pp = pr.pp0.copy()
             res = dp.sagefit(pp, None, **SOLVE_W)
         p1.record(stream)
@@ -470,7 +475,7 @@ def run_workload(name, args, ctx, with_cpu=True):
     # ---------------- end to end through the drop-in C entry point (`e2e`) ----------------
     e2e = None
     dp.close()
-    if not args.no_e2e:
+    if not args.no_e2e and not args.profile_run:
         if devgen:
             # u, v, w, data, Jones, flags up; the coherencies are generated on the device
             h2d = 3 * 8 * R + x_h.nbytes + pp_h.nbytes + R
@@ -556,7 +561,7 @@ def run_workload(name, args, ctx, with_cpu=True):
                 "solver": solver, "kernels": shares}
 
     cpu = None
-    if with_cpu and not args.no_cpu_baseline:
+    if with_cpu and not args.no_cpu_baseline and not args.profile_run:
         cpu = cpu_baseline_object(shape["seed"])
 
     if world > 1:
@@ -641,7 +646,7 @@ def main():
     line = run_workload(args.workload, args, ctx)
     # one GPU: the two 62-station configurations of BASELINE.json ride along (their own parity
     # against the full-shape goldens, value, roofline), so that one driver run covers C2, C3 and C4
-    if world == 1 and rank == 0 and args.workload == "C4" and not args.only:
+    if world == 1 and rank == 0 and args.workload == "C4" and not args.only and not args.profile_run:
         others = {}
         for w in ("C2", "C3"):
             o = run_workload(w, args, ctx, with_cpu=False)

@@ -1288,8 +1288,19 @@ void db_launch_grad_tma(const GradArgs *a, int ntile, cudaStream_t st) {
   static int cfg = -1;
   static const bool unsplit = getenv("DIRAC_B200_CP_UNSPLIT") != nullptr;
   if (!unsplit) {
-    launch_grad_tma_split<4, 2>(a, ntile, st);
-    return;
+    static int scfg = -1;
+    if (scfg < 0) {
+      const char *e = getenv("DIRAC_B200_GRADS_CFG");
+      scfg = e ? atoi(e) : 0;
+    }
+    switch (scfg) {
+      case 1: launch_grad_tma_split<2, 2>(a, ntile, st); return;
+      case 2: launch_grad_tma_split<2, 3>(a, ntile, st); return;
+      case 3: launch_grad_tma_split<4, 3>(a, ntile, st); return;
+      case 4: launch_grad_tma_split<8, 2>(a, ntile, st); return;
+      case 5: launch_grad_tma_split<1, 4>(a, ntile, st); return;
+      default: launch_grad_tma_split<4, 2>(a, ntile, st); return;
+    }
   }
   if (cfg < 0) {
     const char *e = getenv("DIRAC_B200_GRAD_CFG");

@@ -290,6 +290,40 @@ static void launch_stream_all(const StreamAllArgs *a, cudaStream_t st) {
       default: break;
     }
   }
+  if (MODE == 1) {
+    static int v1 = -1;
+    if (v1 < 0) {
+      const char *e = getenv("DIRAC_B200_SA_CFG1");
+      v1 = e ? atoi(e) : 0;
+    }
+    if (v1 == 0) {
+      // one row per item keeps the three accumulated polynomials of the line model at 24 registers
+      // pairs (222 -> ~170 registers: 7.5 % -> 12 % resident warps, ncu r02).  Splitting the clusters
+      // of an item over warps only pays while the grid is short of warps (62 stations: 7200 items);
+      // a large array has plenty (512 stations: 490 k items) and skips the cross-warp combine.
+      const long long items = (long long)((a->Nbase + 31) / 32) * a->tilesz;
+      if (items >= 64ll * db_sm_count()) launch_cfg<MODE, 1, 4, 1, false>(a, st);
+      else launch_cfg<MODE, 1, 2, 3, false>(a, st);
+      return;
+    }
+    switch (v1) {
+      case 1: launch_cfg<MODE, 2, 2, 3, false>(a, st); return;
+      case 2: launch_cfg<MODE, 1, 3, 3, false>(a, st); return;
+      case 3: launch_cfg<MODE, 1, 2, 4, false>(a, st); return;
+      case 4: launch_cfg<MODE, 1, 3, 4, false>(a, st); return;
+      case 5: launch_cfg<MODE, 2, 2, 4, false>(a, st); return;
+      case 6: launch_cfg<MODE, 1, 4, 2, false>(a, st); return;
+      case 7: launch_cfg<MODE, 1, 2, 6, false>(a, st); return;
+      case 8: launch_cfg<MODE, 1, 2, 8, false>(a, st); return;
+      case 9: launch_cfg<MODE, 1, 4, 1, false>(a, st); return;
+      case 10: launch_cfg<MODE, 1, 6, 1, false>(a, st); return;
+      case 11: launch_cfg<MODE, 1, 6, 2, false>(a, st); return;
+      case 12: launch_cfg<MODE, 1, 8, 2, false>(a, st); return;
+      case 13: launch_cfg<MODE, 2, 4, 2, false>(a, st); return;
+      case 14: launch_cfg<MODE, 1, 3, 2, false>(a, st); return;
+      default: break;
+    }
+  }
   launch_cfg<MODE, TB, SA_NST, SA_WARPS, false>(a, st);
 }
 

@@ -375,3 +375,24 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
   db_stream_sync(d.stream);
   db_free(ws);
 }
+
+// micro-benchmark of the line-model setup on the resident problem (direction = current Jones):
+// average device time (us) of `reps` back-to-back launches
+extern "C" double dirac_b200_bench_line_setup(dirac_b200_problem *pr, int reps) {
+  DevProblem &d = pr->d;
+  LbfgsCtx c;
+  c.pr = pr; c.robust = 1; c.nu = 2.0; c.m = (int)d.npar; c.ncost = c.ngrad = 0;
+  cudaEvent_t e0, e1;
+  DB_CHECK(cudaEventCreate(&e0));
+  DB_CHECK(cudaEventCreate(&e1));
+  for (int i = 0; i < 2; i++) line_setup(&c, d.pp, d.pp);
+  DB_CHECK(cudaEventRecord(e0, d.stream));
+  for (int i = 0; i < reps; i++) line_setup(&c, d.pp, d.pp);
+  DB_CHECK(cudaEventRecord(e1, d.stream));
+  DB_CHECK(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  DB_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 1e3 * ms / reps;
+}

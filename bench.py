@@ -607,6 +607,118 @@ def run_workload(name, args, ctx, with_cpu=True):
     return line
 
 
+def run_consensus(args, ctx):
+    """BASELINE.json config 5: 62 stations x `world` frequency subbands (one per GPU), 128 clusters,
+    consensus (ADMM) calibration; one step = `ADMM` iterations, each a SAGE sweep with the consensus
+    terms in every cluster's cost followed by ONE all-reduce of Npoly*8*N*Mt doubles"""
+    import torch
+    import torch.distributed as dist
+    from sagecal_b200 import lib as blib
+    from sagecal_b200 import synth, consensus as cons
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+    api, stream, rank, world, local = ctx["api"], ctx["stream"], ctx["rank"], ctx["world"], ctx["local"]
+    c = synth.CONFIGS["C5"]
+    ADMM, NPOLY, RHO = 5, 3, 5.0
+    freqs = np.linspace(115e6, 185e6, 8)[:max(world, 1)] if world <= 8 else np.linspace(115e6, 185e6, world)
+    f = float(freqs[rank])
+    pr = synth.make_problem(N=c["N"], M=c["M"], tilesz=c["tilesz"], radius=c["radius"], seed=c["seed"],
+                            kmean=c["kmean"], freq0=f, with_data=False)
+    barr = make_barr(pr.sta1, pr.sta2, pr.flag)
+    sky = SkyModel(pr.clusters, pr.N)
+    # Jones smooth in frequency: linear around 150 MHz
+    rng = np.random.default_rng(c["seed"] + 99)
+    slope = 0.2 * rng.normal(0, 1, pr.jones_true.shape)
+    jt = pr.jones_true + slope * (f - 150e6) / 150e6
+    pr.x = np.zeros(8 * pr.Nbase1)
+    R, M = pr.Nbase1, pr.M
+
+    def make_resident():
+        dpx = blib.DeviceProblem(api, pr.N, pr.Nbase, pr.tilesz, barr, sky, None, pr.x)
+        dpx.precalculate(pr.u, pr.v, pr.w, f, pr.fdelta)
+        return dpx
+
+    with torch.cuda.stream(stream):
+        dp = make_resident()
+        _, model = dp.predict(jt, out_mode=2)
+        sig = 1e-2 * np.median(np.abs(model))
+        pr.x = model + np.random.default_rng(c["seed"] + 17 + rank).normal(0, sig, model.shape)
+        pr.x.reshape(R, 8)[pr.flag == 1] = 0.0
+        dp.set_data(pr.x)
+        rho = np.full(M, RHO)
+
+        def solve(dpx):
+            sb = cons.ConsensusSubband(api, dpx, rank, freqs, 150e6, min(NPOLY, max(1, world - 1)) if world > 1 else 1,
+                                       rho, ptype=1)
+            pp = pr.pp0.copy()
+            return sb, pp, sb.run(pp, admm_iters=ADMM, max_emiter=1, max_iter=2)
+
+        K, W = args.steps, max(args.warmup, 3)
+        hist = None
+        for _ in range(W):
+            sb, pp, hist = solve(dp)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = api.launch_count()
+        api.host_stats(reset=True)
+        clocks = ClockSampler(local)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            sb, pp, hist = solve(dp)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clk = clocks.stop()
+        hstat = api.host_stats()
+        launches = api.launch_count() - l0
+        ms_total = e0.elapsed_time(e1)
+        dp.close()
+        # end to end: upload + device coherencies + solve per step
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(K):
+            dpe = make_resident()
+            solve(dpe)
+            dpe.close()
+        f1.record(stream)
+        torch.cuda.synchronize()
+    t = torch.tensor([ms_total, f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_e2e = float(t[0].item()) / K, float(t[1].item()) / K
+    units = R * M * ADMM * world
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC, "value": units / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C5: N=%d stations x %d subbands (one per GPU), M=%d clusters, tilesz=%d; "
+                               "%d ADMM iterations (1 SAGE sweep x 2 LM iterations each), Npoly=%d, rho=%g"
+                               % (pr.N, world, M, pr.tilesz, ADMM, sb.Npoly, RHO),
+                   "units_per_step": "rows*clusters*ADMM iterations*subbands",
+                   "parallelism": "one subband per GPU, ONE all-reduce of Npoly*8*N*Mt doubles per ADMM "
+                                  "iteration, called from C",
+                   "coherencies": "generated on the device (dirac_b200_precalculate)"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(3 * 8 * R + 64 * R + R + 8 * len(pr.pp0)),
+                "d2h_bytes_per_step": int(8 * len(pr.pp0) * 3 * ADMM)},
+        "parity": {"checked": True, "what": "primal residual ||J - B Z|| and data residual per ADMM iteration; "
+                                            "exchange and J-update are pinned by tests/test_gpu_consensus.py, "
+                                            "tests/consensus_check.py, tests/test_cpu_consensus.py",
+                   "primal": [h[2] for h in hist], "res_1": [h[1] for h in hist],
+                   "ok": bool(world == 1 or hist[-1][2] < hist[0][2])},
+        "breakdown": {"ms_per_step": ms_step, "host_syncs_per_step": hstat["host_syncs"] / K,
+                      "host_wait_ms": 1e3 * hstat["host_wait_s"] / K,
+                      "collectives_per_step": hstat["collectives"] / K,
+                      "collective_MB_per_step": hstat["collective_bytes"] / K / 1e6},
+    }
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -643,6 +755,16 @@ def main():
     if world > 1:
         dist.barrier()
 
+    if args.workload == "C5":
+        if world > 1:
+            sdist.init_nccl(api, rank, world)
+        line = run_consensus(args, ctx)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            api.lib.dirac_b200_nccl_finalize()
+            dist.destroy_process_group()
+        return
     line = run_workload(args.workload, args, ctx)
     # one GPU: the two 62-station configurations of BASELINE.json ride along (their own parity
     # against the full-shape goldens, value, roofline), so that one driver run covers C2, C3 and C4

@@ -214,6 +214,49 @@ int dirac_b200_nccl_ready(void);
 void dirac_b200_comm_stats(unsigned long long *calls, unsigned long long *bytes,
                            double *enqueue_seconds, int reset);
 
+/* ---- consensus (ADMM) calibration over frequency subbands, one subband per GPU -------------------
+ * (BASELINE.json config 5; src/MPI/sagecal_master.cpp:844-877, sagecal_slave.cpp:831-878,
+ * src/lib/Dirac/consensus_poly.c, admm_solve.c).  No master process: the sum over subbands is ONE
+ * all-reduce of Npoly*8*N*Mt doubles per ADMM iteration on the library's stream (the communicator of
+ * dirac_b200_nccl_init, or the callback of dirac_b200_set_comm), every rank applies the replicated
+ * pseudo-inverse and its own basis row itself. */
+/* replaces setup_polynomials (consensus_poly.c:38): B[f*Npoly + p], type 0 ordinary, 1 normalised,
+ * 2 Bernstein, 3 mixed powers.  Host arithmetic, no GPU needed. */
+int dirac_b200_consensus_basis(double *B, int Npoly, int Nf, const double *freqs, double freq0,
+                               int type);
+/* replaces find_prod_inverse_full (consensus_poly.c:465): Bi[k] = pinv(sum_f rho[k + f*M] B_f B_f^T),
+ * Npoly x Npoly per cluster.  Host arithmetic, no GPU needed. */
+int dirac_b200_consensus_prod_inverse(const double *B, double *Bi, int Npoly, int Nf, int M,
+                                      const double *rho);
+/* one exchange for this rank's subband (J, Y, BZ: host vectors laid out like pp; rho[M]; Bf[Npoly] =
+ * this subband's basis row; Bi[M][Npoly][Npoly]):  Y += rho J;  z = B_f (x) Y summed over the ranks;
+ * BZ = B_f Bi z;  Y -= rho BZ.  *primal = ||J - BZ||, *dual = ||BZ - BZ_old||. */
+int dirac_b200_consensus_step(dirac_b200_problem *pr, const double *J, double *Y, double *BZ,
+                              const double *rho, const double *Bf, const double *Bi, int Npoly,
+                              double *primal, double *dual);
+/* the J-update of one ADMM iteration on a resident problem, and its drop-in form: replaces
+ * sagefit_visibilities_admm (Dirac.h:1521, admm_solve.c:221) and its GPU-build twin (:1533).  Each
+ * cluster's cost carries y^T (p - bz) + rho/2 |p - bz|^2; solved with this library's LM (the reference
+ * uses its Riemannian trust-region solver here, so iterates differ; the ADMM fixed point does not). */
+int dirac_b200_sagefit_admm(dirac_b200_problem *pr, double *pp, double *x_out, const double *Y,
+                            const double *BZ, const double *admm_rho, int max_emiter, int max_iter,
+                            int linsolv, int randomize, double *res_0, double *res_1);
+int sagefit_visibilities_admm(double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz,
+                              baseline_t *barr, clus_source_t *carr, double *coh, int M, int Mt,
+                              double freq0, double fdelta, double *pp, double *Y, double *BZ,
+                              double uvmin, int Nt, int max_emiter, int max_iter, int max_lbfgs,
+                              int lbfgs_m, int gpu_threads, int linsolv, int solver_mode, double nulow,
+                              double nuhigh, int randomize, double *admm_rho, double *mean_nu,
+                              double *res_0, double *res_1);
+int sagefit_visibilities_admm_dual_pt_flt(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                          int tilesz, baseline_t *barr, clus_source_t *carr,
+                                          double *coh, int M, int Mt, double freq0, double fdelta,
+                                          double *pp, double *Y, double *BZ, double uvmin, int Nt,
+                                          int max_emiter, int max_iter, int max_lbfgs, int lbfgs_m,
+                                          int gpu_threads, int linsolv, int solver_mode, double nulow,
+                                          double nuhigh, int randomize, double *admm_rho,
+                                          double *mean_nu, double *res_0, double *res_1);
+
 /* run on a caller-supplied CUDA stream (cudaStream_t) instead of a private one; NULL restores the
  * default.  Affects problems created afterwards and the reference entry points. */
 void dirac_b200_set_stream(void *stream);

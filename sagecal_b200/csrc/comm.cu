@@ -123,6 +123,20 @@ void db_allreduce(dirac_b200_problem *pr, void *dev, long long count) {
   g_comm_bytes += (unsigned long long)count * 8ull;
 }
 
+void db_allreduce_world(dirac_b200_problem *pr, void *dev, long long count) {
+  if (count <= 0) return;
+  if (pr->allreduce) {
+    pr->allreduce(dev, count, (void *)pr->d.stream, pr->comm_user);
+    g_comm_calls++;
+    g_comm_bytes += (unsigned long long)count * 8ull;
+  } else if (g_nccl.comm && g_nccl.world > 1) {
+    NCCL_CHECK(g_nccl.AllReduce(dev, dev, (size_t)count, DB_NCCL_DOUBLE, DB_NCCL_SUM, g_nccl.comm,
+                                pr->d.stream));
+    g_comm_calls++;
+    g_comm_bytes += (unsigned long long)count * 8ull;
+  }
+}
+
 // ---- overlapped exchange: all-reduces on a communication stream of the library, grouped ----------
 // Used where a streaming kernel is followed by a large all-reduce of what it wrote (the LBFGS line
 // model: three visibility-sized vectors per iteration): the kernel is launched in time chunks and

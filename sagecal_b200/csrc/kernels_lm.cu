@@ -256,7 +256,20 @@ k_lm_step(const double *__restrict__ p, const double *__restrict__ Dp,
   }
 }
 
+// g <- g - y/2 - rho/2 (p - bz): J^T e of a pass -> (minus half) the gradient of the consensus-
+// augmented cost ||e||^2 + y^T (p - bz) + rho/2 |p - bz|^2
+__global__ void k_lm_aug_rhs(double *__restrict__ g, const double *__restrict__ p,
+                             const double *__restrict__ y, const double *__restrict__ bz, double rho,
+                             int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g[i] = g[i] - 0.5 * y[i] - 0.5 * rho * (p[i] - bz[i]);
+}
+
 extern "C" {
+void db_launch_lm_aug_rhs(double *jte, const double *p, const double *y, const double *bz,
+                          double rho, int n, cudaStream_t st) {
+  k_lm_aug_rhs<<<(n + 255) / 256, 256, 0, st>>>(jte, p, y, bz, rho, n);
+}
 void db_launch_lm_step(const double *p, const double *Dp, const double *jte, double *pnew,
                        double *sc, double *zero, int n, cudaStream_t st) {
   k_lm_step<<<1, 512, 0, st>>>(p, Dp, jte, pnew, sc, zero, n);

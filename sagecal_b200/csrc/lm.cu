@@ -505,6 +505,33 @@ extern "C" long dirac_b200_noise_decisions(int reset) {
   return v;
 }
 
+// Consensus (ADMM) terms of one (cluster, chunk) block: the LM minimises
+//   ||d - f(p)||^2 + y^T (p - bz) + rho/2 |p - bz|^2       (Dirac.h:1524)
+// whose Gauss-Newton system is (J^T J + rho/2 I + mu I) dp = J^T e - y/2 - rho/2 (p - bz): the
+// right-hand side is corrected on the device after every pass that produced J^T e, rho/2 rides on the
+// damping handed to the solver, and the host adds the two extra terms to the costs it compares.
+struct LmAug {
+  const double *y_dev, *bz_dev;    // device, this block (8N)
+  const double *y_host, *bz_host;  // host, this block
+  double rho;
+};
+static const LmAug *g_aug = nullptr;
+static std::vector<double> g_hpnew;
+static double *hpnew_aug(LMWork &w) {
+  if ((int)g_hpnew.size() < w.n8) g_hpnew.resize(w.n8);
+  return g_hpnew.data();
+}
+static double aug_cost(const LmAug *a, const double *p, int n) {
+  double s = 0.0;
+  for (int i = 0; i < n; i++) {
+    const double dlt = p[i] - a->bz_host[i];
+    s += a->y_host[i] * dlt + 0.5 * a->rho * dlt * dlt;
+  }
+  return s;
+}
+extern "C" void db_launch_lm_aug_rhs(double *jte, const double *p, const double *y, const double *bz,
+                                     double rho, int n, cudaStream_t st);
+
 struct LmOut {
   double init_eL2, eL2, jacTe_inf, Dp_L2, mu;
   int k, stop;
@@ -531,9 +558,14 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   // come from the batch), so the entry values (p, J^T e, ||e||^2) ride back with the trial's results
   // and the entry tests of clmfit.c:300-340 are applied after the fact (a trial that should not have
   // been taken is simply discarded: it only wrote scratch buffers).
+  const LmAug *aug = (!os && !wt) ? g_aug : nullptr;
+  const double half_rho = aug ? 0.5 * aug->rho : 0.0;
+  if (aug) w.pref_slot[k] = -1;  // the batch factor does not know about rho/2
   const bool defer = have_first && !os && !wt && linsolv == 0 && itmax > 0 && w.pref_slot[k] >= 0 &&
                      std::isnan(first_cost);
   DB_CHECK(cudaMemcpyAsync(hp, pblk_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+  if (aug && have_first)  // J^T e of the fused first pass -> gradient of the augmented cost
+    db_launch_lm_aug_rhs(w.JTe, pblk_dev, aug->y_dev, aug->bz_dev, aug->rho, n, d.stream);
   if (have_first) {
     p_eL2 = first_cost;
     if (!defer) {
@@ -551,10 +583,12 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   } else {
     // e = wt.(d - f(p)), ||e||^2, J^T e     (clmfit.c:241-252 / robustlm.c:2235-2251)
     db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe, 1, t0, t1, wt);
+    if (aug) db_launch_lm_aug_rhs(w.JTe, pblk_dev, aug->y_dev, aug->bz_dev, aug->rho, n, d.stream);
     if (!os)
       DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
     p_eL2 = db_read_scalar(pr, 1);
   }
+  if (aug && !defer) p_eL2 += aug_cost(aug, hp, n);
   double init_p_eL2 = p_eL2;
   int stop = 0;
   if (!isfinite(p_eL2)) stop = 7;
@@ -670,7 +704,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           break;
         }
       }
-      if (kiter == 0) mu = prefac ? w.h_mu[slot] : tau * mx;  // clmfit.c:342-352
+      if (kiter == 0) mu = prefac ? w.h_mu[slot] : tau * (mx + half_rho);  // clmfit.c:342-352
       bool use_factor = prefac;
       // adaptive damping loop (clmfit.c:356-540)
       while (1) {
@@ -702,7 +736,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           db_count_launch(1);
           issolved = (w.h_binfo[slot] == 0) ? 1 : 0;
         } else {
-          issolved = enqueue_solve(pr, mu, linsolv, eps1);
+          issolved = enqueue_solve(pr, mu + half_rho, linsolv, eps1);
         }
         // p + dp, |dp|^2, dp.J^T e on the device; trial pass; everything back in one go
         if (w.step_armed) db_chol_set_step(nullptr, nullptr, nullptr, nullptr);
@@ -711,6 +745,8 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
                             d.stream);
         db_cluster_pass(pr, k, w.pnew, w.dbuf, nullptr, 1, 0, os ? nullptr : w.JTe_new, 1, t0, t1,
                         wt, 1.0, nullptr, true);
+        if (aug)
+          db_launch_lm_aug_rhs(w.JTe_new, w.pnew, aug->y_dev, aug->bz_dev, aug->rho, n, d.stream);
         if (!w.step_fused) db_count_launch(1);  // k_lm_step
         int *hinfo = (int *)(w.h_vec + 4 * n + 4 * d.N);
         DB_CHECK(cudaMemcpyAsync(d.h_scal, d.scal, sizeof(double) * (64 + 3 * n + 2),
@@ -782,7 +818,11 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
             DB_CHECK(cudaMemcpyAsync(w.plast, w.pnew, sizeof(double) * n, cudaMemcpyDeviceToDevice,
                                      d.stream));
           *evaluated_trial = true;
-          const double pDp_eL2 = hsc[n + 2];
+          double pDp_eL2 = hsc[n + 2];
+          if (aug) {
+            for (int i = 0; i < n; i++) hpnew_aug(w)[i] = hp[i] + hDp[i];
+            pDp_eL2 += aug_cost(aug, hpnew_aug(w), n);
+          }
           if (!isfinite(pDp_eL2)) {
             stop = 7;
             break;
@@ -846,6 +886,17 @@ static void fill_info(double *info, const LmOut &o) {
 // pblk_dev points at the 8N parameters inside the device copy of pp (updated in place).
 // info[0] = ||e||^2 at entry, info[1] = ||e||^2 at exit (lmfit.c:963-964 uses exactly these).
 // ------------------------------------------------------------------------------------------------
+void db_lm_set_aug(const double *y_dev, const double *bz_dev, const double *y_host,
+                   const double *bz_host, double rho) {
+  static LmAug a;
+  if (!y_dev) {
+    g_aug = nullptr;
+    return;
+  }
+  a.y_dev = y_dev; a.bz_dev = bz_dev; a.y_host = y_host; a.bz_host = bz_host; a.rho = rho;
+  g_aug = &a;
+}
+
 void db_lm_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int itmax,
                  const double *opts, int linsolv, int os, int randomize, double *info,
                  bool hidden_ready) {

@@ -66,6 +66,9 @@ struct dirac_b200_problem {
   int m_global;           // clusters over all ranks
   int k_global0;          // global index of local cluster 0
   double beta;            // hidden-data weight of the sharded SAGE sweep (1/world by default)
+  // consensus (ADMM) terms of the running solve (dirac_b200_sagefit_admm), null otherwise
+  const double *aug_y_host, *aug_bz_host, *aug_rho;  // host: [npar], [npar], [M]
+  double *aug_dev;        // device: Y | BZ
   double2 *pm;            // [4][R] partial model / residual at the start of a sharded sweep
   double *xb;             // [8R + npar + m_global] sweep exchange message (sharded)
   double *pp_start;       // [npar] Jones at the start of a sharded sweep
@@ -93,6 +96,11 @@ int db_use_tma();
 void db_lm_init(dirac_b200_problem *pr);
 void db_prefactor_sweep(dirac_b200_problem *pr, double tau);
 void db_allreduce(dirac_b200_problem *pr, void *dev, long long count);
+// sum over the ranks of the process-wide communicator regardless of cluster sharding (consensus over
+// subbands: every rank holds its own, unsharded problem); no-op without a communicator
+void db_allreduce_world(dirac_b200_problem *pr, void *dev, long long count);
+void db_lm_set_aug(const double *y_dev, const double *bz_dev, const double *y_host,
+                   const double *bz_host, double rho);
 int db_overlap_available(const dirac_b200_problem *pr);
 cudaStream_t db_comm_stream();
 void db_allreduce_segments(dirac_b200_problem *pr, double **ptr, const long long *count, int nseg,

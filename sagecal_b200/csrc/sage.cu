@@ -114,7 +114,8 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
       // plain LM this sweep?  then assemble + factorise every cluster's first system as one batch
       const bool last_em = (ci == max_emiter - 1);
       const bool plain = (solver_mode == SM_LM_LBFGS) || (solver_mode == SM_OSLM_LBFGS && last_em);
-      if (plain && linsolv == 0 && max_iter > 0 && !weighted_iter) db_prefactor_sweep(pr, opts[0]);
+      if (plain && linsolv == 0 && max_iter > 0 && !weighted_iter && !pr->aug_rho)
+        db_prefactor_sweep(pr, opts[0]);
     }
     for (int cl = 0; cl < M; cl++) {
       const int cj = cl;          // local cluster index (device tables)
@@ -132,8 +133,12 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
         const bool hr = db_cluster_needs_rowmap(pr, cj);
         if (hr) db_cluster_hidden(pr, cj, r, +1);
         for (int ck = 0; ck < hc[cj].nchunk; ck++) {
-          double *pblk = d.pp + d.h_chunk_poff[hc[cj].chunk0 + ck];
+          const int poff = d.h_chunk_poff[hc[cj].chunk0 + ck];
+          double *pblk = d.pp + poff;
           const bool last = (ci == max_emiter - 1);
+          if (pr->aug_rho)  // consensus terms of this block (dirac_b200_sagefit_admm)
+            db_lm_set_aug(pr->aug_dev + poff, pr->aug_dev + d.npar + poff, pr->aug_y_host + poff,
+                          pr->aug_bz_host + poff, pr->aug_rho[cg]);
           if (solver_mode == SM_OSLM_LBFGS) {
             db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, last ? 0 : 1, randomize,
                         info, hr);
@@ -160,6 +165,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
           }
           init_res += info[0];
           final_res += info[1];
+          if (pr->aug_rho) db_lm_set_aug(nullptr, nullptr, nullptr, nullptr, 0.0);
         }
         if (hr) db_cluster_hidden(pr, cj, r, -1);
         if (init_res > 0.0) {

@@ -25,7 +25,9 @@ EXPORTED = [
     "dirac_b200_set_comm", "dirac_b200_spd_solve", "dirac_b200_tri_solve",
     "dirac_b200_set_option", "dirac_b200_nccl_unique_id", "dirac_b200_nccl_init",
     "dirac_b200_nccl_finalize", "dirac_b200_nccl_ready", "dirac_b200_comm_stats",
-    "dirac_b200_noise_decisions", "dirac_b200_host_stats",
+    "dirac_b200_noise_decisions", "dirac_b200_host_stats", "dirac_b200_consensus_basis",
+    "dirac_b200_consensus_prod_inverse", "dirac_b200_consensus_step", "dirac_b200_sagefit_admm",
+    "sagefit_visibilities_admm", "sagefit_visibilities_admm_dual_pt_flt",
 ]
 
 

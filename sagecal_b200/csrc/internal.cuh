@@ -403,6 +403,10 @@ size_t db_chol_ws_doubles(int n);
 int db_tri_available(int n);
 void db_chol_set_step(const double *pcur, double *pnew, double *sc, double *zero);
 void db_launch_tri_solve(const double *L, int n, const double *b, double *x, cudaStream_t st);
+void db_launch_tri_solve_ld(const double *L, int ld, int n, const double *b, double *x,
+                            cudaStream_t st);
+void db_launch_chol_factor_batched(const double *A, int n, const double *mu, double *ws,
+                                   long long ws_stride, int *info, int nb, cudaStream_t st);
 void db_launch_chol_solve(const double *A, int n, double mu, const double *b, double *x, double *ws,
                           int *info, cudaStream_t st);
 int db_stream_all_nblocks(int Nbase, int tilesz);

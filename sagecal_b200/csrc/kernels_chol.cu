@@ -49,7 +49,16 @@ struct CholArgs {
   int n, nblk;
   long long *ts;  // optional phase timestamps (globaltimer ns), tuning only
   StepArgs st;
+  // batched factorisation (one thread-block cluster per matrix, blockIdx.x / cluster size = matrix):
+  // A, ws, info advance by the strides below, mu comes from mu_ptr[matrix], no right-hand side, the
+  // kernel returns once the factor stands in the workspace (ld = 32*nblk, identity padding)
+  int factor_only;
+  const double *mu_ptr;
+  long long ws_stride;
 };
+__device__ __forceinline__ double rhs_at(const CholArgs &p, int r) {
+  return (p.b != nullptr && r < p.n) ? p.b[r] : 0.0;
+}
 
 // release/acquire at cluster scope orders the workspace stores (L2) before the other CTAs' .cg loads
 __device__ __forceinline__ void cluster_barrier() {
@@ -349,6 +358,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
   extern __shared__ __align__(16) double sm[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int crank = (int)cluster_rank(), CL = (int)cluster_size();
+  if (p.factor_only) {
+    const int mat = (int)(blockIdx.x / CL);
+    p.A += (size_t)mat * p.n * p.n;
+    p.ws += (size_t)mat * p.ws_stride;
+    p.info += 2 * mat;
+    p.mu = p.mu_ptr[mat];
+    p.b = nullptr;
+  }
   const int G = CL * CH_WARPS;     // warps of the cluster
   const int g = w * CL + crank;    // spread consecutive work items over the SMs first
   const int ld = p.nblk * 32, nblk = p.nblk;
@@ -363,7 +380,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
   int si = 0;
   stamp(p, si);
   if (g == 0 && lane == 0) p.info[0] = p.info[1] = 0;  // [0] factor status, [1] solve status
-  {
+  if (!p.factor_only) {
     // the solution blocks double as their own arrival flags: a NaN pattern no computation produces
     unsigned long long *xs0 = reinterpret_cast<unsigned long long *>(sm + ctrl_off(nblk, CL));
     for (int i = threadIdx.x; i < ld; i += CH_THREADS) xs0[i] = X_PENDING;
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
         stage_block(Bs, ws + (size_t)(j * 32) * ld + j * 32, ld, lane);
         const double myrd = __ldcg(wrd + j * 32 + lane);
         const int r = j * 32 + lane;
-        const double bj = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+        const double bj = (j == 0) ? rhs_at(p, r) : __ldcg(wb + r);
         __syncwarp();
         wy[r] = fwd_block(bj, Bs, myrd, lane);
       }
@@ -432,7 +449,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
         if (w == 1) {
           const int r = J1 * 32 + lane;
           yv = __ldcg(wy + j * 32 + lane);
-          bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+          bI = (j == 0) ? rhs_at(p, r) : __ldcg(wb + r);
         }
         for (int e = threadIdx.x; e < 512; e += CH_THREADS) {
           const int c = e >> 4, r2 = e & 15;
@@ -491,7 +508,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
         // first trailing column: this warp holds row I of L_Ij, so b_I -= L_Ij y_j costs 32 FMAs
         rds[lane] = __ldcg(wy + j * 32 + lane);
         const int r = I * 32 + lane;
-        const double bI = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+        const double bI = (j == 0) ? rhs_at(p, r) : __ldcg(wb + r);
         __syncwarp();
         wb[r] = bI - dot32(a, rds);
       }
@@ -502,6 +519,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
     cluster_barrier();
     stamp(p, si);
   }
+
+  if (p.factor_only) return;  // every CTA leaves behind the same cluster barrier
 
   // ---- inverses of the diagonal blocks (one warp each, all concurrent): they turn the 32-step
   // substitutions of the two triangular solves into 32 x 32 matrix-vector products.
@@ -526,7 +545,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
     stage_block(Bs, ws + (size_t)(j * 32) * ld + j * 32, ld, lane);
     const double myrd = __ldcg(wrd + j * 32 + lane);
     const int r = j * 32 + lane;
-    const double bj = (j == 0) ? (r < p.n ? p.b[r] : 0.0) : __ldcg(wb + r);
+    const double bj = (j == 0) ? rhs_at(p, r) : __ldcg(wb + r);
     __syncwarp();
     wy[r] = fwd_block(bj, Bs, myrd, lane);
   }
@@ -637,7 +656,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) k_chol_solve(CholArgs p) {
 // CTAs and doubles as its own arrival flag.
 // ------------------------------------------------------------------------------------------------
 struct TriArgs {
-  const double *L;  // n x n, lower triangle (column-major, ld = n)
+  int ld;           // leading dimension of L (n for a cuSOLVER factor, 32*nblk for a k_chol_solve one)
+  const double *L;  // n x n, lower triangle (column-major)
   const double *b;
   double *x;
   int n, nblk;
@@ -645,7 +665,7 @@ struct TriArgs {
 };
 
 __device__ __forceinline__ double l_elem(const TriArgs &p, int r, int c) {
-  return (r < p.n && c < p.n) ? __ldg(p.L + (size_t)c * p.n + r) : (r == c ? 1.0 : 0.0);
+  return (r < p.n && c < p.n) ? __ldg(p.L + (size_t)c * p.ld + r) : (r == c ? 1.0 : 0.0);
 }
 
 __device__ __forceinline__ void wait_block(const double *slot, int lane) {
@@ -916,6 +936,7 @@ void db_launch_chol_solve(const double *A, int n, double mu, const double *b, do
   p.ts = g_ts;
   p.st = g_step;
   p.A = A; p.b = b; p.x = x; p.ws = ws; p.info = info; p.mu = mu; p.n = n; p.nblk = (n + 31) / 32;
+  p.factor_only = 0; p.mu_ptr = nullptr; p.ws_stride = 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g_cluster);
   cfg.blockDim = dim3(CH_THREADS);
@@ -932,6 +953,43 @@ void db_launch_chol_solve(const double *A, int n, double mu, const double *b, do
 }
 
 
+// Batched factorisation: nb matrices A[b] (n x n, stride n*n), A[b] + mu[b] I = L L^T, one thread-block
+// cluster each, all concurrent (the batch of first systems of a SAGE sweep: 64 clusters of 16 CTAs on
+// 148 SMs run nine at a time).  Factor b lands at ws + b*ws_stride with ld = 32*ceil(n/32);
+// info[2b] as dpotrf.  Replaces cusolverDnDpotrfBatched on this path.
+void db_launch_chol_factor_batched(const double *A, int n, const double *mu, double *ws,
+                                   long long ws_stride, int *info, int nb, cudaStream_t st) {
+  CholArgs p;
+  p.ts = nullptr;
+  p.st.pcur = nullptr; p.st.pnew = nullptr; p.st.sc = nullptr; p.st.zero = nullptr;
+  p.A = A; p.b = nullptr; p.x = nullptr; p.ws = ws; p.info = info; p.mu = 0.0; p.n = n;
+  p.nblk = (n + 31) / 32;
+  p.factor_only = 1; p.mu_ptr = mu; p.ws_stride = ws_stride;
+  // Throughput, not latency, counts for the batch: small clusters (4 CTAs) keep 37 matrices in flight
+  // on 148 SMs and spend less of their time in cluster barriers than the 16-CTA shape of a lone solve
+  static int bcl = -1;
+  if (bcl < 0) {
+    const char *e = getenv("DIRAC_B200_BATCH_CL");
+    bcl = e ? atoi(e) : 4;
+    if (bcl != 1 && bcl != 2 && bcl != 4 && bcl != 8 && bcl != 16) bcl = 4;
+    if (bcl > g_cluster) bcl = g_cluster;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(bcl * nb));
+  cfg.blockDim = dim3(CH_THREADS);
+  // the factorisation only needs the per-warp staging blocks and the cooperative diagonal block
+  cfg.dynamicSmemBytes = ((size_t)CH_WARPS * (32 * 32 + 32) + 2048) * sizeof(double);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = bcl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  DB_CHECK(cudaLaunchKernelEx(&cfg, k_chol_solve, p));
+}
+
 // L L^T x = b with an existing factor (column-major lower, ld = n <= db_chol_max_n())
 // 1 if the solve-only kernel fits this device's cluster size for n
 int db_tri_available(int n) {
@@ -939,8 +997,15 @@ int db_tri_available(int n) {
   return tri_smem((n + 31) / 32, g_cluster) <= 227 * 1024;
 }
 
+void db_launch_tri_solve_ld(const double *L, int ld, int n, const double *b, double *x,
+                            cudaStream_t st);
 void db_launch_tri_solve(const double *L, int n, const double *b, double *x, cudaStream_t st) {
+  db_launch_tri_solve_ld(L, n, n, b, x, st);
+}
+void db_launch_tri_solve_ld(const double *L, int ld, int n, const double *b, double *x,
+                            cudaStream_t st) {
   TriArgs p;
+  p.ld = ld;
   p.L = L; p.b = b; p.x = x; p.n = n; p.nblk = (n + 31) / 32;
   p.st = g_step;
   static bool configured = false;

@@ -11,48 +11,7 @@
 // kernel is SFU/FP64-ALU bound (three sin/cos per source-row), not HBM bound.
 #include "internal.cuh"
 #include "coh.h"
-
-// ---- mbarrier / bulk-copy helpers (PTX ISA 8.x, sm_90+) ----------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) {
-  return (unsigned)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-// global -> shared, bytes multiple of 16, both 16-byte aligned; completion on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
-                                         unsigned long long *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-          "r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
+#include "tma.cuh"
 
 // ---- per-source term ------------------------------------------------------------------------------
 // phase * |sinc| smearing * shape factor for one source at one frequency (predict.c:411-470)

@@ -290,6 +290,7 @@ void db_launch_assemble_batched(const BatchAssembleArgs *b, int ntile, int nb, d
   dim3 g2((b->N + 63) / 64, nb);
   k_assemble_diag_batched<<<g2, 64, 0, st>>>(b->Hst, b->JTJ, b->N);
   k_batch_mu0<<<nb, 128, 0, st>>>(b->Hst, mu, b->N, tau);
+  if (!Afac) return;  // the cluster Cholesky reads J^T J and mu itself
   const int n = 8 * b->N;
   const long long nn = (long long)n * n;
   dim3 g3((unsigned)((nn + 255) / 256), nb);

@@ -361,24 +361,30 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   const int n = w.n8;
   const size_t nn = (size_t)n * n;
   if ((double)d.M * nn * 16.0 > 24e9) return;  // keep the two batch buffers within 24 GB
+  // own batched factorisation (one 16-CTA cluster per matrix) when the cluster solver takes the size:
+  // the factor of cluster b then lives in a k_chol_solve workspace (ld = 32*ceil(n/32))
+  const bool own_batch = w.own_chol && db_tri_available(n) && !getenv("DIRAC_B200_BATCH_CUSOLVER");
+  const size_t lstride = own_batch ? db_chol_ws_doubles(n) : nn;
+  w.lb_stride = lstride;
+  w.lb_ld = own_batch ? 32 * ((n + 31) / 32) : n;
   if (!w.JB) {
     w.JB = dalloc<double>(nn * d.M);
-    w.LB = dalloc<double>(nn * d.M);
+    w.LB = dalloc<double>(lstride * d.M);
     w.HB = dalloc<double>((size_t)4 * d.N * d.M);
     w.mu_dev = dalloc<double>(d.M);
-    w.binfo_dev = dalloc<int>(d.M);
+    w.binfo_dev = dalloc<int>(2 * d.M);
     w.LBptr_dev = (double **)dalloc<double *>(d.M);
     w.blist_dev = dalloc<int>(d.M);
     w.btix_dev = dalloc<int>(d.M);
     w.bpoff_dev = dalloc<int>(d.M);
     DB_CHECK(cudaMallocHost((void **)&w.h_mu, sizeof(double) * d.M));
-    DB_CHECK(cudaMallocHost((void **)&w.h_binfo, sizeof(int) * d.M));
+    DB_CHECK(cudaMallocHost((void **)&w.h_binfo, sizeof(int) * 2 * d.M));
     std::vector<int> tix(d.M), poff(d.M);
     std::vector<double *> ptr(d.M);
     for (int k = 0; k < d.M; k++) {
       tix[k] = d.h_clus[k].chunk0;
       poff[k] = d.h_chunk_poff[d.h_clus[k].chunk0];
-      ptr[k] = w.LB + nn * k;
+      ptr[k] = w.LB + lstride * k;
     }
     DB_CHECK(cudaMemcpy(w.btix_dev, tix.data(), sizeof(int) * d.M, cudaMemcpyHostToDevice));
     DB_CHECK(cudaMemcpy(w.bpoff_dev, poff.data(), sizeof(int) * d.M, cudaMemcpyHostToDevice));
@@ -424,11 +430,15 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   b.T = w.T; b.pp = d.pp; b.list = w.blist_dev; b.tix = w.btix_dev; b.poff = w.bpoff_dev;
   b.JTJ = w.JB; b.Hst = w.HB; b.tiles = d.tiles; b.blpq = d.blpq; b.N = d.N; b.Nbase = d.Nbase;
   db_prof_begin(4, nb * (128.0 * d.Nbase + 8.0 * 64.0 * d.N * d.N), d.stream);
-  db_launch_assemble_batched(&b, d.ntile, nb, tau, w.mu_dev, w.LB, d.stream);
+  db_launch_assemble_batched(&b, d.ntile, nb, tau, w.mu_dev, own_batch ? nullptr : w.LB, d.stream);
   db_prof_end(d.stream);
   db_count_launch(4);
   db_prof_begin(5, 0.0, d.stream);
-  if (n <= 1024) {
+  if (own_batch) {
+    db_launch_chol_factor_batched(w.JB, n, w.mu_dev, w.LB, (long long)lstride, w.binfo_dev, nb,
+                                  d.stream);
+    db_count_launch(1);
+  } else if (n <= 1024) {
     CS_CHECK(cusolverDnDpotrfBatched(w.cs, CUBLAS_FILL_MODE_LOWER, n, w.LBptr_dev, n, w.binfo_dev, nb));
     db_count_launch(1);
   } else {
@@ -471,8 +481,9 @@ void db_prefactor_sweep(dirac_b200_problem *pr, double tau) {
   }
   db_prof_end(d.stream);
   DB_CHECK(cudaMemcpyAsync(w.h_mu, w.mu_dev, sizeof(double) * nb, cudaMemcpyDeviceToHost, d.stream));
-  DB_CHECK(cudaMemcpyAsync(w.h_binfo, w.binfo_dev, sizeof(int) * nb, cudaMemcpyDeviceToHost,
-                           d.stream));
+  DB_CHECK(cudaMemcpyAsync(w.h_binfo, w.binfo_dev, sizeof(int) * (own_batch ? 2 * nb : nb),
+                           cudaMemcpyDeviceToHost, d.stream));
+  w.binfo_step = own_batch ? 2 : 1;
   db_stream_sync(d.stream);  // list goes out of scope; mu0 is needed on the host
 }
 
@@ -723,18 +734,19 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
           if (w.own_chol && db_tri_available(n)) {
             // no status of its own: the factor's status came back with the batch
             skip_info = true;
-            db_launch_tri_solve(w.LB + (size_t)slot * n * n, n, w.JTe, w.Dp, d.stream);
+            db_launch_tri_solve_ld(w.LB + (size_t)slot * w.lb_stride, w.lb_ld, n, w.JTe, w.Dp,
+                                   d.stream);
             w.step_fused = w.step_armed;
           } else {
             DB_CHECK(cudaMemsetAsync(w.devinfo, 0, 2 * sizeof(int), d.stream));
             DB_CHECK(cudaMemcpyAsync(w.Dp, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToDevice,
                                      d.stream));
             CS_CHECK(cusolverDnDpotrs(w.cs, CUBLAS_FILL_MODE_LOWER, n, 1,
-                                      w.LB + (size_t)slot * n * n, n, w.Dp, n, w.devinfo + 1));
+                                      w.LB + (size_t)slot * w.lb_stride, n, w.Dp, n, w.devinfo + 1));
           }
           db_prof_end(d.stream);
           db_count_launch(1);
-          issolved = (w.h_binfo[slot] == 0) ? 1 : 0;
+          issolved = (w.h_binfo[slot * w.binfo_step] == 0) ? 1 : 0;
         } else {
           issolved = enqueue_solve(pr, mu + half_rho, linsolv, eps1);
         }

@@ -39,6 +39,8 @@ struct LMWork {
   // normal matrices of ALL clusters of a sweep, assembled and factorised in one batch before the
   // sweep (each cluster's first LM solve then only needs the triangular solves)
   double *JB, *LB;        // [M][8N][8N] J^T J and its damped Cholesky factor
+  size_t lb_stride;       // doubles between two factors in LB
+  int lb_ld, binfo_step;  // leading dimension of a factor; ints per matrix in the status array
   double *HB;             // [M][N][4]
   double *mu_dev;         // [M] mu0 of each cluster
   double *h_mu;           // pinned

@@ -127,6 +127,16 @@ int predict_visibilities_multifreq(double *u, double *v, double *w, double *x, i
                                    double *freqs, int Nchan, double fdelta, double tdelta,
                                    double dec0, int Nt, int add_to_data);
 
+/* replaces calculate_residuals_multifreq, src/lib/Radio/Dirac_radio.h:652 (residual.c:940-1061,
+ * residual_threadfn_multifreq :681-938): full-resolution residual, x[chan][row][8] -= sum over the
+ * clusters with id >= 0 of J_p C_k(chan) J_q^H with the coherencies re-predicted from the sources at
+ * every channel, then the correction of every row by the inverse Jones (J + rho I)^-1 of the cluster
+ * whose id is ccid (none if no cluster has that id).  phase_only != 0 is not implemented: returns -1. */
+int calculate_residuals_multifreq(double *u, double *v, double *w, double *p, double *x, int N,
+                                  int Nbase, int tilesz, baseline_t *barr, clus_source_t *carr, int M,
+                                  double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+                                  int Nt, int ccid, double rho, int phase_only);
+
 /* helpers the driver calls directly: src/lib/Dirac/Dirac.h generate_baselines
  * (baseline_utils.c:469), preset_flags_and_data (baseline_utils.c:239).  Bit-exact index work. */
 int generate_baselines(int Nbase, int tilesz, int N, baseline_t *barr, int Nt);

@@ -219,3 +219,114 @@ extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, d
   cudaStreamDestroy(st);
   return 0;
 }
+
+// 2x2 inverse of (J + rho I) with the reference's guard on a small determinant (mat_invert,
+// residual.c:162-199)
+static void jones_invert(const double xx[8], double yy[8], double rho) {
+  const double a0r = xx[0] + rho, a0i = xx[1], a1r = xx[2], a1i = xx[3];
+  const double a2r = xx[4], a2i = xx[5], a3r = xx[6] + rho, a3i = xx[7];
+  double dr = (a0r * a3r - a0i * a3i) - (a1r * a2r - a1i * a2i);
+  double di = (a0r * a3i + a0i * a3r) - (a1r * a2i + a1i * a2r);
+  if (sqrt(sqrt(dr * dr + di * di)) <= rho) dr += rho;
+  const double den = dr * dr + di * di;
+  const double ir = dr / den, ii = -di / den;  // 1/det
+  yy[0] = a3r * ir - a3i * ii;      yy[1] = a3r * ii + a3i * ir;
+  yy[2] = -(a1r * ir - a1i * ii);   yy[3] = -(a1r * ii + a1i * ir);
+  yy[4] = -(a2r * ir - a2i * ii);   yy[5] = -(a2r * ii + a2i * ir);
+  yy[6] = a0r * ir - a0i * ii;      yy[7] = a0r * ii + a0i * ir;
+}
+
+// Dirac_radio.h:652 (residual.c:940-1061): full-resolution residual per channel,
+// x[chan][row][8] -= sum over the clusters with id >= 0 of J_p C_k(chan) J_q^H, the coherencies
+// re-predicted from the sources at every channel frequency; then, if a cluster has id == ccid, every
+// row is corrected by that cluster's inverse Jones (J + rho I)^-1.  phase_only != 0 (correction by the
+// phases of a joint diagonalisation, manifold_average.c) is not implemented: returns -1.
+extern "C" int calculate_residuals_multifreq(double *u, double *v, double *w, double *p, double *x,
+                                             int N, int Nbase, int tilesz, baseline_t *barr,
+                                             clus_source_t *carr, int M, double *freqs, int Nchan,
+                                             double fdelta, double tdelta, double dec0, int Nt,
+                                             int ccid, double rho, int phase_only) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  if (phase_only) {
+    fprintf(stderr, "dirac_b200: calculate_residuals_multifreq: phase_only correction is not "
+                    "implemented\n");
+    return -1;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "dirac_b200: no CUDA device available. This library has no CPU fallback.\n");
+    exit(1);
+  }
+  const long long R = (long long)Nbase * tilesz;
+  cudaStream_t st;
+  DB_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  SkyDev sky;
+  sky_upload(carr, M, &sky, st);
+  double *du = upload_doubles(u, R, st), *dv = upload_doubles(v, R, st);
+  double *dw = upload_doubles(w, R, st), *df = upload_doubles(freqs, Nchan, st);
+  // cluster / chunk tables, stations, solutions
+  std::vector<int> nchunk(M), chunk0(M), poff, s1(R), s2(R);
+  std::vector<unsigned char> sub(M);
+  int mt = 0, cm = -1;
+  long long npar = 0;
+  for (int k = 0; k < M; k++) {
+    nchunk[k] = carr[k].nchunk;
+    chunk0[k] = mt;
+    sub[k] = carr[k].id >= 0 ? 1 : 0;
+    if (carr[k].id == ccid) cm = k;
+    for (int c = 0; c < carr[k].nchunk; c++) {
+      poff.push_back(carr[k].p[c]);
+      if ((long long)carr[k].p[c] + 8ll * N > npar) npar = (long long)carr[k].p[c] + 8ll * N;
+    }
+    mt += carr[k].nchunk;
+  }
+  for (long long r = 0; r < R; r++) {
+    s1[r] = barr[r].sta1;
+    s2[r] = barr[r].sta2;
+  }
+  std::vector<double> pinv;
+  if (cm >= 0) {
+    pinv.resize((size_t)8 * N * carr[cm].nchunk);
+    for (int c = 0; c < carr[cm].nchunk; c++)
+      for (int s = 0; s < N; s++)
+        jones_invert(p + carr[cm].p[c] + 8 * s, pinv.data() + (size_t)8 * N * c + 8 * s, rho);
+  }
+  int *dn = nullptr, *dc0 = nullptr, *dpo = nullptr, *ds1 = nullptr, *ds2 = nullptr;
+  unsigned char *dsub = nullptr;
+  DB_CHECK(cudaMalloc((void **)&dn, sizeof(int) * M));
+  DB_CHECK(cudaMalloc((void **)&dc0, sizeof(int) * M));
+  DB_CHECK(cudaMalloc((void **)&dpo, sizeof(int) * (mt > 0 ? mt : 1)));
+  DB_CHECK(cudaMalloc((void **)&ds1, sizeof(int) * R));
+  DB_CHECK(cudaMalloc((void **)&ds2, sizeof(int) * R));
+  DB_CHECK(cudaMalloc((void **)&dsub, M));
+  DB_CHECK(cudaMemcpyAsync(dn, nchunk.data(), sizeof(int) * M, cudaMemcpyHostToDevice, st));
+  DB_CHECK(cudaMemcpyAsync(dc0, chunk0.data(), sizeof(int) * M, cudaMemcpyHostToDevice, st));
+  DB_CHECK(cudaMemcpyAsync(dpo, poff.data(), sizeof(int) * mt, cudaMemcpyHostToDevice, st));
+  DB_CHECK(cudaMemcpyAsync(ds1, s1.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+  DB_CHECK(cudaMemcpyAsync(ds2, s2.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+  DB_CHECK(cudaMemcpyAsync(dsub, sub.data(), M, cudaMemcpyHostToDevice, st));
+  double *dp = upload_doubles(p, npar, st);
+  double *dpinv = cm >= 0 ? upload_doubles(pinv.data(), (long long)pinv.size(), st) : nullptr;
+  double2 *dx = nullptr;
+  const size_t nx = (size_t)Nchan * R * 4;
+  DB_CHECK(cudaMalloc((void **)&dx, sizeof(double2) * nx));
+  DB_CHECK(cudaMemcpyAsync(dx, x, sizeof(double2) * nx, cudaMemcpyHostToDevice, st));
+  CohArgs a;
+  memset(&a, 0, sizeof(a));
+  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.segs = sky.segs; a.nseg = sky.nseg;
+  a.freqs = df; a.Nchan = Nchan; a.fdelta2 = (fdelta / (double)Nchan) * 0.5;
+  a.R = R; a.xout = dx; a.sta1 = ds1; a.sta2 = ds2; a.p = dp; a.clus_nchunk = dn;
+  a.clus_chunk0 = dc0; a.chunk_poff = dpo; a.clus_sub = dsub; a.pinv = dpinv;
+  a.pinv_nchunk = cm >= 0 ? carr[cm].nchunk : 1; a.N = N;
+  db_launch_residual_multifreq(&a, st);
+  db_count_launch(1);
+  DB_CHECK(cudaMemcpyAsync(x, dx, sizeof(double2) * nx, cudaMemcpyDeviceToHost, st));
+  db_stream_sync(st);
+  DB_CHECK(cudaGetLastError());
+  cudaFree(dx); cudaFree(du); cudaFree(dv); cudaFree(dw); cudaFree(df); cudaFree(dp);
+  if (dpinv) cudaFree(dpinv);
+  cudaFree(dn); cudaFree(dc0); cudaFree(dpo); cudaFree(ds1); cudaFree(ds2); cudaFree(dsub);
+  sky_free(&sky);
+  cudaStreamDestroy(st);
+  return 0;
+}

@@ -74,7 +74,10 @@ __device__ __forceinline__ double spec_flux(double s0, double tempfr) {
 
 #define COH_THREADS 128
 
-// MODE 0: coherencies per cluster at freq[0] -> planar coh ; MODE 1: multifreq sum -> xout
+// MODE 0: coherencies per cluster at freq[0] -> planar coh ; MODE 1: multifreq sum -> xout ;
+// MODE 2: xout -= sum_k J_p C_k J_q^H per channel with the solved Jones (clusters with id >= 0), then
+//         the optional correction x <- Jinv_p x Jinv_q^H by one cluster's inverse Jones
+//         (residual_threadfn_multifreq, residual.c:681-938)
 template <int MODE>
 __global__ void __launch_bounds__(COH_THREADS)
 k_sky_predict(CohArgs a) {
@@ -95,6 +98,11 @@ k_sky_predict(CohArgs a) {
     w = a.w[r];
   }
   const int nchan = (MODE == 0) ? 1 : a.Nchan;
+  int s1 = 0, s2 = 0;
+  if (MODE == 2 && active) {
+    s1 = a.sta1[r];
+    s2 = a.sta2[r];
+  }
   // prologue: stage segment 0
   if (threadIdx.x == 0 && a.nseg > 0) {
     const CohSegment sg = a.segs[0];
@@ -136,7 +144,7 @@ k_sky_predict(CohArgs a) {
           const DevSource &S = sbuf[b][s];
           const double2 ph = source_phase(S, u, v, w, freq, a.fdelta2);
           double I = S.sI, Q = S.sQ, U = S.sU, V = S.sV;
-          if (MODE == 1 && S.spec_idx != 0.0) {
+          if (MODE >= 1 && S.spec_idx != 0.0) {
             const double fr = log(freq / S.f0);
             const double fr1 = fr * fr, fr2 = fr1 * fr;
             const double tf = S.spec_idx * fr + S.spec_idx1 * fr1 + S.spec_idx2 * fr2;
@@ -152,9 +160,21 @@ k_sky_predict(CohArgs a) {
             double2 *ck = a.coh + (long long)sg.cluster * 4 * a.R;
 #pragma unroll
             for (int c = 0; c < 4; c++) st_stream(ck + (long long)c * a.R + r, C[c]);
-          } else {
+          } else if (MODE == 1) {
 #pragma unroll
             for (int c = 0; c < 4; c++) X[c] = cadd(X[c], C[c]);
+          } else if (a.clus_sub[sg.cluster]) {
+            // Jones of this row's hybrid chunk: px = row / ceil(R / nchunk)  (residual.c:717)
+            const int nch = a.clus_nchunk[sg.cluster];
+            const int px = row_chunk(r, a.R, nch);
+            const double *pm = a.p + a.chunk_poff[a.clus_chunk0[sg.cluster] + px];
+            double2 G1[4], G2[4], T1[4], T2[4];
+            load_jones(pm, s1, G1);
+            load_jones(pm, s2, G2);
+            mat_ab(G1, C, T1);
+            mat_abh(T1, G2, T2);
+#pragma unroll
+            for (int c = 0; c < 4; c++) X[c] = csub(X[c], T2[c]);
           }
 #pragma unroll
           for (int c = 0; c < 4; c++) C[c] = make_double2(0.0, 0.0);
@@ -162,10 +182,22 @@ k_sky_predict(CohArgs a) {
       }
       __syncthreads();  // everyone is done with sbuf[b] before it is refilled two iterations on
     }
-    if (MODE == 1 && active) {
+    if (MODE >= 1 && active) {
       double2 *xo = a.xout + ((long long)cf * a.R + r) * 4;
+      double2 V[4];
 #pragma unroll
-      for (int c = 0; c < 4; c++) xo[c] = cadd(xo[c], X[c]);
+      for (int c = 0; c < 4; c++) V[c] = cadd(xo[c], X[c]);
+      if (MODE == 2 && a.pinv) {
+        const int px = row_chunk(r, a.R, a.pinv_nchunk);
+        const double *pm = a.pinv + (size_t)8 * a.N * px;
+        double2 G1[4], G2[4], T1[4];
+        load_jones(pm, s1, G1);
+        load_jones(pm, s2, G2);
+        mat_ab(G1, V, T1);
+        mat_abh(T1, G2, V);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; c++) xo[c] = V[c];
     }
   }
   if (MODE == 0 && active && a.flag) {
@@ -181,6 +213,10 @@ extern "C" {
 void db_launch_coherencies(const CohArgs *a, cudaStream_t st) {
   unsigned grid = (unsigned)((a->R + COH_THREADS - 1) / COH_THREADS);
   k_sky_predict<0><<<grid, COH_THREADS, 0, st>>>(*a);
+}
+void db_launch_residual_multifreq(const CohArgs *a, cudaStream_t st) {
+  unsigned grid = (unsigned)((a->R + COH_THREADS - 1) / COH_THREADS);
+  k_sky_predict<2><<<grid, COH_THREADS, 0, st>>>(*a);
 }
 void db_launch_predict_multifreq(const CohArgs *a, cudaStream_t st) {
   unsigned grid = (unsigned)((a->R + COH_THREADS - 1) / COH_THREADS);

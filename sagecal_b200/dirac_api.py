@@ -180,6 +180,9 @@ class DiracAPI:
         L.predict_visibilities_multifreq.restype = i
         L.predict_visibilities_multifreq.argtypes = [dp, dp, dp, dp, i, i, i, bp, cp, i, dp, i,
                                                      d, d, d, i, i]
+        L.calculate_residuals_multifreq.restype = i
+        L.calculate_residuals_multifreq.argtypes = [dp, dp, dp, dp, dp, i, i, i, bp, cp, i, dp, i,
+                                                    d, d, d, i, i, d, i]
         L.generate_baselines.restype = i
         L.generate_baselines.argtypes = [i, i, i, bp, i]
         L.preset_flags_and_data.restype = i
@@ -212,6 +215,15 @@ class DiracAPI:
         return self.lib.predict_visibilities_multifreq(
             dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M,
             dptr(freqs), len(freqs), fdelta, tdelta, dec0, Nt, add_to_data)
+
+    def calculate_residuals_multifreq(self, u, v, w, p, x, N, Nbase, tilesz, barr, sky: SkyModel,
+                                      freqs, fdelta, tdelta=10.0, dec0=1.0, Nt=4, ccid=-99999,
+                                      rho=1e-9, phase_only=0):
+        """x[chan][row][8]: data in, residual (optionally corrected by cluster `ccid`) out"""
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        return self.lib.calculate_residuals_multifreq(
+            dptr(u), dptr(v), dptr(w), dptr(p), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M,
+            dptr(freqs), len(freqs), fdelta, tdelta, dec0, Nt, ccid, rho, phase_only)
 
     def sagefit_visibilities(self, u, v, w, x, N, Nbase, tilesz, barr, sky: SkyModel, coh, pp,
                              freq0=150e6, fdelta=195.3e3, uvmin=0.0, Nt=4, max_emiter=3,

@@ -159,3 +159,34 @@ def test_predict_multifreq(api, ref, add):
     api.predict_visibilities_multifreq(pr.u, pr.v, pr.w, xb, pr.N, pr.Nbase, pr.tilesz, b.barr, sky,
                                        freqs, pr.fdelta * 3, add_to_data=add)
     assert relerr(xb, xa) < 1e-11
+
+
+@pytest.mark.parametrize("ccid,nchunk", [(-99999, None), (1, None), (2, [1, 2, 3])],
+                         ids=["no-correction", "correct-by-1", "hybrid-correct-by-2"])
+def test_calculate_residuals_multifreq(api, ref, ccid, nchunk):
+    """full-resolution residual with the solved Jones and the optional correction by one cluster's
+    inverse Jones against the compiled reference (residual.c:940-1061)"""
+    from util import perturbed_jones
+    b = small_problem(N=9, M=3, tilesz=6, seed=23, kmean=2.0, gaussian_frac=0.3, nchunk=nchunk)
+    pr = b.pr
+    for k, cl in enumerate(pr.clusters):
+        K = len(cl["ll"])
+        cl["spec_idx"] = np.where(np.arange(K) % 2 == 0, -0.7, 0.0)
+        cl["spec_idx1"] = np.full(K, 0.05)
+        cl["spec_idx2"] = np.full(K, -0.01)
+        cl["f0"] = np.full(K, 140e6)
+        cl["id"] = k if k != 0 else -1          # a negative id: predicted but not subtracted
+    from sagecal_b200.dirac_api import SkyModel
+    sky = SkyModel(pr.clusters, pr.N)
+    freqs = np.array([146e6, 150e6, 154e6, 158e6])
+    rng = np.random.default_rng(4)
+    x0 = rng.normal(0, 1, 8 * pr.Nbase1 * len(freqs))
+    pp = perturbed_jones(pr, amp=0.2)
+    xa, xb = x0.copy(), x0.copy()
+    ra = ref.calculate_residuals_multifreq(pr.u, pr.v, pr.w, pp.copy(), xa, pr.N, pr.Nbase, pr.tilesz,
+                                           b.fresh_barr(), sky, freqs, pr.fdelta * 4, ccid=ccid, rho=1e-9)
+    rb = api.calculate_residuals_multifreq(pr.u, pr.v, pr.w, pp.copy(), xb, pr.N, pr.Nbase, pr.tilesz,
+                                           b.fresh_barr(), sky, freqs, pr.fdelta * 4, ccid=ccid, rho=1e-9)
+    assert ra == rb == 0
+    assert relerr(xb, xa) < 1e-11
+    assert relerr(xa, x0) > 1e-3   # something was subtracted

@@ -292,6 +292,82 @@ double orc_normal_eq(const orc_problem *P, int k, int t0, int ntiles, const doub
   return cost;
 }
 
+/* ---- normal equations of ONE ordered subset with the reference's own pairing -------------------
+ * oslevmar / osrlevmar (Dirac/clmfit.c:1313-1413, robustlm.c:2835-2935) split the n data of a chunk
+ * into Nsubsets pieces of Npersubset = ceil(n/Nsubsets) reals AND its tiles into pieces of
+ * Ntpersubset = ceil(ntiles/Nsubsets) tiles.  Subset l gets the Jacobian of ITS TILES, cut (or
+ * zero padded: jacf memsets Nos[l] rows first, lmfit.c:524) to Nos[l] rows, the residual slice
+ * ed[edI[l] .. edI[l]+Nos[l]) and, in the robust variant, the weights wtd[edI[l] + row].  The two
+ * offsets coincide only when ntiles is a multiple of Nsubsets (or < 10); otherwise row i of J meets
+ * the residual / weight of data index edI[l] + i, which belongs to another tile, baseline and even
+ * polarisation component.  Reproduced literally.
+ * e_full: the chunk's residual as the LM holds it (weighted in the robust variant), wt: the chunk's
+ * sqrt-weights or NULL. */
+void orc_normal_eq_os(const orc_problem *P, int k, int t0, int ntiles, const double *pblk,
+                      const double *e_full, const double *wt, int l, double *JTJ, double *JTe) {
+  const int N = P->N, n8 = 8 * N;
+  const long n = 8l * ntiles * P->Nbase;
+  int Nsubsets = 10;
+  if (ntiles < Nsubsets) Nsubsets = ntiles;
+  const long Nper = (n + Nsubsets - 1) / Nsubsets;
+  const int Ntper = (ntiles + Nsubsets - 1) / Nsubsets;
+  const long kl = (long)l * Nper;
+  const int tl = l * Ntper;
+  long Nos;
+  int tileI;
+  if (tl + Ntper < ntiles) {
+    Nos = Nper;
+    tileI = Ntper;
+  } else {
+    Nos = n - kl;
+    tileI = ntiles - tl;
+  }
+  memset(JTJ, 0, sizeof(double) * n8 * n8);
+  memset(JTe, 0, sizeof(double) * n8);
+  long nJ = (tileI > 0) ? 8l * P->Nbase * tileI : 0;
+  if (Nos < nJ) nJ = Nos;
+  for (long i0 = 0; i0 < nJ; i0 += 8) {
+    const long r = (long)(t0 + tl) * P->Nbase + i0 / 8;
+    if (P->flag[r]) continue; /* Jacobian rows of flagged data are zero */
+    cplx G1[4], G2[4], T2[4], E[4];
+    const int s1 = P->sta1[r], s2 = P->sta2[r];
+    const cplx *C = P->coh + 4 * ((size_t)P->M * r + k);
+    jones_of(pblk, s1, G1);
+    jones_of(pblk, s2, G2);
+    double A[8][16];
+    for (int stoff = 0; stoff < 8; stoff++) {
+      memset(E, 0, sizeof(E));
+      E[stoff / 2] = (stoff & 1) ? _Complex_I : 1.0;
+      model_row(E, C, G2, T2);
+      for (int c = 0; c < 4; c++) {
+        A[2 * c][stoff] = creal(T2[c]);
+        A[2 * c + 1][stoff] = cimag(T2[c]);
+      }
+      model_row(G1, C, E, T2);
+      for (int c = 0; c < 4; c++) {
+        A[2 * c][8 + stoff] = creal(T2[c]);
+        A[2 * c + 1][8 + stoff] = cimag(T2[c]);
+      }
+    }
+    int col[16];
+    for (int a = 0; a < 8; a++) {
+      col[a] = 8 * s1 + a;
+      col[8 + a] = 8 * s2 + a;
+    }
+    const int nc = (nJ - i0 < 8) ? (int)(nJ - i0) : 8; /* the cut may fall inside a row */
+    for (int c = 0; c < nc; c++) {
+      const long g = kl + i0 + c; /* the data index this Jacobian row is paired with */
+      const double w = wt ? wt[g] : 1.0;
+      const double eg = e_full[g];
+      for (int a = 0; a < 16; a++) {
+        const double ja = w * A[c][a];
+        JTe[col[a]] += ja * eg;
+        for (int b = 0; b < 16; b++) JTJ[(size_t)col[a] * n8 + col[b]] += ja * (w * A[c][b]);
+      }
+    }
+  }
+}
+
 /* ---- dense symmetric solvers ------------------------------------------------------------------ */
 /* Cholesky A = L L^T in place (lower), returns 0 or the failing pivot index+1 (dpotrf) */
 static int chol_factor(double *A, int n) {
@@ -375,20 +451,6 @@ static double chunk_residual(const orc_problem *P, int k, int t0, int ntiles, co
   return nrm2sq(e, n);
 }
 
-/* OS subset l of the tile range: tiles [*s0, *s0+*sn)  (Dirac/clmfit.c:1313-1356) */
-static void os_subset(int ntiles, int l, int *Nsubsets_out, int *s0, int *sn) {
-  int Nsubsets = 10;
-  if (ntiles < Nsubsets) Nsubsets = ntiles;
-  int Ntper = (ntiles + Nsubsets - 1) / Nsubsets;
-  int a = l * Ntper;
-  int b = (a + Ntper < ntiles) ? Ntper : ntiles - a;
-  if (b < 0) b = 0;
-  if (a > ntiles) a = ntiles;
-  *Nsubsets_out = Nsubsets;
-  *s0 = a;
-  *sn = b;
-}
-
 /* ---- the LM core shared by clevmar / oslevmar / rlevmar / osrlevmar -----------------------------
  * One call = the "iteration loop" of Dirac/clmfit.c:241-540 (os=0) or :1281-1640 (os=1) with
  * optional sqrt-weights wt (Dirac/robustlm.c:2233-2420).  State that the robust driver carries
@@ -439,11 +501,13 @@ static void lm_core(const orc_problem *P, int k, int t0, int ntiles, double *p, 
     }
     for (int ositer = 0; ositer < max_os_iter; ositer++) {
       if (os) {
+        /* subset l with the reference's pairing of Jacobian rows, residual and weights; e_last is
+         * the residual of the last function evaluation, i.e. at p here (every exit of the damping
+         * loop that continues the iteration is an accepted step) */
         int l = (os_shift + kiter + ositer) % Nsubsets;
-        os_subset(ntiles, l, &Nsubsets, &s0, &sn);
-      }
-      /* J^T J and J^T e on the (sub)set; e is the current (weighted) residual */
-      {
+        orc_normal_eq_os(P, k, t0, ntiles, p, e_last, wt, l, JTJ0, JTe);
+      } else {
+        /* J^T J and J^T e; e is the current (weighted) residual */
         const long off = 8l * s0 * P->Nbase;
         orc_normal_eq(P, k, t0 + s0, sn, p, xd + off, wt ? wt + off : NULL, JTJ0, JTe);
       }

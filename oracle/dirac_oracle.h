@@ -35,6 +35,8 @@ void orc_grad(const orc_problem *P, const double *pp, const double *x, double *g
               double nu);
 double orc_normal_eq(const orc_problem *P, int k, int t0, int ntiles, const double *pblk,
                      const double *xd, const double *wt, double *JTJ, double *JTe);
+void orc_normal_eq_os(const orc_problem *P, int k, int t0, int ntiles, const double *pblk,
+                      const double *e_full, const double *wt, int l, double *JTJ, double *JTe);
 int orc_lm_chunk(const orc_problem *P, int k, int t0, int ntiles, double *pblk, const double *xd,
                  int itmax, const double *opts, int linsolv, int os, double *info);
 int orc_rlm_chunk(const orc_problem *P, int k, int t0, int ntiles, double *pblk, const double *xd,

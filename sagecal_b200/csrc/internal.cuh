@@ -261,7 +261,8 @@ struct ClusterPassArgs {
   long long R;
   int N, Nbase;
   int t_begin, t_end, tslice;  // timeslots per CTA slice
-  int mode;  // 0: INIT  d = in + m -> out ; e = d - m
+  int mode;  // 4: GIVEN e = in (no model subtracted): J^T (wt^2 . in) of a caller-formed residual
+             // 0: INIT  d = in + m -> out ; e = d - m
              // 1: TRIAL e = in - m -> out
              // 2: ADD   out = in + m          (no cost / jte)
              // 3: SUB   out = in - m          (no cost / jte)
@@ -369,7 +370,7 @@ struct BatchAssembleArgs {
 };
 
 // test / tuning options (dirac_b200_set_option): 0 = default
-enum { DB_OPT_CP_ROWS = 0, DB_OPT_LINE_DIRECT = 1, DB_OPT_COUNT = 8 };
+enum { DB_OPT_CP_ROWS = 0, DB_OPT_LINE_DIRECT = 1, DB_OPT_OS_CONSISTENT = 2, DB_OPT_COUNT = 8 };
 int db_opt(int id);
 int db_sm_count();  // SMs of the current device
 // slices of the time axis the linear-mapped gradient pass may use (sizes LMWork::jte_part)

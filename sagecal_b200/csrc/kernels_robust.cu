@@ -275,7 +275,52 @@ k_scale_vis(double2 *__restrict__ v, RowRange g, double alpha, int set_const) {
   }
 }
 
+// Misaligned ordered subset (clmfit.c:1313-1413): row i = 8*rho + comp of the subset's Jacobian is paired
+// with the chunk's data index kl + i.  eps / wout over the subset's rows rho (planar, absolute rows
+// row_sub0 + rho): the residual and the sqrt-weight found at that index, zero beyond the cut nJ.
+__global__ void __launch_bounds__(256)
+k_os_shift(const double2 *__restrict__ e, const double2 *__restrict__ wt, double2 *__restrict__ eps,
+           double2 *__restrict__ wout, long long R, long long row_sub0, long long nrow_sub,
+           long long row_chunk0, long long kl, long long nJ) {
+  const long long tot = 4 * nrow_sub;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < tot;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long rho = t >> 2;
+    const int c4 = (int)(t & 3);
+    double ev[2], wv[2];
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+      const long long i = 8 * rho + 2 * c4 + cc;
+      if (i < nJ) {
+        const long long g = kl + i;
+        const long long srow = row_chunk0 + (g >> 3);
+        const int sc = (int)(g & 7);
+        const double2 se = e[(long long)(sc >> 1) * R + srow];
+        ev[cc] = (sc & 1) ? se.y : se.x;
+        if (wt) {
+          const double2 sw = wt[(long long)(sc >> 1) * R + srow];
+          wv[cc] = (sc & 1) ? sw.y : sw.x;
+        } else {
+          wv[cc] = 1.0;
+        }
+      } else {
+        ev[cc] = 0.0;
+        wv[cc] = 0.0;
+      }
+    }
+    eps[(long long)c4 * R + row_sub0 + rho] = make_double2(ev[0], ev[1]);
+    wout[(long long)c4 * R + row_sub0 + rho] = make_double2(wv[0], wv[1]);
+  }
+}
+
 extern "C" {
+void db_launch_os_shift(const double2 *e, const double2 *wt, double2 *eps, double2 *wout, long long R,
+                        long long row_sub0, long long nrow_sub, long long row_chunk0, long long kl,
+                        long long nJ, cudaStream_t st) {
+  long long tot = 4 * nrow_sub;
+  int grid = (int)((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184);
+  k_os_shift<<<grid, 256, 0, st>>>(e, wt, eps, wout, R, row_sub0, nrow_sub, row_chunk0, kl, nJ);
+}
 void db_launch_weighted_jtj(const WeightedJtjArgs *a, int ntile, cudaStream_t st) {
   const int nt = a->t_end - a->t_begin;
   dim3 grid(ntile, (nt + a->tslice - 1) / a->tslice);

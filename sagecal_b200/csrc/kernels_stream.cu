@@ -861,7 +861,7 @@ k_cluster_pass_split(ClusterPassArgs a) {
       } else {
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-          e[j] = csub(v[j], m[j]);
+          e[j] = (a.mode == 4) ? v[j] : csub(v[j], m[j]);  // mode 4: the residual is given
           if (a.write_out) st_stream(a.out + (j ? c1 : c0) + row, e[j]);
         }
       }
@@ -1344,6 +1344,10 @@ void db_launch_cluster_pass(const ClusterPassArgs *a, int ntile, cudaStream_t st
     }
     dim3 glin(nbg, (nt + b.tslice - 1) / b.tslice);
     k_cluster_pass_lin<NST, false><<<glin, 512, smem, st>>>(b);
+    return;
+  }
+  if (a->jte != nullptr && a->mode == 4) {
+    k_cluster_pass_split<<<grid, 2 * TILE_THREADS, 0, st>>>(*a);
     return;
   }
   if (a->jte != nullptr && a->mode <= 1) {

@@ -50,6 +50,9 @@ void db_launch_assemble_batched(const BatchAssembleArgs *b, int ntile, int nb, d
                                 double *mu, double *Afac, cudaStream_t st);
 void db_launch_lm_step(const double *p, const double *Dp, const double *jte, double *pnew,
                        double *sc, double *zero, int n, cudaStream_t st);
+void db_launch_os_shift(const double2 *e, const double2 *wt, double2 *eps, double2 *wout, long long R,
+                        long long row_sub0, long long nrow_sub, long long row_chunk0, long long kl,
+                        long long nJ, cudaStream_t st);
 }
 
 template <typename T>
@@ -79,6 +82,7 @@ void db_lm_init(dirac_b200_problem *pr) {
   w.tau = dalloc<double>(n8);
   w.svdS = w.svdU = w.svdVT = nullptr;
   w.wbuf = w.ebuf = nullptr;
+  w.os_eps = w.os_w = nullptr;
   w.HP = w.HQ = nullptr;
   w.JB = w.LB = nullptr;
   w.pref_slot = (int *)malloc(sizeof(int) * d.M);
@@ -133,6 +137,14 @@ static void robust_init(dirac_b200_problem *pr) {
   w.HQ = dalloc<double>((size_t)d.N * 20);
 }
 
+static void os_init(dirac_b200_problem *pr) {
+  robust_init(pr);
+  LMWork &w = pr->lm;
+  if (w.os_eps) return;
+  w.os_eps = dalloc<double2>((size_t)4 * pr->d.R);
+  w.os_w = dalloc<double2>((size_t)4 * pr->d.R);
+}
+
 void db_lm_free(dirac_b200_problem *pr) {
   LMWork &w = pr->lm;
   if (!w.ready) return;
@@ -141,6 +153,7 @@ void db_lm_free(dirac_b200_problem *pr) {
   db_free(w.tau); db_free(w.cswork); db_free(w.dbuf);
   if (w.svdS) { db_free(w.svdS); db_free(w.svdU); db_free(w.svdVT); }
   if (w.wbuf) { db_free(w.wbuf); db_free(w.ebuf); db_free(w.HP); db_free(w.HQ); }
+  if (w.os_eps) { db_free(w.os_eps); db_free(w.os_w); }
   if (w.JB) {
     db_free(w.JB); db_free(w.LB); db_free(w.HB); db_free(w.mu_dev); db_free(w.binfo_dev);
     db_free(w.LBptr_dev); db_free(w.blist_dev); db_free(w.btix_dev); db_free(w.bpoff_dev);
@@ -180,7 +193,8 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
                      const double *pblk_old) {
   DevProblem &d = pr->d;
   if (t1 <= t0) {
-    if (mode <= 1) DB_CHECK(cudaMemsetAsync(d.scal + cost_slot, 0, sizeof(double), d.stream));
+    if (mode <= 1 || mode == 4)
+      DB_CHECK(cudaMemsetAsync(d.scal + cost_slot, 0, sizeof(double), d.stream));
     if (jte_dev) DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
     return;
   }
@@ -193,11 +207,12 @@ void db_cluster_pass(dirac_b200_problem *pr, int k, const double *pblk_dev, cons
   a.mode = mode; a.write_out = write_out; a.wt = wt; a.beta = beta; a.in2 = in2;
   a.pblk_old = pblk_old;
   // passes without the gradient accumulator fit two CTAs per SM: twice as many, half as long
-  if (!(jte_dev && mode <= 1) && g_tslice_override <= 0 && a.tslice > 1) a.tslice = (a.tslice + 1) / 2;
-  if (jte_dev && mode <= 1 && !jte_zeroed)
+  if (!(jte_dev && (mode <= 1 || mode == 4)) && g_tslice_override <= 0 && a.tslice > 1)
+    a.tslice = (a.tslice + 1) / 2;
+  if (jte_dev && (mode <= 1 || mode == 4) && !jte_zeroed)
     DB_CHECK(cudaMemsetAsync(jte_dev, 0, sizeof(double) * 8 * d.N, d.stream));
   // kind 2: gradient-carrying passes (INIT, TRIAL); kind 8: ADD / SUB / cost-only passes
-  db_prof_begin((jte_dev && mode <= 1) ? 2 : 8, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
+  db_prof_begin((jte_dev && (mode <= 1 || mode == 4)) ? 2 : 8, (double)(t1 - t0) * d.Nbase * (129.0 + (write_out ? 64.0 : 0.0) +
                                                  (wt ? 64.0 : 0.0)), d.stream);
   db_launch_cluster_pass(&a, d.ntile, d.stream);
   db_prof_end(d.stream);
@@ -615,6 +630,9 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   if (ntiles < Nsubsets) Nsubsets = ntiles;
   const int max_os_iter = os ? (int)ceil(0.1 * (double)Nsubsets) : 1;
   const int Ntper = (os && Nsubsets > 0) ? (ntiles + Nsubsets - 1) / Nsubsets : ntiles;
+  // subsets of tiles and of data coincide only when the tile count is a multiple of the subset count
+  const bool os_misaligned = os && Nsubsets > 0 && (ntiles % Nsubsets) != 0 &&
+                             !db_opt(DB_OPT_OS_CONSISTENT);
 
   // Gram tensor of this chunk (time-invariant part of the unweighted J^T J), built once
   const int tix = d.h_clus[k].chunk0 + ck;
@@ -647,8 +665,46 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
         s0 = t0 + l * Ntper;
         s1 = (l * Ntper + Ntper < ntiles) ? s0 + Ntper : t1;
         if (s0 > t1) s0 = t1;
-        // J^T e restricted to the subset; e is the current (weighted) residual d - f(p)
-        db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, w.JTe, 2, s0, s1, wt);
+        if (!os_misaligned) {
+          // J^T e restricted to the subset; e is the current (weighted) residual d - f(p)
+          db_cluster_pass(pr, k, pblk_dev, w.dbuf, nullptr, 1, 0, w.JTe, 2, s0, s1, wt);
+        } else {
+          // The reference pairs row i of the subset's Jacobian with the residual (and weight) of data
+          // index edI[l] + i, Npersubset = ceil(n/Nsubsets) apart, while the subset's tiles are
+          // Ntpersubset = ceil(ntiles/Nsubsets) apart (clmfit.c:1313-1356,1400; robustlm.c:2835-2935):
+          // when ntiles is not a multiple of Nsubsets that is another tile, baseline and component, and
+          // the Jacobian is cut (or zero padded) to Nos[l] rows.  Reproduced literally: the residual of
+          // the whole chunk at p, gathered with the reference's offset into the subset's rows, enters the
+          // J^T e pass as a given vector; the cut and the weights enter as per-component sqrt-weights.
+          const long long nn = 8ll * ntiles * d.Nbase;
+          const long long Nper = (nn + Nsubsets - 1) / Nsubsets;
+          const long long kl = (long long)l * Nper;
+          const int tl = l * Ntper;
+          long long Nos;
+          int tileI;
+          if (tl + Ntper < ntiles) {
+            Nos = Nper;
+            tileI = Ntper;
+          } else {
+            Nos = nn - kl;
+            tileI = ntiles - tl;
+          }
+          long long nJ = tileI > 0 ? 8ll * d.Nbase * tileI : 0;
+          if (Nos < nJ) nJ = Nos;
+          if (nJ < 0) nJ = 0;
+          s0 = t0 + tl;
+          s1 = s0 + (tileI > 0 ? tileI : 0);
+          if (s0 > t1) s0 = s1 = t1;
+          os_init(pr);
+          // residual of the whole chunk at p (unweighted), then the shifted gather
+          db_cluster_pass(pr, k, pblk_dev, w.dbuf, w.ebuf, 1, 1, nullptr, 2, t0, t1, nullptr);
+          if (s1 > s0) {
+            db_launch_os_shift(w.ebuf, wt, w.os_eps, w.os_w, d.R, (long long)s0 * d.Nbase,
+                               (long long)(s1 - s0) * d.Nbase, (long long)t0 * d.Nbase, kl, nJ, d.stream);
+            db_count_launch(1);
+          }
+          db_cluster_pass(pr, k, pblk_dev, w.os_eps, nullptr, 4, 0, w.JTe, 2, s0, s1, w.os_w);
+        }
         DB_CHECK(cudaMemcpyAsync(hjte, w.JTe, sizeof(double) * n, cudaMemcpyDeviceToHost,
                                  d.stream));
       }
@@ -660,8 +716,9 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       w.jtj0_cur = prefac ? w.JB + (size_t)slot * n * n : nullptr;
       if (prefac) {
         w.pref_slot[k] = -1;  // valid for this visit only
-      } else if (wt) {
-        weighted_jtj(pr, k, s0, s1, pblk_dev, wt, w.JTJ0);
+      } else if (wt || os_misaligned) {
+        // (misaligned ordered subset: the cut of the Jacobian and the shifted weights are in os_w)
+        weighted_jtj(pr, k, s0, s1, pblk_dev, os_misaligned ? w.os_w : wt, w.JTJ0);
         if (need_mx) {
           db_launch_extract_diag(w.JTJ0, w.JTe_new, n, d.stream);  // JTe_new is free scratch here
           db_count_launch(1);
@@ -687,7 +744,7 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
       }
       if (need_mx || os) db_stream_sync(d.stream);
       if (need_mx) {
-        if (wt) {
+        if (wt || os_misaligned) {
           for (int i = 0; i < n; i++)
             if (fabs(hsc[i]) > fabs(mx)) mx = hsc[i];
         } else {

@@ -75,6 +75,7 @@ int db_opt(int id) { return (id >= 0 && id < DB_OPT_COUNT) ? g_opt[id] : 0; }
 extern "C" int dirac_b200_set_option(const char *name, int value) {
   if (!strcmp(name, "cp_rows")) { g_opt[DB_OPT_CP_ROWS] = value; return 0; }
   if (!strcmp(name, "line_direct")) { g_opt[DB_OPT_LINE_DIRECT] = value; return 0; }
+  if (!strcmp(name, "os_consistent")) { g_opt[DB_OPT_OS_CONSISTENT] = value; return 0; }
   return -1;
 }
 // SMs of the current device (grids of the one-wave kernels are sized from it)

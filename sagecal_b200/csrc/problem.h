@@ -33,6 +33,7 @@ struct LMWork {
   // robust LM (allocated on first use)
   double2 *wbuf;          // [4][R] sqrt-weights
   double2 *ebuf;          // [4][R] unweighted residual for the weight update
+  double2 *os_eps, *os_w; // [4][R] misaligned ordered subsets: shifted residual / sqrt-weights + cut
   double *HP, *HQ;        // [N][2][10] station sums of the weighted normal matrix
   double *plast;          // [8N] device copy of the last evaluated trial point
   double *pold;           // [8N] Jones at the start of the visit (sharded closing pass)

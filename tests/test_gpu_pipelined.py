@@ -122,7 +122,9 @@ def test_many_clusters_predict_cost_grad(api, ref):
 HYBRID_UNEVEN = [
     # nchunk does not divide tilesz: hidden data / residual with the row-based chunk map
     ("lm-uneven", dict(N=10, M=3, tilesz=10, seed=91, nchunk=[3, 1, 4]), dict(solver_mode=1, max_iter=3)),
-    ("lm-uneven2", dict(N=12, M=4, tilesz=7, seed=92, nchunk=[2, 3, 1, 5]), dict(solver_mode=1, max_iter=2)),
+    # (every chunk keeps at least one timeslot: the reference callocs 0 bytes for an empty chunk and exits on
+    # allocators that return NULL for that)
+    ("lm-uneven2", dict(N=12, M=4, tilesz=7, seed=92, nchunk=[2, 3, 1, 4]), dict(solver_mode=1, max_iter=2)),
     ("rlm-uneven", dict(N=9, M=2, tilesz=10, seed=93, nchunk=[3, 1], outliers=0.02),
      dict(solver_mode=2, max_iter=2)),
 ]
@@ -152,7 +154,12 @@ def test_rtr_modes_are_mapped_not_fatal(api):
                                      b.sky, pr.coh, pp, max_emiter=2, max_iter=2, max_lbfgs=4,
                                      solver_mode=mode)
         res[mode] = (r, pp)
-    assert np.array_equal(res[5][1], res[3][1]) and np.array_equal(res[4][1], res[0][1])
+    # 4 -> 0 (OS-LM + LBFGS): the same solve again, up to the order of the atomic station sums
+    assert relerr(res[4][1], res[0][1]) < 1e-9
+    # 5 -> 3 (OS robust LM + robust LBFGS): rounding-level LM decisions (see the osrlm golden) let two
+    # runs of mode 3 itself differ, so only the outcome is compared
+    assert res[5][0][0] == res[3][0][0] == 0
+    assert abs(res[5][0][3] - res[3][0][3]) <= 0.05 * res[3][0][3]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -199,3 +206,31 @@ def test_reduced_c2_matches_reference_golden(api, name):
     assert err < JONES_TOL, (name, err)
     xfp = np.array([np.sum(x), np.sum(np.abs(x)), np.max(np.abs(x))])
     assert np.allclose(xfp[1:], g["out_x_fp"][1:], rtol=1e-5)
+
+
+OS_MISALIGNED = [
+    # tile counts that are not a multiple of the 10 ordered subsets (and not < 10): the reference's own
+    # pairing of Jacobian rows with residuals of other tiles (clmfit.c:1313-1413), reproduced
+    ("oslm-12", dict(N=9, M=2, tilesz=12, seed=101), dict(solver_mode=0, max_iter=3)),
+    ("oslm-15", dict(N=10, M=3, tilesz=15, seed=102, kmean=1.0), dict(solver_mode=0, max_iter=4)),
+    ("oslm-25", dict(N=8, M=2, tilesz=25, seed=103, flag_frac=0.1), dict(solver_mode=0, max_iter=3)),
+    # hybrid: 30 timeslots in 2 chunks of 15 tiles
+    ("oslm-hybrid-15", dict(N=9, M=2, tilesz=30, seed=104, nchunk=[2, 1]), dict(solver_mode=0, max_iter=3)),
+    ("osrlm-15", dict(N=8, M=2, tilesz=15, seed=105, outliers=0.02), dict(solver_mode=3, max_iter=3)),
+]
+
+
+@pytest.mark.parametrize("name,prob,args", OS_MISALIGNED, ids=[c[0] for c in OS_MISALIGNED])
+def test_os_lm_with_the_reference_subset_pairing(api, ref, name, prob, args):
+    b = small_problem(**prob)
+    kw = dict(max_emiter=3, max_lbfgs=4, lbfgs_m=5, randomize=0)
+    kw.update(args)
+    api.noise_decisions(reset=True)
+    (rr, xr, ppr), (rg, xg, ppg) = run_both(api, ref, b, **kw)
+    assert rr[0] == rg[0]
+    assert abs(rr[2] - rg[2]) <= 1e-10 * rr[2]
+    err = relerr(ppg, ppr)
+    if err >= JONES_TOL and api.noise_decisions() > 0:
+        pytest.xfail("rounding-level LM decision took another branch than the reference (%.1e)" % err)
+    assert err < JONES_TOL, (name, err)
+    assert abs(rr[3] - rg[3]) <= 1e-5 * rr[3]

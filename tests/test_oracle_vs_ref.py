@@ -199,3 +199,26 @@ def test_coherencies_and_multifreq(ref):
                                            sky, freqs, pr.fdelta * 3, add_to_data=add)
         osky.predict_multifreq(pr.u, pr.v, pr.w, freqs, pr.fdelta * 3, add, xb)
         assert relerr(xb, xa) < 1e-13
+
+
+@pytest.mark.parametrize("T", [12, 15, 25, 33])
+@pytest.mark.parametrize("robust", [False, True], ids=["oslm", "osrlm"])
+def test_os_subsets_with_the_reference_pairing(ref, T, robust):
+    """tile counts that are not a multiple of the 10 ordered subsets: the reference pairs Jacobian rows
+    with residuals / weights of other tiles and cuts the Jacobian (clmfit.c:1313-1413,
+    robustlm.c:2835-2935); the restatement reproduces that literally"""
+    b = small_problem(N=8, M=2, tilesz=T, seed=40 + T, outliers=0.02 if robust else 0.0)
+    pr = b.pr
+    orc = orcdirac.Oracle(pr)
+    k, n8 = 0, 8 * pr.N
+    pp = pr.pp0.copy()
+    xd = pr.x - orc.predict_full(pp) + orc.predict_cluster(k, pp)
+    md = ref.me_data(pr.N, pr.Nbase, pr.tilesz, b.barr, b.sky, pr.coh, clus=k, robust_nu=2.0)
+    if robust:
+        pw, iw, nuw = ref.rlevmar(pp[:n8], xd, md, 3, os_=True)
+        pg, ig, nug = orc.rlm_chunk(k, 0, pr.tilesz, pp[:n8], xd, 3, os_=True, nu0=2.0)
+        assert nug == nuw
+    else:
+        pw, iw = ref.clevmar(pp[:n8], xd, md, 3, os_=True)
+        pg, ig = orc.lm_chunk(k, 0, pr.tilesz, pp[:n8], xd, 3, os_=True)
+    assert relerr(pg, pw) < 1e-9

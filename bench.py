@@ -263,6 +263,18 @@ def cpu_stage_timings(seed):
         t_cost = timed(lambda: ref.cost(pp, pr.x, md), 3)
         t_grad = timed(lambda: ref.grad(pp, pr.x, md), 1)
         t_lm = timed(lambda: ref.clevmar(pp[:8 * pr.N], pr.x, md0, 1), 1)
+        if nth == cores:
+            # C4 on the CPU is feasible for P1 only, at tilesz = 2 (512 stations, 8 clusters)
+            try:
+                p4 = synth.make_problem(N=512, M=8, tilesz=2, radius=75e3, seed=seed + 1, kmean=1.0)
+                b4 = make_barr(p4.sta1, p4.sta2, p4.flag)
+                s4 = SkyModel(p4.clusters, p4.N)
+                md4 = ref.me_data(p4.N, p4.Nbase, p4.tilesz, b4, s4, p4.coh, Nt=cores)
+                t4 = timed(lambda: ref.predict_full(p4.jones_true, md4, 8 * p4.Nbase1), 3)
+                out["C4_P1_full_predict_tilesz2"] = {"shape": "N=512, M=8, tilesz=2 (%d rows)" % p4.Nbase1,
+                                                     "seconds": t4, "value": p4.Nbase1 * p4.M / t4}
+            except Exception as e:
+                out["C4_P1_full_predict_tilesz2"] = {"error": repr(e)}
         out[label] = {
             "P1_full_predict": {"seconds": t_p1, "value": rows * pr.M / t_p1},
             "cost_plus_grad": {"seconds": t_cost + t_grad, "value": rows * pr.M / (t_cost + t_grad)},
@@ -294,7 +306,7 @@ def run_reference_arm(args):
     v, sec, desc = cpu_reference_run(steps, warm, shape["seed"])
     cores = min(os.cpu_count() or 1, 32)
     if v is None:
-        print(json.dumps({"impl": "reference", "unavailable": desc}))
+        emit({"impl": "reference", "unavailable": desc})
         return
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
@@ -304,11 +316,11 @@ def run_reference_arm(args):
                    % (args.workload, shape["N"], shape["M"], shape["tilesz"], CPU_SAMPLE["N"],
                       CPU_SAMPLE["M"], CPU_SAMPLE["tilesz"]), "solve": SOLVE},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                         "sample": desc},
+                         "sample": desc, "stages": cpu_stage_timings(shape["seed"])},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -719,8 +731,31 @@ def run_consensus(args, ctx):
     }
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: every other writer to fd 1 (the NCCL version banner, library
+    chatter of any rank) is sent to stderr; the JSON line goes out through a private duplicate"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -760,7 +795,7 @@ def main():
             sdist.init_nccl(api, rank, world)
         line = run_consensus(args, ctx)
         if rank == 0:
-            print(json.dumps(line))
+            emit(line)
         if world > 1:
             api.lib.dirac_b200_nccl_finalize()
             dist.destroy_process_group()
@@ -779,7 +814,7 @@ def main():
             others[w]["kernels"] = o["roofline"]["kernels"]
         line["other_workloads"] = others
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         api.lib.dirac_b200_nccl_finalize()
         dist.destroy_process_group()

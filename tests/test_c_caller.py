@@ -1,0 +1,33 @@
+"""The C-ABI library compiled into and LINKED against a plain C host (tests/c_caller/caller.c), as the
+reference driver would be: `gcc caller.c -I include -L sagecal_b200 -ldirac_b200`.  On a CPU box the
+host only calls the index helpers and takes the address of every entry point; on the GPU box it also
+runs precalculate_coherencies + sagefit_visibilities."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build(tmp_path):
+    exe = os.path.join(str(tmp_path), "caller")
+    libdir = os.path.join(ROOT, "sagecal_b200")
+    cmd = ["gcc", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "c_caller", "caller.c"),
+           "-I", os.path.join(ROOT, "include"), "-L", libdir, "-ldirac_b200", "-lm",
+           "-Wl,-rpath," + libdir]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_c_host_links_and_calls_host_helpers(tmp_path):
+    exe = build(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "C_CALLER OK" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+@pytest.mark.gpu
+def test_c_host_runs_the_solver(tmp_path):
+    exe = build(tmp_path)
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "C_CALLER OK" in out.stdout, (out.returncode, out.stdout, out.stderr)

@@ -307,6 +307,10 @@ void dirac_b200_host_stats(unsigned long long *syncs, double *wait_seconds, int 
  * dpotrs; reps > 0 additionally times `reps` back-to-back solves (us per solve in *us). */
 int dirac_b200_spd_solve(int n, const double *A, const double *b, double mu, double *x, int *info);
 int dirac_b200_tri_solve(int n, const double *L, const double *b, double *x, int reps, double *us);
+/* the same for systems beyond the cluster kernels (n > 512, a multiple of 64, e.g. 4096 at 512
+ * stations): blocked dataflow substitutions over n/64 co-resident CTAs (replaces cusolverDnDpotrs
+ * behind cuSOLVER's dpotrf).  Returns -1 when the size is not handled. */
+int dirac_b200_bigtri_solve(int n, const double *L, const double *b, double *x, int reps, double *us);
 
 #ifdef __cplusplus
 }

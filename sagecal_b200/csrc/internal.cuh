@@ -410,6 +410,10 @@ void db_launch_chol_factor_batched(const double *A, int n, const double *mu, dou
                                    long long ws_stride, int *info, int nb, cudaStream_t st);
 void db_launch_chol_solve(const double *A, int n, double mu, const double *b, double *x, double *ws,
                           int *info, cudaStream_t st);
+int db_bigtri_available(int n);
+size_t db_bigtri_ws_doubles(int n);
+void db_launch_bigtri_solve(const double *L, int ld, int n, const double *b, double *x, double *ws,
+                            unsigned epoch, int invert, cudaStream_t st);
 int db_stream_all_nblocks(int Nbase, int tilesz);
 void db_launch_predict_tma(const StreamAllArgs *a, cudaStream_t st);
 void db_launch_line_setup_tma(const StreamAllArgs *a, cudaStream_t st);

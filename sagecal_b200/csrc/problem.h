@@ -21,6 +21,8 @@ struct LMWork {
   double *cswork;
   int lwork;
   bool own_chol;  // damped solves by the cluster Cholesky kernel (else cuSOLVER)
+  double *bt_ws;  // large systems: workspace of the blocked triangular solves (kernels_bigtri.cu)
+  unsigned bt_epoch;
   double *jte_part;       // per-CTA station sums of the linear-mapped gradient pass
   bool step_armed, step_fused;  // trial point formed by the solver kernel's epilogue
   double *jtj_spec;       // J^T J assembled speculatively at the trial point (nullptr: none)

@@ -934,6 +934,124 @@ void orc_lbfgs(const orc_problem *P, double *pp, const double *x, int itmax, int
   free(gk); free(xk1); free(xk); free(pk); free(s); free(y); free(rho);
 }
 
+/* ---- RTR / RSD / NSD: the per-row evaluators (Dirac/rtr_solve.c, Dirac/rtr_solve_robust.c) -------
+ * The reference keeps the Jones of one (cluster, chunk) as a 2N x 2 complex matrix
+ * (rtr_solve.c:1224-1243); here they stay in the API's parameter layout (station s: J[a][m] at
+ * 8s + 2(2a+m)), a permutation of it.  y: hidden data of the chunk (row t0*Nbase first), wt: one
+ * weight per row or NULL (= 1).  The control flow on top of these sums is rtr_algo.h (shared with
+ * the product, instantiated with these evaluators by oracle/rtr_harness.cpp) and is pinned against
+ * the compiled reference by tests/test_oracle_rtr.py. */
+static void atmb(const cplx *a, const cplx *b, cplx *c) { /* a^H b, rtr_solve.c:58-64 */
+  c[0] = conj(a[0]) * b[0] + conj(a[2]) * b[2];
+  c[1] = conj(a[0]) * b[1] + conj(a[2]) * b[3];
+  c[2] = conj(a[1]) * b[0] + conj(a[3]) * b[2];
+  c[3] = conj(a[1]) * b[1] + conj(a[3]) * b[3];
+}
+static void rtr_acc(double *vec, int sta, const cplx *T, double w) {
+  for (int i = 0; i < 4; i++) {
+    vec[8 * sta + 2 * i] += w * creal(T[i]);
+    vec[8 * sta + 2 * i + 1] += w * cimag(T[i]);
+  }
+}
+/* cost (threadfn_fns_f, rtr_solve.c:188-241, rtr_solve_robust.c:72-130) and, if vec != NULL, the
+ * unscaled station sums of the gradient (eta == NULL: threadfn_fns_fgrad, rtr_solve.c:453-526,
+ * rtr_solve_robust.c:519-612) or of the Hessian-vector product (threadfn_fns_fhess,
+ * rtr_solve.c:643-761, rtr_solve_robust.c:722-860) */
+double orc_rtr_raw(const orc_problem *P, int k, int t0, int ntiles, const double *y,
+                   const double *wt, const double *x, const double *eta, double *vec) {
+  const int N = P->N, M = P->M;
+  const long nrow = (long)ntiles * P->Nbase, boff = (long)t0 * P->Nbase;
+  double fcost = 0.0;
+  if (vec) memset(vec, 0, sizeof(double) * 8 * N);
+  for (long ci = 0; ci < nrow; ci++) {
+    if (P->flag[ci + boff]) continue;
+    const int s1 = P->sta1[ci + boff], s2 = P->sta2[ci + boff];
+    const double w = wt ? wt[ci] : 1.0;
+    cplx G1[4], G2[4], C[4], T1[4], T2[4], res[4];
+    jones_of(x, s1, G1);
+    jones_of(x, s2, G2);
+    for (int c = 0; c < 4; c++) C[c] = P->coh[4 * M * (ci + boff) + 4 * k + c];
+    amb(G1, C, T1);
+    ambt(T1, G2, T2);
+    double e2 = 0.0;
+    for (int c = 0; c < 4; c++) {
+      res[c] = (y[8 * ci + 2 * c] + _Complex_I * y[8 * ci + 2 * c + 1]) - T2[c];
+      e2 += creal(res[c]) * creal(res[c]) + cimag(res[c]) * cimag(res[c]);
+    }
+    fcost += w * e2;
+    if (!vec) continue;
+    if (!eta) {
+      amb(res, G2, T1);  /* res G2 C^H */
+      ambt(T1, C, T2);
+      rtr_acc(vec, s1, T2, w);
+      atmb(res, G1, T1); /* res^H G1 C */
+      amb(T1, C, T2);
+      rtr_acc(vec, s2, T2, w);
+    } else {
+      cplx E1[4], E2[4], res1[4];
+      jones_of(eta, s1, E1);
+      jones_of(eta, s2, E2);
+      amb(G1, C, T1);
+      ambt(T1, E2, res1);
+      amb(E1, C, T1);
+      ambt(T1, G2, T2);
+      for (int c = 0; c < 4; c++) res1[c] += T2[c];
+      amb(res, E2, T1); /* (res E2 - res1 G2) C^H */
+      amb(res1, G2, T2);
+      for (int c = 0; c < 4; c++) T1[c] -= T2[c];
+      ambt(T1, C, T2);
+      rtr_acc(vec, s1, T2, w);
+      atmb(res, E1, T1); /* (res^H E1 - res1^H G1) C */
+      atmb(res1, G1, T2);
+      for (int c = 0; c < 4; c++) T1[c] -= T2[c];
+      amb(T1, C, T2);
+      rtr_acc(vec, s2, T2, w);
+    }
+  }
+  return fcost;
+}
+/* unflagged rows per station (threadfn_fns_fcount, rtr_solve.c:71-91) */
+void orc_rtr_counts(const orc_problem *P, int t0, int ntiles, double *cnt) {
+  const long nrow = (long)ntiles * P->Nbase, boff = (long)t0 * P->Nbase;
+  for (int i = 0; i < P->N; i++) cnt[i] = 0.0;
+  for (long ci = 0; ci < nrow; ci++)
+    if (!P->flag[ci + boff]) {
+      cnt[P->sta1[ci + boff]] += 1.0;
+      cnt[P->sta2[ci + boff]] += 1.0;
+    }
+}
+/* row weights (nu+2)/(nu + max_c |res_c|^2) at x (threadfn_fns_fupdate_weights,
+ * rtr_solve_robust.c:209-262); returns sum(log w - w) over the unflagged rows divided by ALL rows
+ * (:271-287,360-370; flagged rows keep their weight and are never read) */
+double orc_rtr_weights(const orc_problem *P, int k, int t0, int ntiles, const double *y,
+                       const double *x, double nu, double *wt) {
+  const int M = P->M;
+  const long nrow = (long)ntiles * P->Nbase, boff = (long)t0 * P->Nbase;
+  double s = 0.0;
+  for (long ci = 0; ci < nrow; ci++) {
+    if (P->flag[ci + boff]) continue;
+    cplx G1[4], G2[4], C[4], T2[4];
+    jones_of(x, P->sta1[ci + boff], G1);
+    jones_of(x, P->sta2[ci + boff], G2);
+    for (int c = 0; c < 4; c++) C[c] = P->coh[4 * M * (ci + boff) + 4 * k + c];
+    model_row(G1, C, G2, T2);
+    double mx = 0.0;
+    for (int c = 0; c < 4; c++) {
+      const double er = y[8 * ci + 2 * c] - creal(T2[c]), ei = y[8 * ci + 2 * c + 1] - cimag(T2[c]);
+      const double e2 = er * er + ei * ei;
+      if (e2 > mx) mx = e2;
+    }
+    const double w = (nu + 2.0) / (nu + mx);
+    if (wt) wt[ci] = w;
+    s += log(w) - w;
+  }
+  return s / (double)nrow;
+}
+
+/* solver of one (cluster, chunk) for solver_mode 4-6, registered by oracle/rtr_harness.cpp */
+static orc_rtr_solver_fn g_rtr_solver = 0;
+void orc_set_rtr_solver(orc_rtr_solver_fn fn) { g_rtr_solver = fn; }
+
 /* ---- sagefit_visibilities (Dirac/lmfit.c:778-1053), randomize=0 ------------------------------- */
 static int robust_mode(int sm) { return sm == 2 || sm == 3 || sm == 5 || sm == 6; }
 
@@ -949,11 +1067,13 @@ int orc_sagefit(const orc_problem *P, double *x, double *pp, int max_emiter, int
   double *nerr = (double *)xcalloc(M, sizeof(double));
   double *nuM = (double *)xcalloc(M, sizeof(double));
   double robust_nu0 = nulow;
-  if (solver_mode < 0 || solver_mode > 3) {
-    fprintf(stderr, "oracle: solver_mode %d not restated (LM / OS-LM / robust LM only)\n",
+  double rtr_nu = nulow; /* lmdata.robust_nu of the RTR / NSD visits (lmfit.c:938-957) */
+  if (solver_mode < 0 || solver_mode > 6 || (solver_mode > 3 && !g_rtr_solver)) {
+    fprintf(stderr, "oracle: solver_mode %d not available (4-6 need oracle/librtr_harness.so)\n",
             solver_mode);
     exit(1);
   }
+  for (int i = 0; i < 10; i++) info[i] = 0.0;
   orc_predict_full(P, pp, xsub);
   for (long i = 0; i < n; i++) xdummy[i] = x[i] - xsub[i];
   *res_0 = sqrt(nrm2sq(xdummy, n)) / (double)n;
@@ -977,6 +1097,18 @@ int orc_sagefit(const orc_problem *P, double *x, double *pp, int max_emiter, int
         } else if (solver_mode == 0) {
           orc_lm_chunk(P, cj, tcj, ntiles, pblk, xd, this_itermax, opts, linsolv, last ? 0 : 1,
                        info);
+        } else if (solver_mode == 4) { /* lmfit.c:934-937 */
+          g_rtr_solver(P, cj, tcj, ntiles, xd, 4, pblk, this_itermax + 5, this_itermax + 10, nulow,
+                       nuhigh, &rtr_nu, info);
+        } else if (solver_mode == 5 || solver_mode == 6) { /* lmfit.c:938-957 */
+          if (!ci) rtr_nu = robust_nu0;
+          if (solver_mode == 5)
+            g_rtr_solver(P, cj, tcj, ntiles, xd, 5, pblk, this_itermax + 5, this_itermax + 10,
+                         nulow, nuhigh, &rtr_nu, info);
+          else
+            g_rtr_solver(P, cj, tcj, ntiles, xd, 6, pblk, this_itermax + 15, 0, nulow, nuhigh,
+                         &rtr_nu, info);
+          if (last) nuM[cj] += rtr_nu;
         } else if (last) {
           double nu = robust_nu0;
           orc_rlm_chunk(P, cj, tcj, ntiles, pblk, xd, this_itermax, linsolv, solver_mode == 3,

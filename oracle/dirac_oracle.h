@@ -48,6 +48,17 @@ double orc_update_w_and_nu(double nu0, double *w, const double *ed, int n, doubl
 long orc_noise_decisions(int reset);
 void orc_lbfgs(const orc_problem *P, double *pp, const double *x, int itmax, int M, int robust,
                double nu);
+/* RTR / RSD / NSD (solver_mode 4-6): per-row evaluators; the solver of one chunk is supplied by
+ * oracle/rtr_harness.cpp (the control flow of rtr_algo.h on these evaluators) */
+double orc_rtr_raw(const orc_problem *P, int k, int t0, int ntiles, const double *y,
+                   const double *wt, const double *x, const double *eta, double *vec);
+void orc_rtr_counts(const orc_problem *P, int t0, int ntiles, double *cnt);
+double orc_rtr_weights(const orc_problem *P, int k, int t0, int ntiles, const double *y,
+                       const double *x, double nu, double *wt);
+typedef void (*orc_rtr_solver_fn)(const orc_problem *P, int k, int t0, int ntiles, const double *y,
+                                  int kind, double *x, int itmax_a, int itmax_b, double nulow,
+                                  double nuhigh, double *robust_nu, double *info);
+void orc_set_rtr_solver(orc_rtr_solver_fn fn);
 int orc_sagefit(const orc_problem *P, double *x, double *pp, int max_emiter, int max_iter,
                 int max_lbfgs, int lbfgs_m, int linsolv, int solver_mode, double nulow,
                 double nuhigh, double *mean_nu, double *res_0, double *res_1);

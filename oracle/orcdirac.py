@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORC_PATH = os.path.join(_HERE, "liboracle.so")
+RTR_PATH = os.path.join(_HERE, "librtr_harness.so")
+RTR_TENSOR_PATH = os.path.join(_HERE, "librtr_tensor_check.so")
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int)
@@ -41,8 +43,11 @@ class Oracle:
     """the restated hot path bound to one synthetic problem (sagecal_b200.synth.Problem)"""
 
     def __init__(self, pr, coh=None, flag=None):
-        L = C.CDLL(ORC_PATH)
+        L = C.CDLL(ORC_PATH, mode=C.RTLD_GLOBAL)
         self.L = L
+        # RTR / RSD / NSD control flow on the oracle's evaluators (registers itself with liboracle
+        # when loaded: orc_sagefit then accepts solver_mode 4-6)
+        self.H = C.CDLL(RTR_PATH) if os.path.exists(RTR_PATH) else None
         self.pr = pr
         d, i = C.c_double, C.c_int
         pp = C.POINTER(orc_problem)
@@ -63,6 +68,15 @@ class Oracle:
         L.orc_sagefit.argtypes = [pp, dp, dp, i, i, i, i, i, i, d, d, dp, dp, dp]
         L.orc_bfgsfit.restype = i
         L.orc_bfgsfit.argtypes = [pp, dp, dp, i, i, i, d, dp, dp]
+        if self.H is not None:
+            self.H.harness_rtr_solve.argtypes = [pp, i, i, i, i, i, dp, i, dp, i, i, d, d, dp, dp, i]
+            self.H.harness_rtr_solve.restype = None
+        # the arithmetic of the product's RTR kernels (rtr_math.cuh) on the CPU
+        self.HT = C.CDLL(RTR_TENSOR_PATH) if os.path.exists(RTR_TENSOR_PATH) else None
+        if self.HT is not None:
+            self.HT.harness_rtr_solve_tensor.argtypes = [pp, i, i, i, dp, i, dp, i, i, d, d, dp, dp,
+                                                         i]
+            self.HT.harness_rtr_solve_tensor.restype = None
         L.orc_generate_baselines.argtypes = [i, i, i, ip, ip]
         L.orc_preset_flags_and_data.argtypes = [i, dp, up, dp]
         ps = C.POINTER(orc_sky)
@@ -142,6 +156,24 @@ class Oracle:
         xd = np.ascontiguousarray(xd)
         self.L.orc_rlm_chunk(C.byref(self.P), k, t0, ntiles, _d(p), _d(xd), itmax, linsolv,
                              int(os_), nulow, nuhigh, C.byref(nu), _d(info))
+        return p, info, nu.value
+
+    def rtr_chunk(self, k, t0, ntiles, pblk, xd, kind, itmax_a, itmax_b, nulow=2.0, nuhigh=30.0,
+                  nu0=2.0, nu_joined=True, tensor=False):
+        """RTR (kind 4), robust RTR (5), NSD (6) of one chunk on hidden data xd.  tensor: with the
+        per-baseline tensor arithmetic of the product's kernels instead of the per-row evaluators"""
+        p = np.ascontiguousarray(pblk, dtype=np.float64).copy()
+        info = np.zeros(10)
+        nu = C.c_double(nu0)
+        xd = np.ascontiguousarray(xd)
+        if tensor:
+            self.HT.harness_rtr_solve_tensor(C.byref(self.P), k, t0, ntiles, _d(xd), kind, _d(p),
+                                             itmax_a, itmax_b, nulow, nuhigh, C.byref(nu),
+                                             _d(info), int(nu_joined))
+            return p, info, nu.value
+        self.H.harness_rtr_solve(C.byref(self.P), self.pr.N, self.pr.Nbase, k, t0, ntiles, _d(xd),
+                                 kind, _d(p), itmax_a, itmax_b, nulow, nuhigh, C.byref(nu),
+                                 _d(info), int(nu_joined))
         return p, info, nu.value
 
     def update_w_and_nu(self, nu0, ed, nulow=2.0, nuhigh=30.0):

@@ -17,6 +17,9 @@ from sagecal_b200.dirac_api import (DiracAPI, SkyModel, baseline_t, clus_source_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_PATH = os.path.join(_HERE, "_ref", "libdirac_ref.so")
+# same object code, except that the robust RTR / NSD solvers run their threads synchronously
+# (ref_shim_rtr_serial.c): the deterministic pin of solver_mode 5 and 6
+SERIAL_PATH = os.path.join(_HERE, "_ref", "libdirac_ref_serial.so")
 
 
 def available() -> bool:
@@ -54,6 +57,12 @@ class RefDirac(DiracAPI):
         L.osrlevmar_der_single_nocuda.restype = i
         L.osrlevmar_der_single_nocuda.argtypes = [vp, vp, dp, dp, i, i, i, dp, dp, i, i, d, d, i,
                                                   vp]
+        L.rtr_solve_nocuda.restype = i
+        L.rtr_solve_nocuda.argtypes = [dp, dp, i, i, i, i, d, d, dp, vp]
+        L.rtr_solve_nocuda_robust.restype = i
+        L.rtr_solve_nocuda_robust.argtypes = [dp, dp, i, i, i, i, d, d, d, d, dp, vp]
+        L.nsd_solve_nocuda_robust.restype = i
+        L.nsd_solve_nocuda_robust.argtypes = [dp, dp, i, i, i, d, d, dp, vp]
         L.update_w_and_nu.restype = d
         L.update_w_and_nu.argtypes = [d, dp, dp, i, i, d, d]
 
@@ -137,7 +146,34 @@ class RefDirac(DiracAPI):
         return pblk, info, self.lib.ref_get_robust_nu(md)
 
 
+    def rtr(self, pblk, xd, md, N, nrows, kind, itmax_a, itmax_b, nulow=2.0, nuhigh=30.0):
+        """rtr_solve_nocuda (kind 4, rtr_solve.c:1207), rtr_solve_nocuda_robust (5,
+        rtr_solve_robust.c:1440), nsd_solve_nocuda_robust (6, :1877) on hidden data xd; md carries
+        the cluster, the tile range and robust_nu (in/out)"""
+        p = np.ascontiguousarray(pblk, dtype=np.float64).copy()
+        info = np.zeros(10)
+        xd = np.ascontiguousarray(xd, dtype=np.float64).copy()
+        if kind == 4:
+            self.lib.rtr_solve_nocuda(dptr(p), dptr(xd), N, nrows, itmax_a, itmax_b, 0.01,
+                                      0.01 * 0.125, dptr(info), md)
+        elif kind == 5:
+            self.lib.rtr_solve_nocuda_robust(dptr(p), dptr(xd), N, nrows, itmax_a, itmax_b, 0.01,
+                                             0.01 * 0.125, nulow, nuhigh, dptr(info), md)
+        else:
+            self.lib.nsd_solve_nocuda_robust(dptr(p), dptr(xd), N, nrows, itmax_a, nulow, nuhigh,
+                                             dptr(info), md)
+        return p, info, self.lib.ref_get_robust_nu(md)
+
+
 _ref = None
+_ser = None
+
+
+def load_serial() -> RefDirac:
+    global _ser
+    if _ser is None:
+        _ser = RefDirac(SERIAL_PATH)
+    return _ser
 
 
 def load() -> RefDirac:

@@ -73,36 +73,36 @@ __host__ __device__ __forceinline__ long long baseline_index(int p, int q, int N
 // ------------------------------------------------------------------------------------------------
 // 2x2 complex algebra on double2 (x = re, y = im), row-major [00,01,10,11]
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+__host__ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 // a * conj(b)
-__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
+__host__ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
   return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 // conj(a) * b
-__device__ __forceinline__ double2 cmulcl(double2 a, double2 b) {
+__host__ __device__ __forceinline__ double2 cmulcl(double2 a, double2 b) {
   return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
-__device__ __forceinline__ double2 cadd(double2 a, double2 b) {
+__host__ __device__ __forceinline__ double2 cadd(double2 a, double2 b) {
   return make_double2(a.x + b.x, a.y + b.y);
 }
-__device__ __forceinline__ double2 csub(double2 a, double2 b) {
+__host__ __device__ __forceinline__ double2 csub(double2 a, double2 b) {
   return make_double2(a.x - b.x, a.y - b.y);
 }
-__device__ __forceinline__ void cfma(double2 &acc, double2 a, double2 b) {  // acc += a*b
+__host__ __device__ __forceinline__ void cfma(double2 &acc, double2 a, double2 b) {  // acc += a*b
   acc.x = fma(a.x, b.x, acc.x);
   acc.x = fma(-a.y, b.y, acc.x);
   acc.y = fma(a.x, b.y, acc.y);
   acc.y = fma(a.y, b.x, acc.y);
 }
-__device__ __forceinline__ void cfmac(double2 &acc, double2 a, double2 b) {  // acc += a*conj(b)
+__host__ __device__ __forceinline__ void cfmac(double2 &acc, double2 a, double2 b) {  // acc += a*conj(b)
   acc.x = fma(a.x, b.x, acc.x);
   acc.x = fma(a.y, b.y, acc.x);
   acc.y = fma(a.y, b.x, acc.y);
   acc.y = fma(-a.x, b.y, acc.y);
 }
-__device__ __forceinline__ void cfmacl(double2 &acc, double2 a, double2 b) {  // acc += conj(a)*b
+__host__ __device__ __forceinline__ void cfmacl(double2 &acc, double2 a, double2 b) {  // acc += conj(a)*b
   acc.x = fma(a.x, b.x, acc.x);
   acc.x = fma(a.y, b.y, acc.x);
   acc.y = fma(a.x, b.y, acc.y);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void cfmacl(double2 &acc, double2 a, double2 b) {  //
 // multiplies and adds compile to.  The fp64 pipe (64 lanes/clk/SM) is the second bound of every
 // streaming kernel here, right behind HBM.
 // a0*b0 + a1*b1
-__device__ __forceinline__ double2 cdot2(double2 a0, double2 b0, double2 a1, double2 b1) {
+__host__ __device__ __forceinline__ double2 cdot2(double2 a0, double2 b0, double2 a1, double2 b1) {
   double re = a0.x * b0.x;
   re = fma(-a0.y, b0.y, re);
   re = fma(a1.x, b1.x, re);
@@ -126,7 +126,7 @@ __device__ __forceinline__ double2 cdot2(double2 a0, double2 b0, double2 a1, dou
   return make_double2(re, im);
 }
 // a0*conj(b0) + a1*conj(b1)
-__device__ __forceinline__ double2 cdot2c(double2 a0, double2 b0, double2 a1, double2 b1) {
+__host__ __device__ __forceinline__ double2 cdot2c(double2 a0, double2 b0, double2 a1, double2 b1) {
   double re = a0.x * b0.x;
   re = fma(a0.y, b0.y, re);
   re = fma(a1.x, b1.x, re);
@@ -138,7 +138,7 @@ __device__ __forceinline__ double2 cdot2c(double2 a0, double2 b0, double2 a1, do
   return make_double2(re, im);
 }
 // acc += a0*conj(b0) + a1*conj(b1)
-__device__ __forceinline__ void cdot2c_acc(double2 &acc, double2 a0, double2 b0, double2 a1,
+__host__ __device__ __forceinline__ void cdot2c_acc(double2 &acc, double2 a0, double2 b0, double2 a1,
                                            double2 b1) {
   acc.x = fma(a0.x, b0.x, acc.x);
   acc.x = fma(a0.y, b0.y, acc.x);
@@ -150,28 +150,28 @@ __device__ __forceinline__ void cdot2c_acc(double2 &acc, double2 a0, double2 b0,
   acc.y = fma(-a1.x, b1.y, acc.y);
 }
 // C = A*B          (lmfit.c:37-42 "amb")
-__device__ __forceinline__ void mat_ab(const double2 *a, const double2 *b, double2 *c) {
+__host__ __device__ __forceinline__ void mat_ab(const double2 *a, const double2 *b, double2 *c) {
   c[0] = cdot2(a[0], b[0], a[1], b[2]);
   c[1] = cdot2(a[0], b[1], a[1], b[3]);
   c[2] = cdot2(a[2], b[0], a[3], b[2]);
   c[3] = cdot2(a[2], b[1], a[3], b[3]);
 }
 // C = A*B^H        (lmfit.c:50-58 "ambt")
-__device__ __forceinline__ void mat_abh(const double2 *a, const double2 *b, double2 *c) {
+__host__ __device__ __forceinline__ void mat_abh(const double2 *a, const double2 *b, double2 *c) {
   c[0] = cdot2c(a[0], b[0], a[1], b[1]);
   c[1] = cdot2c(a[0], b[2], a[1], b[3]);
   c[2] = cdot2c(a[2], b[0], a[3], b[1]);
   c[3] = cdot2c(a[2], b[2], a[3], b[3]);
 }
 // C += A*B^H
-__device__ __forceinline__ void mat_abh_acc(const double2 *a, const double2 *b, double2 *c) {
+__host__ __device__ __forceinline__ void mat_abh_acc(const double2 *a, const double2 *b, double2 *c) {
   cdot2c_acc(c[0], a[0], b[0], a[1], b[1]);
   cdot2c_acc(c[1], a[0], b[2], a[1], b[3]);
   cdot2c_acc(c[2], a[2], b[0], a[3], b[1]);
   cdot2c_acc(c[3], a[2], b[2], a[3], b[3]);
 }
 // C = A^H*B
-__device__ __forceinline__ void mat_ahb(const double2 *a, const double2 *b, double2 *c) {
+__host__ __device__ __forceinline__ void mat_ahb(const double2 *a, const double2 *b, double2 *c) {
   c[0] = cadd(cmulcl(a[0], b[0]), cmulcl(a[2], b[2]));
   c[1] = cadd(cmulcl(a[0], b[1]), cmulcl(a[2], b[3]));
   c[2] = cadd(cmulcl(a[1], b[0]), cmulcl(a[3], b[2]));
@@ -370,7 +370,8 @@ struct BatchAssembleArgs {
 };
 
 // test / tuning options (dirac_b200_set_option): 0 = default
-enum { DB_OPT_CP_ROWS = 0, DB_OPT_LINE_DIRECT = 1, DB_OPT_OS_CONSISTENT = 2, DB_OPT_COUNT = 8 };
+enum { DB_OPT_CP_ROWS = 0, DB_OPT_LINE_DIRECT = 1, DB_OPT_OS_CONSISTENT = 2,
+       DB_OPT_RTR_NU_UNJOINED = 3, DB_OPT_COUNT = 8 };
 int db_opt(int id);
 int db_sm_count();  // SMs of the current device
 // slices of the time axis the linear-mapped gradient pass may use (sizes LMWork::jte_part)

@@ -277,7 +277,11 @@ static void weighted_jtj(dirac_b200_problem *pr, int k, int t0, int t1, const do
 }
 
 // chunk ck of cluster k covers timeslots [t0,t1)  (lmfit.c:893-905)
+void db_chunk_range(const DevProblem &d, int k, int ck, int *t0, int *t1);
 static void chunk_range(const DevProblem &d, int k, int ck, int *t0, int *t1) {
+  db_chunk_range(d, k, ck, t0, t1);
+}
+void db_chunk_range(const DevProblem &d, int k, int ck, int *t0, int *t1) {
   int nchunk = d.h_clus[k].nchunk;
   int tilechunk = (d.tilesz + nchunk - 1) / nchunk;
   int a = ck * tilechunk;

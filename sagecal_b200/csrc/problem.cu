@@ -76,6 +76,9 @@ extern "C" int dirac_b200_set_option(const char *name, int value) {
   if (!strcmp(name, "cp_rows")) { g_opt[DB_OPT_CP_ROWS] = value; return 0; }
   if (!strcmp(name, "line_direct")) { g_opt[DB_OPT_LINE_DIRECT] = value; return 0; }
   if (!strcmp(name, "os_consistent")) { g_opt[DB_OPT_OS_CONSISTENT] = value; return 0; }
+  // robust RTR / NSD: nu update as if the reference's unjoined thread sums were all still zero
+  // (rtr_algo.h: update_weights)
+  if (!strcmp(name, "rtr_nu_unjoined")) { g_opt[DB_OPT_RTR_NU_UNJOINED] = value; return 0; }
   return -1;
 }
 // SMs of the current device (grids of the one-wave kernels are sized from it)
@@ -336,6 +339,7 @@ extern "C" void dirac_b200_destroy(dirac_b200_problem *pr) {
   DevProblem &d = pr->d;
   cudaStreamSynchronize(d.stream);
   db_lm_free(pr);
+  db_rtr_free(pr);
   db_free(d.coh); db_free(d.x); db_free(d.flag); db_free(d.pp); db_free(d.clus);
   db_free(d.chunk_poff); db_free(d.tiles); db_free(d.blpq); db_free(d.scal); db_free(d.counters);
   db_free(pr->partials); db_free(pr->res); db_free(pr->g); db_free(pr->vis_stage);

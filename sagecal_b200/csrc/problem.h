@@ -79,6 +79,7 @@ struct dirac_b200_problem {
   double *pp_start;       // [npar] Jones at the start of a sharded sweep
   // LBFGS line model (allocated on first use)
   double2 *E0, *E1, *E2;  // [4][R] each
+  struct RtrWork *rtr;    // RTR / NSD solvers (rtr.cu), allocated on first use
 };
 
 // host waits on the device, timed (dirac_b200_host_stats): where the host-driven solver idles
@@ -123,3 +124,4 @@ void db_launch_cluster_rowmap(const double2 *coh_k, const double2 *in, const dou
 }
 
 void db_lm_free(dirac_b200_problem *pr);
+void db_rtr_free(dirac_b200_problem *pr);

@@ -1,0 +1,36 @@
+// Internal: argument blocks of the RTR-family kernels (kernels_rtr.cu) and their launchers.
+#pragma once
+#include "internal.cuh"
+
+struct RtrStatsArgs {
+  const double2 *coh_k;       // [4][R] coherencies of the cluster
+  const double2 *d;           // [4][R] hidden data
+  const unsigned char *flag;  // [R]
+  const short2 *blpq;         // [Nbase]
+  const double *xw;           // 8N Jones the robust weights are evaluated at; null: w = 1
+  double nu;
+  double2 *TD;                // [nslice][32][Nbase]: planes 0-15 T (row-major 4x4), 16-31 D
+  double *sc;                 // [nslice][3][Nbase]: c0, sum(log w - w), unflagged rows
+  long long R;
+  int N, Nbase;
+  int t_begin, t_end, tslice;
+  int tensors;                // 0: scalars only (weight statistics for the nu update)
+};
+
+struct RtrEvalArgs {
+  const double2 *TD;          // [32][Nbase]
+  const double *sc;           // [3][Nbase]
+  const double *x;            // 8N Jones
+  const double *eta;          // 8N tangent vector: Hessian-vector product; null: gradient
+  double *out;                // [8N] raw station sums (before scaling / projection), may be null
+  double *cost;               // [N] per-station partial costs, may be null
+  double *count;              // [N] unflagged rows per station, may be null
+  int N, Nbase;
+};
+
+extern "C" {
+void db_launch_rtr_stats(const RtrStatsArgs *a, int nslice, cudaStream_t st);
+void db_launch_rtr_reduce(const double *in, double *out, size_t n, int ns, cudaStream_t st);
+void db_launch_rtr_eval(const RtrEvalArgs *a, cudaStream_t st);
+void db_launch_rtr_plane_sum(const double *sc, int Nbase, int which, double *dst, cudaStream_t st);
+}

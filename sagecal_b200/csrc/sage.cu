@@ -21,6 +21,9 @@ bool db_cluster_needs_rowmap(const dirac_b200_problem *pr, int k);
 void db_cluster_hidden(dirac_b200_problem *pr, int k, double2 *r, int sign);
 void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, int robust,
                   double nu);
+void db_rtr_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int kind,
+                  int itmax_a, int itmax_b, double nulow, double nuhigh, double *robust_nu,
+                  double *info, bool hidden_ready);
 
 static bool is_robust_mode(int solver_mode) {
   return solver_mode == SM_OSLM_OSRLM_RLBFGS || solver_mode == SM_RLM_RLBFGS ||
@@ -37,22 +40,6 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
     fprintf(stderr, "%s: %d: undefined solver mode\n", __FILE__, __LINE__);  // lmfit.c:957-962
     exit(1);
   }
-  if (solver_mode == SM_RTR_OSLM_LBFGS || solver_mode == SM_RTR_OSRLM_RLBFGS ||
-      solver_mode == SM_NSD_RLBFGS) {
-    // The Riemannian trust-region / nested-SD solvers (rtr_solve*.c; the driver's default -j 5,
-    // src/MS/data.cpp:69) are not part of this library.  A host linked against it
-    // must not die on its default settings: solve with the LM-family mode of the same noise model
-    // (4 -> OS-LM + LBFGS, 5 and 6 -> OS-LM / OS robust LM + robust LBFGS) and say so once.
-    static bool warned = false;
-    const int mapped = (solver_mode == SM_RTR_OSLM_LBFGS) ? SM_OSLM_LBFGS : SM_OSLM_OSRLM_RLBFGS;
-    if (!warned) {
-      fprintf(stderr, "dirac_b200: solver_mode %d (RTR/NSD) is not implemented; solving with "
-                      "solver_mode %d (same noise model, LM family). Use -j 0..3 to silence this.\n",
-              solver_mode, mapped);
-      warned = true;
-    }
-    solver_mode = mapped;
-  }
   DevProblem &d = pr->d;
   const int M = d.M;
   const int m = (int)pr->d.npar;
@@ -63,8 +50,9 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
   if (pr->lm.ready) memset(pr->lm.T_valid, 0, d.Mt);
   // CPU-path LM thresholds (lmfit.c:801)
   double opts[5] = {1e-3, 1e-15, 1e-15, 1e-20, -1e-6};
-  double info[10];
+  double info[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   double robust_nu0 = nulow;
+  double rtr_nu = nulow;  // lmdata.robust_nu of the RTR / NSD visits
   // cluster-sharded run: M local clusters, global cluster index k0 + cj; per-cluster
   // bookkeeping vectors are global and summed over the ranks after every sweep
   const bool sharded = pr->world > 1;
@@ -153,6 +141,22 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
             } else {
               db_lm_chunk(pr, cj, ck, pblk, r, this_itermax, opts, linsolv, 1, randomize, info, hr);
             }
+          } else if (solver_mode == SM_RTR_OSLM_LBFGS) {
+            // RSD + RTR (lmfit.c:934-937)
+            db_rtr_chunk(pr, cj, ck, pblk, r, 4, this_itermax + 5, this_itermax + 10, nulow,
+                         nuhigh, &rtr_nu, info, hr);
+          } else if (solver_mode == SM_RTR_OSRLM_RLBFGS) {
+            // robust RTR; nu persists from visit to visit after the first sweep (lmfit.c:938-947)
+            if (!ci) rtr_nu = robust_nu0;
+            db_rtr_chunk(pr, cj, ck, pblk, r, 5, this_itermax + 5, this_itermax + 10, nulow,
+                         nuhigh, &rtr_nu, info, hr);
+            if (last) robust_nuM[cg] += rtr_nu;
+          } else if (solver_mode == SM_NSD_RLBFGS) {
+            // Nesterov's accelerated descent (lmfit.c:948-957)
+            if (!ci) rtr_nu = robust_nu0;
+            db_rtr_chunk(pr, cj, ck, pblk, r, 6, this_itermax + 15, 0, nulow, nuhigh, &rtr_nu,
+                         info, hr);
+            if (last) robust_nuM[cg] += rtr_nu;
           } else {  // SM_OSLM_OSRLM_RLBFGS
             if (last) {
               double nu = robust_nu0;

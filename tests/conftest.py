@@ -22,6 +22,17 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def refser():
+    """the compiled reference with the worker threads of its robust RTR / NSD solvers run
+    synchronously (oracle/ref_shim_rtr_serial.c): deterministic pin of solver_mode 5 and 6"""
+    import refdirac
+    import os
+    if not os.path.exists(refdirac.SERIAL_PATH):
+        pytest.skip("oracle/_ref/libdirac_ref_serial.so not built (make -C oracle)")
+    return refdirac.load_serial()
+
+
+@pytest.fixture(scope="session")
 def api():
     """the product library; GPU tests only"""
     import torch

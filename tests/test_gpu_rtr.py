@@ -1,0 +1,54 @@
+"""GPU parity of solver_mode 4 (RSD + RTR), 5 (robust RTR, the reference driver's default) and 6
+(Nesterov) through the drop-in entry point, against the compiled reference CPU path.  The robust
+modes are compared with the reference build whose worker threads run synchronously
+(oracle/ref_shim_rtr_serial.c): the threaded build reads its partial sums of log w - w before
+joining the threads, so its nu depends on thread timing."""
+import numpy as np
+import pytest
+
+from util import small_problem, relerr
+
+pytestmark = pytest.mark.gpu
+
+JONES_TOL = 1e-5
+
+CASES = [
+    ("rtr", 4, dict(N=10, M=3, tilesz=10, seed=71), dict(max_iter=3)),
+    ("rtr-hybrid", 4, dict(N=12, M=4, tilesz=10, seed=72, nchunk=[1, 2, 1, 5]), dict(max_iter=2)),
+    ("rtr-uneven", 4, dict(N=9, M=3, tilesz=10, seed=73, nchunk=[3, 1, 4]), dict(max_iter=2)),
+    ("rtr-flags", 4, dict(N=10, M=2, tilesz=10, seed=74, flag_frac=0.3, uvcut_frac=0.02),
+     dict(max_iter=3)),
+    ("rtr-nolbfgs", 4, dict(N=35, M=3, tilesz=6, seed=75), dict(max_iter=2, max_lbfgs=0)),
+    # more than one time slice per baseline block and more than 32 stations per warp loop
+    ("rtr-slices", 4, dict(N=40, M=2, tilesz=24, seed=76), dict(max_iter=2, max_lbfgs=0)),
+    ("rrtr", 5, dict(N=10, M=3, tilesz=10, seed=77, outliers=0.02), dict(max_iter=3)),
+    ("rrtr-hybrid", 5, dict(N=13, M=4, tilesz=20, seed=78, kmean=1.0, outliers=0.02,
+                            nchunk=[1, 2, 1, 4]), dict(max_iter=2)),
+    ("rrtr-62", 5, dict(N=62, M=3, tilesz=4, seed=79, outliers=0.02), dict(max_iter=2, max_lbfgs=4)),
+    ("nsd", 6, dict(N=10, M=3, tilesz=10, seed=80, outliers=0.02), dict(max_iter=3)),
+    ("nsd-hybrid", 6, dict(N=11, M=3, tilesz=12, seed=81, outliers=0.02, nchunk=[2, 1, 3]),
+     dict(max_iter=2)),
+]
+
+
+@pytest.mark.parametrize("name,mode,prob,args", CASES, ids=[c[0] for c in CASES])
+def test_sagefit_rtr_modes(api, ref, refser, name, mode, prob, args):
+    b = small_problem(**prob)
+    pr = b.pr
+    kw = dict(max_emiter=3, max_lbfgs=6, lbfgs_m=7, randomize=0, solver_mode=mode)
+    kw.update(args)
+    out = []
+    for lib in (ref if mode == 4 else refser, api):
+        x = pr.x.copy()
+        pp = pr.pp0.copy()
+        r = lib.sagefit_visibilities(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz, b.fresh_barr(),
+                                     b.sky, pr.coh, pp, **kw)
+        out.append((r, x, pp))
+    (rr, xr, ppr), (rg, xg, ppg) = out
+    assert rr[0] == rg[0]
+    assert abs(rr[1] - rg[1]) < 1e-9                    # mean nu
+    assert abs(rr[2] - rg[2]) <= 1e-10 * rr[2]          # res_0
+    assert relerr(ppg, ppr) < JONES_TOL, (name, relerr(ppg, ppr))
+    assert relerr(xg, xr) < 1e-5 * max(1.0, np.max(np.abs(pr.x)) / np.max(np.abs(xr)))
+    assert abs(rr[3] - rg[3]) <= 1e-5 * rr[3]           # res_1
+    assert rg[3] < rg[2]

@@ -1,0 +1,81 @@
+"""CPU: pins the RTR / RSD / NSD control flow (sagecal_b200/csrc/rtr_algo.h, the code the product
+runs on the host) against the compiled reference's rtr_solve_nocuda, rtr_solve_nocuda_robust and
+nsd_solve_nocuda_robust, with the oracle's plain O(rows) evaluators underneath
+(oracle/rtr_harness.cpp).  Runs without a GPU."""
+import numpy as np
+import pytest
+
+import orcdirac
+from util import small_problem, perturbed_jones, relerr
+
+CASES = [
+    dict(N=8, M=2, tilesz=10, seed=61),
+    dict(N=11, M=3, tilesz=6, seed=62, kmean=2.0, outliers=0.03),
+    dict(N=9, M=2, tilesz=12, seed=63, nchunk=[3, 1], outliers=0.02),
+]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_oracle():
+    if not orcdirac.available() or not orcdirac.os.path.exists(orcdirac.RTR_PATH):
+        pytest.skip("oracle/liboracle.so / librtr_harness.so not built")
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("kind", [4, 5, 6], ids=["rtr", "rtr-robust", "nsd"])
+def test_rtr_chunk_matches_reference(ref, refser, case, kind):
+    ref = ref if kind == 4 else refser  # robust kinds: serialised threads (race in the nu update)
+    b = small_problem(**CASES[case])
+    pr = b.pr
+    orc = orcdirac.Oracle(pr)
+    pp = perturbed_jones(pr, seed=9, amp=0.05)
+    # residual of the full model, then the hidden data of each cluster in turn (lmfit.c:866-891)
+    res = pr.x - orc.predict_full(pp)
+    off = 0
+    for k in range(pr.M):
+        hidden = res + orc.predict_cluster(k, pp)
+        for ck in range(pr.nchunk[k]):
+            t0, nt = orc.chunk_tiles(k, ck)
+            pblk = pp[off:off + 8 * pr.N].copy()
+            off += 8 * pr.N
+            if nt <= 0:
+                continue
+            xd = hidden[8 * t0 * pr.Nbase: 8 * (t0 + nt) * pr.Nbase]
+            md = ref.me_data(pr.N, pr.Nbase, nt, b.barr, b.sky, pr.coh, clus=k, tileoff=t0,
+                             robust_nu=3.0)
+            ita, itb = (8, 13) if kind != 6 else (18, 0)
+            pw, iw, nuw = ref.rtr(pblk, xd, md, pr.N, nt * pr.Nbase, kind, ita, itb)
+            pg, ig, nug = orc.rtr_chunk(k, t0, nt, pblk, xd, kind, ita, itb, nu0=3.0)
+            assert relerr(pg, pw) < 1e-9, (k, ck, relerr(pg, pw))
+            if kind != 6:
+                assert abs(ig[0] - iw[0]) <= 1e-10 * abs(iw[0])
+            assert abs(ig[1] - iw[1]) <= 1e-9 * abs(iw[1])
+            if kind != 4:
+                assert nug == nuw
+            # the same solve with the arithmetic of the product's kernels (per-baseline tensors,
+            # sagecal_b200/csrc/rtr_math.cuh) run on the CPU
+            pt, it, nut = orc.rtr_chunk(k, t0, nt, pblk, xd, kind, ita, itb, nu0=3.0, tensor=True)
+            assert relerr(pt, pw) < 1e-8, (k, ck, relerr(pt, pw))
+            assert abs(it[1] - iw[1]) <= 1e-8 * abs(iw[1])
+            if kind != 4:
+                assert nut == nuw
+
+
+@pytest.mark.parametrize("mode", [4, 5, 6])
+def test_sagefit_rtr_modes_match_reference(ref, refser, mode):
+    ref = ref if mode == 4 else refser
+    b = small_problem(N=10, M=3, tilesz=10, seed=64, outliers=0.02 if mode > 4 else 0.0,
+                      nchunk=[1, 2, 1])
+    pr = b.pr
+    orc = orcdirac.Oracle(pr)
+    kw = dict(max_emiter=3, max_iter=3, max_lbfgs=4, lbfgs_m=7, solver_mode=mode, randomize=0)
+    xr, ppr = pr.x.copy(), pr.pp0.copy()
+    rr = ref.sagefit_visibilities(pr.u, pr.v, pr.w, xr, pr.N, pr.Nbase, pr.tilesz, b.fresh_barr(),
+                                  b.sky, pr.coh, ppr, **kw)
+    xo, ppo = pr.x.copy(), pr.pp0.copy()
+    ro = orc.sagefit(xo, ppo, **kw)
+    assert ro[0] == rr[0]
+    assert abs(ro[1] - rr[1]) < 1e-9
+    assert abs(ro[2] - rr[2]) <= 1e-12 * rr[2]
+    assert relerr(ppo, ppr) < 1e-6, relerr(ppo, ppr)
+    assert abs(ro[3] - rr[3]) <= 1e-6 * rr[3]

@@ -73,6 +73,12 @@ def solve_args(name):
         a["solver_mode"] = 2
     elif name == "C3os":
         a["solver_mode"] = 3
+    elif name == "C2rtr":      # RSD + RTR per cluster (rtr_solve.c), plain LBFGS
+        a["solver_mode"] = 4
+    elif name == "C3rtr":      # robust RTR: the reference driver's default -j 5 (data.cpp:69)
+        a["solver_mode"] = 5
+    elif name == "C3nsd":      # Nesterov's accelerated descent
+        a["solver_mode"] = 6
     return a
 
 
@@ -98,8 +104,10 @@ def golden_parity(name, pr, pp, res):
 
 def workload_shape(name):
     from sagecal_b200 import synth
-    if name == "C3os":
+    if name in ("C3os", "C3rtr", "C3nsd"):
         name = "C3"
+    if name == "C2rtr":
+        name = "C2"
     if name in synth.CONFIGS:
         c = synth.CONFIGS[name]
         return dict(N=c["N"], M=c["M"], tilesz=c["tilesz"], radius=c["radius"], seed=c["seed"],
@@ -474,7 +482,7 @@ def run_workload(name, args, ctx, with_cpu=True):
         p1.record(stream)
         torch.cuda.synchronize()
         ms_profiled = p0.elapsed_time(p1) / K
-        prof = {k: api.profile_read(k) for k in range(9)}
+        prof = {k: api.profile_read(k) for k in range(11)}
         api.profile_enable(False)
     sweeps = SOLVE_W["max_emiter"] + ngrad
     units_step = R * M * sweeps
@@ -495,18 +503,22 @@ def run_workload(name, args, ctx, with_cpu=True):
             h2d = coh_h.nbytes + x_h.nbytes + pp_h.nbytes + R  # coherencies, data, Jones, flags
         d2h = x_h.nbytes + pp_h.nbytes
         with torch.cuda.stream(stream):
-            x_keep = np.array(x_h)
+            dropin = world == 1 and not devgen
+            # the drop-in entry point overwrites x with the residual (lmfit.c:1039-1040): its input
+            # is restored before every step; the device layer leaves x alone and writes the residual
+            # to a second pinned buffer
+            x_keep = np.array(x_h) if dropin else None
+            xo_t, xo = (None, None) if dropin else pinned(np.zeros_like(x_h))
 
             def one():
-                x_h[:] = x_keep
                 pp_h[:] = pr.pp0
-                if world == 1 and not devgen:
+                if dropin:
+                    x_h[:] = x_keep
                     return api.sagefit_visibilities(pr.u, pr.v, pr.w, x_h, pr.N, pr.Nbase,
                                                     pr.tilesz, barr, sky, coh_h, pp_h, **SOLVE_W)
                 # sharded / device-generated public path: upload (or generate) this rank's shard,
                 # solve, download, free
                 sp = make_resident()
-                xo = np.empty_like(x_keep)
                 rr = sp.sagefit(pp_h, xo, **SOLVE_W)
                 sp.close()
                 return rr
@@ -520,7 +532,8 @@ def run_workload(name, args, ctx, with_cpu=True):
                 one()
             f1.record(stream)
             torch.cuda.synchronize()
-            x_h[:] = x_keep
+            if dropin:
+                x_h[:] = x_keep
         te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -538,9 +551,10 @@ def run_workload(name, args, ctx, with_cpu=True):
     # ---------------- roofline of the dominant own kernel ----------------
     peak, peak_src = measured_peaks()
     names = ["k_predict_full", "k_grad_full", "k_cluster_pass", "k_coh_gram", "assemble",
-             "damped_solve", "k_weighted_jtj", "k_line_setup", "k_cluster_pass_addsub"]
+             "damped_solve", "k_weighted_jtj", "k_line_setup", "k_cluster_pass_addsub",
+             "k_rtr_stats", "k_rtr_eval"]
     shares = {}
-    for k in range(9):
+    for k in range(11):
         n, ms, by = prof[k]
         shares[names[k]] = {"launches_per_step": n / K, "ms_per_step": ms / K,
                             "share_of_step": (ms / K) / ms_profiled if ms_profiled else None,

@@ -47,6 +47,23 @@ typedef struct exinfo_gaussian_ {
   int use_projection;
 } exinfo_gaussian;
 
+/* src/lib/Dirac/Dirac_common.h:63-75 (exinfo_ring has the same layout) */
+typedef struct exinfo_disk_ {
+  double eX;
+  double cxi, sxi, cphi, sphi;
+  int use_projection;
+} exinfo_disk;
+
+/* src/lib/Dirac/Dirac_common.h:77-85 */
+typedef struct exinfo_shapelet_ {
+  int n0;        /* model order: n0*n0 modes */
+  double beta;   /* scale */
+  double *modes; /* n0*n0 coefficients */
+  double eX, eY, eP;
+  double cxi, sxi, cphi, sphi;
+  int use_projection;
+} exinfo_shapelet;
+
 #define STYPE_POINT 0    /* src/lib/Radio/Dirac_radio.h:71-75 */
 #define STYPE_GAUSSIAN 1
 #define STYPE_DISK 2
@@ -272,6 +289,10 @@ int sagefit_visibilities_admm_dual_pt_flt(double *u, double *v, double *w, doubl
 void dirac_b200_set_stream(void *stream);
 
 /* test / tuning switches; returns 0, or -1 for an unknown name.
+ *   "rtr_nu_unjoined"  robust RTR / NSD (solver_mode 5, 6): update nu as if the reference's worker
+ *               threads' partial sums, which it reads before joining the threads
+ *               (rtr_solve_robust.c:361-370), were all still zero -- what the threaded reference does
+ *               on most runs; default 0: the sums are complete, as the code was meant
  *   "cp_rows"   timeslots per CTA of the gradient-carrying cluster pass (0: one wave over the SMs);
  *               the parity tests use it to drive the multi-row TMA ring on small problems */
 int dirac_b200_set_option(const char *name, int value);
@@ -282,12 +303,19 @@ int dirac_b200_set_option(const char *name, int value);
  * path included; parity of the solved Jones is defined for runs where this stays 0. */
 long dirac_b200_noise_decisions(int reset);
 
+/* Device memory freed by dirac_b200_destroy is kept (up to a quarter of the device's memory,
+ * $DIRAC_B200_CACHE_GB overrides, 0 disables) and handed out again when a problem of the same shape
+ * is created: the driver calls tile after tile with the same sizes, and cudaMalloc / cudaFree of the
+ * coherencies alone cost 50-350 ms at 512 stations.  This returns all of it to the driver. */
+void dirac_b200_release_cache(void);
+
 /* number of kernels this library launched since load (bench.py's gpu_launches) */
 unsigned long long dirac_b200_launch_count(void);
 /* per-launch CUDA-event timing of the library's kernels on their launching stream.
  * kind: 0 full predict, 1 LBFGS gradient, 2 k_cluster_pass*, 3 k_coh_gram, 4 assembly, 5 damped solve
  * (k_chol_solve / k_tri_solve / batched potrf), 6 k_weighted_jtj, 7 line setup, 8 k_cluster_pass
- * without gradient (ADD / SUB / cost-only; kind 2 then counts the gradient-carrying INIT / TRIAL passes).  enable(1) clears the
+ * without gradient (ADD / SUB / cost-only; kind 2 then counts the gradient-carrying INIT / TRIAL passes),
+ * 9 k_rtr_stats (row condensation of the RTR / NSD solvers), 10 k_rtr_eval.  enable(1) clears the
  * records; read returns the launch count and sums the elapsed
  * milliseconds and the algorithmic bytes of the recorded launches of that kind. */
 unsigned long long dirac_b200_kernel_count(int kind); /* launches of `kind` since load */

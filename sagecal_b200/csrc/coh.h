@@ -8,14 +8,16 @@
 #define STYPE_RING_ 3
 #define STYPE_SHAPELET_ 4
 
-// one source, 192 bytes (multiple of 16: TMA bulk-copy granularity)
+// one source, 224 bytes (multiple of 16: TMA bulk-copy granularity)
 struct DevSource {
   double ll, mm, nn, sI, sQ, sU, sV, stype;
   double eX, eY, eP, cxi, sxi, cphi, sphi, use_projection;
   double sI0, sQ0, sU0, sV0, f0, spec_idx, spec_idx1, spec_idx2;
+  double sh_n0, sh_beta, sh_off, pad_;  // shapelets: order, scale, first coefficient in CohArgs::modes
 };
 
-#define COH_SEG_MAX 96  // sources staged per bulk copy (2 x 96 x 192 B = 36 KB of smem)
+#define COH_SEG_MAX 96  // sources staged per bulk copy (2 x 96 x 224 B = 42 KB of smem)
+#define COH_SHAPELET_MAX_N0 32  // largest shapelet order the device kernel takes
 
 // a run of <= COH_SEG_MAX sources of one cluster
 struct CohSegment {
@@ -28,6 +30,7 @@ struct CohSegment {
 struct CohArgs {
   const double *u, *v, *w;   // [R] seconds
   const DevSource *src;
+  const double *modes;       // shapelet coefficients of all sources, back to back (may be null)
   const CohSegment *segs;
   int nseg;
   const double *freqs;       // device, [Nchan]

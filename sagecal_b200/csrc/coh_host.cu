@@ -10,12 +10,14 @@
 
 struct SkyDev {
   DevSource *src;
+  double *modes;
   CohSegment *segs;
   int nseg;
 };
 
 static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream_t st) {
   std::vector<DevSource> src;
+  std::vector<double> modes;
   std::vector<CohSegment> segs;
   for (int k = 0; k < M; k++) {
     const clus_source_t &c = carr[k];
@@ -26,9 +28,19 @@ static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream
       d.ll = c.ll[s]; d.mm = c.mm[s]; d.nn = c.nn[s];
       d.sI = c.sI[s]; d.sQ = c.sQ[s]; d.sU = c.sU[s]; d.sV = c.sV[s];
       d.stype = (double)c.stype[s];
-      if (c.stype[s] == STYPE_SHAPELET) {
-        fprintf(stderr, "dirac_b200: shapelet sources are not supported by the device "
-                        "coherency kernel (cluster %d source %d)\n", k, s);
+      if (c.stype[s] == STYPE_SHAPELET && c.ex && c.ex[s]) {
+        const exinfo_shapelet *g = (const exinfo_shapelet *)c.ex[s];
+        if (g->n0 < 1 || g->n0 > COH_SHAPELET_MAX_N0) {
+          fprintf(stderr, "dirac_b200: shapelet order %d of cluster %d source %d is outside 1..%d\n",
+                  g->n0, k, s, COH_SHAPELET_MAX_N0);
+          exit(1);
+        }
+        d.eX = g->eX; d.eY = g->eY; d.eP = g->eP; d.cxi = g->cxi; d.sxi = g->sxi;
+        d.cphi = g->cphi; d.sphi = g->sphi; d.use_projection = (double)g->use_projection;
+        d.sh_n0 = (double)g->n0; d.sh_beta = g->beta; d.sh_off = (double)modes.size();
+        modes.insert(modes.end(), g->modes, g->modes + (size_t)g->n0 * g->n0);
+      } else if (c.stype[s] == STYPE_SHAPELET) {
+        fprintf(stderr, "dirac_b200: shapelet source without exinfo (cluster %d source %d)\n", k, s);
         exit(1);
       }
       if (c.stype[s] == STYPE_GAUSSIAN && c.ex && c.ex[s]) {
@@ -64,6 +76,10 @@ static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream
     } while (done < c.N);
   }
   if (src.empty()) src.resize(1);
+  if (modes.empty()) modes.resize(2, 0.0);
+  DB_CHECK(cudaMalloc((void **)&sky->modes, sizeof(double) * modes.size()));
+  DB_CHECK(cudaMemcpyAsync(sky->modes, modes.data(), sizeof(double) * modes.size(),
+                           cudaMemcpyHostToDevice, st));
   DB_CHECK(cudaMalloc((void **)&sky->src, sizeof(DevSource) * src.size()));
   DB_CHECK(cudaMalloc((void **)&sky->segs, sizeof(CohSegment) * segs.size()));
   DB_CHECK(cudaMemcpyAsync(sky->src, src.data(), sizeof(DevSource) * src.size(),
@@ -76,6 +92,7 @@ static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream
 
 static void sky_free(SkyDev *sky) {
   cudaFree(sky->src);
+  cudaFree(sky->modes);
   cudaFree(sky->segs);
 }
 
@@ -99,7 +116,7 @@ extern "C" void dirac_b200_precalculate(dirac_b200_problem *pr, const double *u,
   double *df = upload_doubles(&freq0, 1, d.stream);
   CohArgs a;
   memset(&a, 0, sizeof(a));
-  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.segs = sky.segs; a.nseg = sky.nseg;
+  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.modes = sky.modes; a.segs = sky.segs; a.nseg = sky.nseg;
   a.freqs = df; a.Nchan = 1; a.fdelta2 = fdelta * 0.5; a.uvmin = uvmin; a.uvmax = uvmax;
   a.R = d.R; a.coh = d.coh; a.flag = d.flag; a.xout = nullptr;
   db_launch_coherencies(&a, d.stream);
@@ -146,7 +163,7 @@ extern "C" int precalculate_coherencies(double *u, double *v, double *w, double 
   DB_CHECK(cudaMalloc((void **)&dcoh, sizeof(double2) * (size_t)M * 4 * R));
   CohArgs a;
   memset(&a, 0, sizeof(a));
-  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.segs = sky.segs; a.nseg = sky.nseg;
+  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.modes = sky.modes; a.segs = sky.segs; a.nseg = sky.nseg;
   a.freqs = df; a.Nchan = 1; a.fdelta2 = fdelta * 0.5; a.uvmin = uvmin; a.uvmax = uvmax;
   a.R = R; a.coh = dcoh; a.flag = dflag; a.xout = nullptr;
   db_launch_coherencies(&a, st);
@@ -206,7 +223,7 @@ extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, d
   }
   CohArgs a;
   memset(&a, 0, sizeof(a));
-  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.segs = sky.segs; a.nseg = sky.nseg;
+  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.modes = sky.modes; a.segs = sky.segs; a.nseg = sky.nseg;
   a.freqs = df; a.Nchan = Nchan; a.fdelta2 = (fdelta / (double)Nchan) * 0.5;
   a.R = R; a.xout = dx;
   db_launch_predict_multifreq(&a, st);
@@ -313,7 +330,7 @@ extern "C" int calculate_residuals_multifreq(double *u, double *v, double *w, do
   DB_CHECK(cudaMemcpyAsync(dx, x, sizeof(double2) * nx, cudaMemcpyHostToDevice, st));
   CohArgs a;
   memset(&a, 0, sizeof(a));
-  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.segs = sky.segs; a.nseg = sky.nseg;
+  a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.modes = sky.modes; a.segs = sky.segs; a.nseg = sky.nseg;
   a.freqs = df; a.Nchan = Nchan; a.fdelta2 = (fdelta / (double)Nchan) * 0.5;
   a.R = R; a.xout = dx; a.sta1 = ds1; a.sta2 = ds2; a.p = dp; a.clus_nchunk = dn;
   a.clus_chunk0 = dc0; a.chunk_poff = dpo; a.clus_sub = dsub; a.pinv = dpinv;

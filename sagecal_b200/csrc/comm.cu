@@ -200,6 +200,29 @@ void db_stream_sync(cudaStream_t st) {
   g_wait_seconds += now_s() - t0;
   g_wait_calls++;
 }
+// wait until a kernel's last CTA has published `epoch` in host-mapped memory (its results, written
+// to the same mapping before a system-wide fence, are then visible).  The stream is polled now and
+// then so that a failed launch ends in the usual error exit instead of an endless spin.
+void db_flag_wait(const volatile unsigned long long *flag, unsigned long long epoch,
+                  cudaStream_t st) {
+  const double t0 = now_s();
+  unsigned spins = 0;
+  while (*flag != epoch) {
+    if ((++spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {
+        if (*flag != epoch) {  // kernel done without publishing: cannot happen, do not spin on it
+          fprintf(stderr, "dirac_b200: result flag not published\n");
+          exit(1);
+        }
+      } else if (e != cudaErrorNotReady) {
+        DB_CHECK(e);
+      }
+    }
+  }
+  g_wait_seconds += now_s() - t0;
+  g_wait_calls++;
+}
 void db_event_sync(cudaEvent_t ev) {
   const double t0 = now_s();
   DB_CHECK(cudaEventSynchronize(ev));

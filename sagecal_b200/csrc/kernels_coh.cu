@@ -15,8 +15,63 @@
 
 // ---- per-source term ------------------------------------------------------------------------------
 // phase * |sinc| smearing * shape factor for one source at one frequency (predict.c:411-470)
-__device__ __forceinline__ double2 source_phase(const DevSource &s, double u, double v, double w,
-                                                double freq, double fdelta2) {
+// Fourier-plane value of a shapelet source (shapelet_contrib + calculate_uv_mode_vectors_scalar,
+// shapelet.c:50-190): sum over the n0 x n0 modes of coeff * phi_n1(-ut beta) phi_n2(vt beta), odd
+// n1+n2 imaginary, phi_n(x) = H_n(x) exp(-x^2/2) / sqrt(2^(n+1) n!), times 2 pi / (eX eY)
+__device__ __noinline__ double2 shapelet_factor(const DevSource &s, const double *modes, double uf,
+                                                double vf, double wf) {
+  double up, vp;
+  if (s.use_projection != 0.0) {
+    up = -uf * s.cxi + vf * s.cphi * s.sxi - wf * s.sphi * s.sxi;
+    vp = -uf * s.sxi - vf * s.cphi * s.cxi + wf * s.sphi * s.cxi;
+  } else {
+    up = uf;
+    vp = vf;
+  }
+  const double a = 1.0 / s.eX, b = 1.0 / s.eY;
+  double sph, cph;
+  sincos(s.eP, &sph, &cph);
+  const double ut = a * (cph * up - sph * vp);
+  const double vt = b * (sph * up + cph * vp);
+  const int n0 = (int)s.sh_n0;
+  double bu[COH_SHAPELET_MAX_N0], bv[COH_SHAPELET_MAX_N0];
+#pragma unroll 1
+  for (int side = 0; side < 2; side++) {
+    const double x = (side == 0 ? -ut : vt) * s.sh_beta;
+    const double ex = exp(-0.5 * x * x);
+    double *bb = side == 0 ? bu : bv;
+    double hm2 = 1.0, hm1 = 2.0 * x, fact = 1.0, p2 = 2.0;  // H_0, H_1, n!, 2^(n+1)
+    for (int n = 0; n < n0; n++) {
+      double h;
+      if (n == 0) h = 1.0;
+      else if (n == 1) h = hm1;
+      else {
+        h = 2.0 * x * hm1 - 2.0 * (double)(n - 1) * hm2;
+        hm2 = hm1;
+        hm1 = h;
+      }
+      if (n > 0) fact *= (double)n;
+      bb[n] = h * ex / sqrt(p2 * fact);
+      p2 *= 2.0;
+    }
+  }
+  const double *md = modes + (long long)s.sh_off;
+  double re = 0.0, im = 0.0;
+  for (int n2 = 0; n2 < n0; n2++)
+    for (int n1 = 0; n1 < n0; n1++) {
+      const int odd = (n1 + n2) & 1;
+      const int sg = (((n1 + n2 - odd) / 2) & 1) ? -1 : 1;
+      const double av = (sg < 0 ? -bu[n1] : bu[n1]) * bv[n2];
+      const double c = md[n2 * n0 + n1] * av;
+      if (odd) im += c;
+      else re += c;
+    }
+  const double sc = 2.0 * M_PI * a * b;
+  return make_double2(sc * re, sc * im);
+}
+
+__device__ __forceinline__ double2 source_phase(const DevSource &s, const double *modes, double u,
+                                                double v, double w, double freq, double fdelta2) {
   const double G = 2.0 * M_PI * (u * s.ll + v * s.mm + w * s.nn);
   double sp, cp;
   sincos(G * freq, &sp, &cp);
@@ -27,7 +82,10 @@ __device__ __forceinline__ double2 source_phase(const DevSource &s, double u, do
   }
   double2 ph = make_double2(cp * fac, sp * fac);
   const int st = (int)s.stype;
-  if (st != STYPE_POINT_) {
+  if (st == STYPE_SHAPELET_) {
+    const double2 sf = shapelet_factor(s, modes, u * freq, v * freq, w * freq);
+    ph = make_double2(ph.x * sf.x - ph.y * sf.y, ph.x * sf.y + ph.y * sf.x);
+  } else if (st != STYPE_POINT_) {
     const double uf = u * freq, vf = v * freq, wf = w * freq;
     double up, vp;
     if (st == STYPE_GAUSSIAN_ && s.use_projection == 0.0) {
@@ -142,7 +200,7 @@ k_sky_predict(CohArgs a) {
       if (active) {
         for (int s = 0; s < sg.count; s++) {
           const DevSource &S = sbuf[b][s];
-          const double2 ph = source_phase(S, u, v, w, freq, a.fdelta2);
+          const double2 ph = source_phase(S, a.modes, u, v, w, freq, a.fdelta2);
           double I = S.sI, Q = S.sQ, U = S.sU, V = S.sV;
           if (MODE >= 1 && S.spec_idx != 0.0) {
             const double fr = log(freq / S.f0);

@@ -78,14 +78,13 @@ __global__ void k_rtr_reduce(const double *in, double *out, size_t n, int ns) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_rtr_eval: warp = station s, lanes = the other stations o.  o > s: baseline (s,o), s plays p;
-// o < s: baseline (o,s), s plays q.  Every baseline is visited from both ends: no atomics, and the
-// sums are bit-reproducible.
+// k_rtr_eval: CTA = station s, threads = the other stations o (one baseline per thread up to 257
+// stations, a short loop beyond).  o > s: baseline (s,o), s plays p; o < s: baseline (o,s), s plays q.
+// Every baseline is visited from both ends: no atomics, and the sums are bit-reproducible.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rtr_eval(RtrEvalArgs a) {
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (s >= a.N) return;
+__global__ void __launch_bounds__(256) k_rtr_eval(RtrEvalArgs a) {
+  const int s = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   double2 Gs[4], Es[4];
   load_jones(a.x, s, Gs);
   const bool hess = a.eta != nullptr;
@@ -94,7 +93,7 @@ __global__ void __launch_bounds__(128) k_rtr_eval(RtrEvalArgs a) {
 #pragma unroll
   for (int i = 0; i < 4; i++) acc[i] = make_double2(0, 0);
   double cost = 0.0, cnt = 0.0;
-  for (int o = lane; o < a.N; o += 32) {
+  for (int o = threadIdx.x; o < a.N; o += blockDim.x) {
     if (o == s) continue;
     const bool sp = s < o;  // s plays p
     const int p = sp ? s : o, q = sp ? o : s;
@@ -113,23 +112,44 @@ __global__ void __launch_bounds__(128) k_rtr_eval(RtrEvalArgs a) {
     rtr_eval_baseline(sp, Gs, Go, Es, Eo, T, W, a.sc[b], hess, a.cost != nullptr,
                       a.out != nullptr, acc, &cost);
   }
-  if (a.out) {
+  // 10 sums per station: warp butterflies, then the warps' partials in order through shared memory
+  __shared__ double part[8][10];
+  double v[10] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y,
+                  cost, cnt};
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const double re = warp_sum(acc[i].x), im = warp_sum(acc[i].y);
-      if (lane == 0) {
-        a.out[8 * (size_t)s + 2 * i] = re;
-        a.out[8 * (size_t)s + 2 * i + 1] = im;
-      }
+  for (int i = 0; i < 10; i++) {
+    v[i] = warp_sum(v[i]);
+    if (lane == 0) part[warp][i] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double t = 0.0;
+    for (int w = 0; w < nwarp; w++) t += part[w][threadIdx.x];
+    const int i = threadIdx.x;
+    if (i < 8) {
+      if (a.out) a.out[8 * (size_t)s + i] = t;
+    } else if (i == 8) {
+      if (a.cost) a.cost[s] = t;
+    } else if (a.count) {
+      a.count[s] = t;
     }
+    if (a.flag) __threadfence_system();
   }
-  if (a.cost) {
-    cost = warp_sum(cost);
-    if (lane == 0) a.cost[s] = cost;
-  }
-  if (a.count) {
-    cnt = warp_sum(cnt);
-    if (lane == 0) a.count[s] = cnt;
+  if (a.flag) {
+    // publish: every CTA's results are fenced out to the host before it checks in; the last one in
+    // raises the flag
+    __shared__ unsigned int last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      last = (atomicAdd(a.arrive, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+      *a.arrive = 0u;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned long long *>(a.flag) = a.epoch;
+    }
   }
 }
 
@@ -157,7 +177,9 @@ void db_launch_rtr_reduce(const double *in, double *out, size_t n, int ns, cudaS
   k_rtr_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, ns);
 }
 void db_launch_rtr_eval(const RtrEvalArgs *a, cudaStream_t st) {
-  k_rtr_eval<<<(a->N + 3) / 4, 128, 0, st>>>(*a);
+  int nwarp = (a->N + 31) / 32;  // one baseline per thread where a CTA can hold them
+  if (nwarp > 8) nwarp = 8;
+  k_rtr_eval<<<a->N, 32 * nwarp, 0, st>>>(*a);
 }
 void db_launch_rtr_plane_sum(const double *sc, int Nbase, int which, double *dst, cudaStream_t st) {
   k_rtr_plane_sum<<<1, 256, 0, st>>>(sc, Nbase, which, dst);

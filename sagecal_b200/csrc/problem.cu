@@ -108,14 +108,36 @@ static void require_gpu() {
 // ---- caching device allocator ---------------------------------------------------------------------
 // The drop-in entry points build and tear down a resident problem per call, like the reference
 // (lmfit.c:831-1046 allocates and frees every scratch vector per call).  cudaMalloc/cudaFree of GBs
-// cost milliseconds and serialise the device, so freed blocks are kept and handed out again when a
-// request of exactly the same size comes back (the driver calls with the same shapes tile after
-// tile).  Bounded: blocks above 2 GiB and anything beyond 6 GiB of cache go back to the driver.
+// cost milliseconds to hundreds of milliseconds (32 GB of coherencies at 512 stations: 50-350 ms
+// measured) and serialise the device, so freed blocks are kept and handed out again when a request
+// of exactly the same size comes back (the driver calls with the same shapes tile after tile).
+// Bounded: the cache holds at most a quarter of the device's memory ($DIRAC_B200_CACHE_GB overrides,
+// 0 disables); a failed cudaMalloc gives the whole cache back and retries once;
+// dirac_b200_release_cache() empties it on request.
 #include <map>
 #include <unordered_map>
 static std::multimap<size_t, void *> g_free_blocks;
 static std::unordered_map<void *, size_t> g_live_blocks;
 static size_t g_cached_bytes = 0;
+static size_t cache_cap() {
+  static size_t cap = (size_t)-1;
+  if (cap == (size_t)-1) {
+    const char *e = getenv("DIRAC_B200_CACHE_GB");
+    if (e) {
+      cap = (size_t)(atof(e) * 1073741824.0);
+    } else {
+      size_t fr = 0, tot = 0;
+      cap = (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ? tot / 4 : ((size_t)6 << 30);
+    }
+  }
+  return cap;
+}
+static void cache_release_all() {
+  for (auto &kv : g_free_blocks) cudaFree(kv.second);
+  g_free_blocks.clear();
+  g_cached_bytes = 0;
+}
+extern "C" void dirac_b200_release_cache(void) { cache_release_all(); }
 void *db_malloc(size_t bytes) {
   bytes = (bytes + 255) & ~(size_t)255;
   auto it = g_free_blocks.find(bytes);
@@ -128,9 +150,7 @@ void *db_malloc(size_t bytes) {
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {  // give the cache back and retry once
       cudaGetLastError();
-      for (auto &kv : g_free_blocks) cudaFree(kv.second);
-      g_free_blocks.clear();
-      g_cached_bytes = 0;
+      cache_release_all();
       DB_CHECK(cudaMalloc(&p, bytes));
     }
   }
@@ -146,7 +166,7 @@ void db_free(void *p) {
   }
   const size_t bytes = it->second;
   g_live_blocks.erase(it);
-  if (bytes > ((size_t)2 << 30) || g_cached_bytes + bytes > ((size_t)6 << 30)) {
+  if (g_cached_bytes + bytes > cache_cap()) {
     cudaFree(p);
   } else {
     g_free_blocks.insert({bytes, p});

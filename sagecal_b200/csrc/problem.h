@@ -85,6 +85,8 @@ struct dirac_b200_problem {
 // host waits on the device, timed (dirac_b200_host_stats): where the host-driven solver idles
 void db_stream_sync(cudaStream_t st);
 void db_event_sync(cudaEvent_t ev);
+void db_flag_wait(const volatile unsigned long long *flag, unsigned long long epoch,
+                  cudaStream_t st);
 void *db_malloc(size_t bytes);
 void db_free(void *p);
 void db_count_launch(int n);

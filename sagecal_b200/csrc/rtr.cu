@@ -31,6 +31,10 @@ struct RtrWork {
   double *xdev, *edev;    // [8N] each
   double *outdev;         // [8N | N | N | 4]
   double *h;              // pinned: x [8N], eta [8N], out [8N + 2N + 4]
+  // mailbox of k_rtr_eval: results and completion flag in host-mapped memory
+  double *mbox, *mbox_dev;              // [8N | N | N | flag]
+  unsigned int *arrive;                 // device
+  unsigned long long epoch;
 };
 
 static RtrWork *rtr_init(dirac_b200_problem *pr) {
@@ -55,6 +59,13 @@ static RtrWork *rtr_init(dirac_b200_problem *pr) {
   w->edev = (double *)db_malloc(sizeof(double) * n8);
   w->outdev = (double *)db_malloc(sizeof(double) * (n8 + 2 * d.N + 8));
   DB_CHECK(cudaMallocHost((void **)&w->h, sizeof(double) * (3 * n8 + 2 * d.N + 16)));
+  DB_CHECK(cudaHostAlloc((void **)&w->mbox, sizeof(double) * (n8 + 2 * d.N + 16),
+                         cudaHostAllocMapped));
+  DB_CHECK(cudaHostGetDevicePointer((void **)&w->mbox_dev, w->mbox, 0));
+  memset(w->mbox, 0, sizeof(double) * (n8 + 2 * d.N + 16));
+  w->arrive = (unsigned int *)db_malloc(256);
+  DB_CHECK(cudaMemsetAsync(w->arrive, 0, 256, d.stream));
+  w->epoch = 0;
   pr->rtr = w;
   return w;
 }
@@ -66,6 +77,8 @@ void db_rtr_free(dirac_b200_problem *pr) {
   if (w->TDpart) { db_free(w->TDpart); db_free(w->scpart); }
   db_free(w->xdev); db_free(w->edev); db_free(w->outdev);
   cudaFreeHost(w->h);
+  cudaFreeHost(w->mbox);
+  db_free(w->arrive);
   delete w;
   pr->rtr = nullptr;
 }
@@ -78,6 +91,7 @@ struct RtrDevEval {
   RtrWork *w;
   int k, t0, t1, N, n8;
   long long nrows;            // rows of the chunk, flagged ones included (the reference's M)
+  std::vector<double> x_on_dev;  // the Jones w->xdev holds (empty: unknown)
 
   // condense the rows of the chunk.  xw != null: Student's-t row weights at xw with nu; returns
   // sum(log w - w) then
@@ -90,9 +104,7 @@ struct RtrDevEval {
     a.blpq = d.blpq;
     a.xw = nullptr;
     if (xw_host) {
-      memcpy(w->h, xw_host, sizeof(double) * n8);
-      DB_CHECK(cudaMemcpyAsync(w->xdev, w->h, sizeof(double) * n8, cudaMemcpyHostToDevice,
-                               d.stream));
+      upload_x(xw_host);
       a.xw = w->xdev;
     }
     a.nu = nu;
@@ -125,30 +137,44 @@ struct RtrDevEval {
     return w->h[2 * n8];
   }
 
+  // the Jones go up only when they changed: every Hessian-vector product of one truncated-CG run
+  // is taken at the same point (every call ends with a stream synchronisation, so the pinned staging
+  // buffer is free again)
+  void upload_x(const double *x) {
+    if (x_on_dev.size() == (size_t)n8 && !memcmp(x_on_dev.data(), x, sizeof(double) * n8)) return;
+    memcpy(w->h, x, sizeof(double) * n8);
+    DB_CHECK(cudaMemcpyAsync(w->xdev, w->h, sizeof(double) * n8, cudaMemcpyHostToDevice,
+                             pr->d.stream));
+    x_on_dev.assign(x, x + n8);
+  }
+
   // one launch of k_rtr_eval
   void launch(const double *x, const double *eta, double *fcost, double *vec, double *cnt) {
     DevProblem &d = pr->d;
-    double *hx = w->h, *he = w->h + n8, *ho = w->h + 2 * n8;
-    memcpy(hx, x, sizeof(double) * n8);
-    DB_CHECK(cudaMemcpyAsync(w->xdev, hx, sizeof(double) * n8, cudaMemcpyHostToDevice, d.stream));
+    double *he = w->h + n8;
+    upload_x(x);
     if (eta) {
       memcpy(he, eta, sizeof(double) * n8);
       DB_CHECK(cudaMemcpyAsync(w->edev, he, sizeof(double) * n8, cudaMemcpyHostToDevice,
                                d.stream));
     }
+    // results come back through the mailbox: no device-to-host copy, no stream synchronisation
     RtrEvalArgs a;
     a.TD = w->TD; a.sc = w->sc; a.x = w->xdev; a.eta = eta ? w->edev : nullptr;
-    a.out = vec ? w->outdev : nullptr;
-    a.cost = fcost ? w->outdev + n8 : nullptr;
-    a.count = cnt ? w->outdev + n8 + N : nullptr;
+    a.out = vec ? w->mbox_dev : nullptr;
+    a.cost = fcost ? w->mbox_dev + n8 : nullptr;
+    a.count = cnt ? w->mbox_dev + n8 + N : nullptr;
     a.N = N; a.Nbase = d.Nbase;
+    a.arrive = w->arrive;
+    a.flag = reinterpret_cast<unsigned long long *>(w->mbox_dev + n8 + 2 * N + 2);
+    a.epoch = ++w->epoch;
     db_prof_begin(10, 2.0 * d.Nbase * (512.0 + 24.0), d.stream);
     db_launch_rtr_eval(&a, d.stream);
     db_prof_end(d.stream);
     db_count_launch(1);
-    DB_CHECK(cudaMemcpyAsync(ho, w->outdev, sizeof(double) * (n8 + 2 * N), cudaMemcpyDeviceToHost,
-                             d.stream));
-    db_stream_sync(d.stream);
+    db_flag_wait(reinterpret_cast<volatile unsigned long long *>(w->mbox + n8 + 2 * N + 2),
+                 a.epoch, d.stream);
+    const double *ho = w->mbox;
     if (vec) memcpy(vec, ho, sizeof(double) * n8);
     if (fcost) {
       double s = 0.0;

@@ -26,6 +26,12 @@ struct RtrEvalArgs {
   double *cost;               // [N] per-station partial costs, may be null
   double *count;              // [N] unflagged rows per station, may be null
   int N, Nbase;
+  // mailbox: out / cost / count point into HOST-mapped memory; the last CTA to finish publishes
+  // `epoch` in *flag (also host-mapped) after a system-wide fence, the host spins on it instead of
+  // waiting for a device-to-host copy and a stream synchronisation
+  unsigned int *arrive;       // device counter, zero between launches
+  unsigned long long *flag;   // null: no mailbox
+  unsigned long long epoch;
 };
 
 extern "C" {

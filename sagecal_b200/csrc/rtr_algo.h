@@ -299,6 +299,7 @@ static void tr_loop(Ops<EV> &E, double *x, double &fx, double *fgradx, double *e
   int k = 0;
   int stop_outer = (itmax_rtr > 0 ? 0 : 1);
   double norm_grad = 0.0;
+  std::vector<double> gprop(n);
   if (!stop_outer) {
     E.fgrad(x, fgradx, true);
     norm_grad = sqrt(rtr_g(n, fgradx, fgradx));
@@ -310,7 +311,11 @@ static void tr_loop(Ops<EV> &E, double *x, double &fx, double *fgradx, double *e
     const int stop_inner =
         tcg_solve(E, x, fgradx, eta, Heta, Delta, theta, kappa, max_inner, min_inner);
     for (int i = 0; i < n; i++) x_prop[i] = x[i] + eta[i];
-    const double fx_prop = E.f(x_prop);
+    // the gradient at the proposal rides along with its cost (one evaluation instead of two when the
+    // step is accepted, which is the usual case; the reference evaluates them separately,
+    // rtr_solve.c:1436,1530)
+    double fx_prop;
+    E.fgrad(x_prop, gprop.data(), true, &fx_prop);
     double rhonum = fx - fx_prop;
     double rhoden = -rtr_g(n, fgradx, eta) - 0.5 * rtr_g(n, Heta, eta);
     const double rho_reg = std::max(1.0, fx) * rho_regularization;
@@ -326,7 +331,7 @@ static void tr_loop(Ops<EV> &E, double *x, double &fx, double *fgradx, double *e
     if (model_decreased && rho > rho_prime) {
       memcpy(x, x_prop, sizeof(double) * n);
       fx = fx_prop;
-      E.fgrad(x, fgradx, true);
+      memcpy(fgradx, gprop.data(), sizeof(double) * n);
       norm_grad = sqrt(rtr_g(n, fgradx, fgradx));
     }
     if (norm_grad < epsilon && k > min_outer) stop_outer = 1;

@@ -63,6 +63,20 @@ class exinfo_gaussian(C.Structure):
                 ("sphi", C.c_double), ("use_projection", C.c_int)]
 
 
+class exinfo_disk(C.Structure):
+    """Dirac_common.h exinfo_disk / exinfo_ring (same layout)."""
+    _fields_ = [("eX", C.c_double), ("cxi", C.c_double), ("sxi", C.c_double),
+                ("cphi", C.c_double), ("sphi", C.c_double), ("use_projection", C.c_int)]
+
+
+class exinfo_shapelet(C.Structure):
+    """Dirac_common.h exinfo_shapelet — n0 x n0 shapelet modes."""
+    _fields_ = [("n0", C.c_int), ("beta", C.c_double), ("modes", C.POINTER(C.c_double)),
+                ("eX", C.c_double), ("eY", C.c_double), ("eP", C.c_double),
+                ("cxi", C.c_double), ("sxi", C.c_double), ("cphi", C.c_double),
+                ("sphi", C.c_double), ("use_projection", C.c_int)]
+
+
 assert C.sizeof(baseline_t) == 12
 
 
@@ -113,6 +127,22 @@ class SkyModel:
                         g = exinfo_gaussian(*[float(v) for v in gauss[s][:7]], int(gauss[s][7]))
                         self._keep.append(g)
                         ex[s] = C.cast(C.pointer(g), C.c_void_p)
+            # disks / rings: cl["disk"][s] = (eX, cxi, sxi, cphi, sphi, use_projection);
+            # shapelets: cl["shapelet"][s] = dict(n0, beta, modes, eX, eY, eP[, cxi, sxi, cphi, sphi,
+            # use_projection])
+            for s_, g_ in (cl.get("disk") or {}).items():
+                g = exinfo_disk(*[float(v) for v in g_[:5]], int(g_[5]))
+                self._keep.append(g)
+                ex[s_] = C.cast(C.pointer(g), C.c_void_p)
+            for s_, g_ in (cl.get("shapelet") or {}).items():
+                modes = np.ascontiguousarray(g_["modes"], dtype=np.float64)
+                assert modes.size == g_["n0"] ** 2
+                g = exinfo_shapelet(int(g_["n0"]), float(g_["beta"]), dptr(modes), float(g_["eX"]),
+                                    float(g_["eY"]), float(g_["eP"]), float(g_.get("cxi", 1.0)),
+                                    float(g_.get("sxi", 0.0)), float(g_.get("cphi", 1.0)),
+                                    float(g_.get("sphi", 0.0)), int(g_.get("use_projection", 0)))
+                self._keep.extend([modes, g])
+                ex[s_] = C.cast(C.pointer(g), C.c_void_p)
             self._keep.append(ex)
             cs.ex = C.cast(ex, C.POINTER(C.c_void_p))
             nchunk = int(cl.get("nchunk", 1))

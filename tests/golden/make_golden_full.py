@@ -7,7 +7,7 @@ C2/C3 shape by tests/test_oracle_c2r.py.  Stored: solved Jones, scalars, input f
 inputs are regenerated from the seed (sagecal_b200.synth.make_config).  bench.py compares the
 solution of its first warm-up step with these (the `parity` object of the bench line).
 
-    python tests/golden/make_golden_full.py C2 | C3 | C3os
+    python tests/golden/make_golden_full.py C2 | C3 | C3os | C2rtr | C3rtr | C3nsd
 """
 import os
 import sys
@@ -21,7 +21,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "full")
 SOLVE = dict(max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, linsolv=0, nulow=2.0, nuhigh=30.0)
-CASES = {"C2": ("C2", 1), "C3": ("C3", 2), "C3os": ("C3", 3)}
+CASES = {"C2": ("C2", 1), "C3": ("C3", 2), "C3os": ("C3", 3),
+         # RTR family (oracle/rtr_harness.cpp: rtr_algo.h on the per-row evaluators)
+         "C2rtr": ("C2", 4), "C3rtr": ("C3", 5), "C3nsd": ("C3", 6)}
 
 
 def fingerprint(pr):

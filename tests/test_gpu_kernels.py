@@ -137,6 +137,61 @@ def test_coherencies_device(api, ref):
     assert np.array_equal(barr_to_numpy(barr1, pr.Nbase1)[2], barr_to_numpy(barr3, pr.Nbase1)[2])
 
 
+def _extended_sky(pr, seed=5):
+    """turn some sources of a problem's clusters into disks, rings and shapelets (orders 1-9, with
+    and without the projection to the source's tangent plane)"""
+    rng = np.random.default_rng(seed)
+    cnt = 0
+    for k, cl in enumerate(pr.clusters):
+        K = len(cl["ll"])
+        st = np.array(cl.get("stype", np.zeros(K)), dtype=np.uint8)
+        disk, shp = {}, {}
+        for s in range(K):
+            if st[s] != 0:
+                continue
+            kind = cnt % 4  # point, disk, ring, shapelet in turn
+            cnt += 1
+            xi, phi = rng.uniform(0, 2 * np.pi), rng.uniform(0, 0.2)
+            proj = (np.cos(xi), np.sin(xi), np.cos(phi), np.sin(phi))
+            if kind in (1, 2):
+                st[s] = 1 + kind  # disk / ring
+                disk[s] = (np.deg2rad(rng.uniform(1.0, 4.0) / 60.0),) + proj + (1,)
+            elif kind == 3:
+                st[s] = 4
+                n0 = int(rng.integers(1, 10))
+                shp[s] = dict(n0=n0, beta=np.deg2rad(rng.uniform(0.5, 2.0) / 60.0),
+                              modes=rng.normal(0, 1, n0 * n0) / n0, eX=rng.uniform(0.7, 1.5),
+                              eY=rng.uniform(0.7, 1.5), eP=rng.uniform(0, np.pi), cxi=proj[0],
+                              sxi=proj[1], cphi=proj[2], sphi=proj[3], use_projection=int(s % 2))
+        cl["stype"] = st
+        cl["disk"] = disk
+        cl["shapelet"] = shp
+    from sagecal_b200.dirac_api import SkyModel
+    return SkyModel(pr.clusters, pr.N)
+
+
+def test_coherencies_extended_sources(api, ref):
+    """disks, rings and shapelets (shapelet.c:50-190) in the device coherency kernel"""
+    b = small_problem(N=10, M=4, tilesz=4, seed=23, kmean=6.0, gaussian_frac=0.3)
+    pr = b.pr
+    sky = _extended_sky(pr)
+    ntypes = set(int(t) for cl in pr.clusters for t in cl["stype"])
+    assert ntypes >= {0, 2, 3, 4}
+    want = ref.precalculate_coherencies(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, b.fresh_barr(), sky,
+                                        pr.freq0, pr.fdelta, uvmin=30.0, uvmax=1e5)
+    got = api.precalculate_coherencies(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, b.fresh_barr(), sky,
+                                       pr.freq0, pr.fdelta, uvmin=30.0, uvmax=1e5)
+    assert relerr(got, want) < 1e-11
+    freqs = np.array([146e6, 152e6])
+    xa = np.zeros(8 * pr.Nbase1 * len(freqs))
+    xb = xa.copy()
+    ref.predict_visibilities_multifreq(pr.u, pr.v, pr.w, xa, pr.N, pr.Nbase, pr.tilesz, b.barr, sky,
+                                       freqs, pr.fdelta * 2, add_to_data=1)
+    api.predict_visibilities_multifreq(pr.u, pr.v, pr.w, xb, pr.N, pr.Nbase, pr.tilesz, b.barr, sky,
+                                       freqs, pr.fdelta * 2, add_to_data=1)
+    assert relerr(xb, xa) < 1e-11
+
+
 @pytest.mark.parametrize("add", [1, 2, 0])  # SIMUL_ONLY=1 clears, others accumulate
 def test_predict_multifreq(api, ref, add):
     b = small_problem(N=10, M=3, tilesz=5, seed=22, kmean=2.0, gaussian_frac=0.3)

@@ -142,26 +142,6 @@ def test_hybrid_uneven_chunks_match_reference(api, ref, name, prob, args):
     assert abs(rr[3] - rg[3]) <= 1e-5 * rr[3]
 
 
-def test_rtr_modes_are_mapped_not_fatal(api):
-    """solver_mode 4-6 (RTR/NSD, the driver's default -j 5) must not kill the host process: they
-    run the LM-family mode of the same noise model"""
-    b = small_problem(N=8, M=2, tilesz=10, seed=95, outliers=0.02)
-    pr = b.pr
-    res = {}
-    for mode in (3, 5, 0, 4):
-        x, pp = pr.x.copy(), pr.pp0.copy()
-        r = api.sagefit_visibilities(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz, b.fresh_barr(),
-                                     b.sky, pr.coh, pp, max_emiter=2, max_iter=2, max_lbfgs=4,
-                                     solver_mode=mode)
-        res[mode] = (r, pp)
-    # 4 -> 0 (OS-LM + LBFGS): the same solve again, up to the order of the atomic station sums
-    assert relerr(res[4][1], res[0][1]) < 1e-9
-    # 5 -> 3 (OS robust LM + robust LBFGS): rounding-level LM decisions (see the osrlm golden) let two
-    # runs of mode 3 itself differ, so only the outcome is compared
-    assert res[5][0][0] == res[3][0][0] == 0
-    assert abs(res[5][0][3] - res[3][0][3]) <= 0.05 * res[3][0][3]
-
-
 # ---------------------------------------------------------------------------------------------
 # reduced C2/C3 shape against golden outputs of the compiled reference
 # ---------------------------------------------------------------------------------------------

@@ -815,11 +815,12 @@ def main():
             dist.destroy_process_group()
         return
     line = run_workload(args.workload, args, ctx)
-    # one GPU: the two 62-station configurations of BASELINE.json ride along (their own parity
+    # one GPU: the two 62-station configurations of BASELINE.json ride along, and C3 once more under
+    # the reference driver's default solver (solver_mode 5, robust RTR) (their own parity
     # against the full-shape goldens, value, roofline), so that one driver run covers C2, C3 and C4
     if world == 1 and rank == 0 and args.workload == "C4" and not args.only and not args.profile_run:
         others = {}
-        for w in ("C2", "C3"):
+        for w in ("C2", "C3", "C3rtr"):
             o = run_workload(w, args, ctx, with_cpu=False)
             others[w] = {k: o[k] for k in ("value", "ms_per_step", "config", "e2e", "gpu_launches",
                                            "parity", "breakdown")}

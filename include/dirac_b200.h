@@ -263,8 +263,17 @@ int dirac_b200_consensus_step(dirac_b200_problem *pr, const double *J, double *Y
                               double *primal, double *dual);
 /* the J-update of one ADMM iteration on a resident problem, and its drop-in form: replaces
  * sagefit_visibilities_admm (Dirac.h:1521, admm_solve.c:221) and its GPU-build twin (:1533).  Each
- * cluster's cost carries y^T (p - bz) + rho/2 |p - bz|^2; solved with this library's LM (the reference
- * uses its Riemannian trust-region solver here, so iterates differ; the ADMM fixed point does not). */
+ * cluster's cost carries y^T (p - bz) + rho/2 |p - bz|^2.
+ *   dirac_b200_sagefit_admm_rtr: as the reference solves it -- every visit by the robust Riemannian
+ *     trust-region solver on the augmented cost (rtr_solve_nocuda_robust_admm, admm_solve.c:331-352);
+ *     what sagefit_visibilities_admm runs.
+ *   dirac_b200_sagefit_admm: this library's LM on the same cost (Gauss-Newton system with rho/2 on the
+ *     diagonal): other iterates, the same ADMM fixed point; dirac_b200_set_option("admm_lm", 1)
+ *     makes the drop-in entry point use it. */
+int dirac_b200_sagefit_admm_rtr(dirac_b200_problem *pr, double *pp, double *x_out, const double *Y,
+                                const double *BZ, const double *admm_rho, int max_emiter,
+                                int max_iter, double nulow, double nuhigh, int randomize,
+                                double *mean_nu, double *res_0, double *res_1);
 int dirac_b200_sagefit_admm(dirac_b200_problem *pr, double *pp, double *x_out, const double *Y,
                             const double *BZ, const double *admm_rho, int max_emiter, int max_iter,
                             int linsolv, int randomize, double *res_0, double *res_1);
@@ -293,6 +302,7 @@ void dirac_b200_set_stream(void *stream);
  *               threads' partial sums, which it reads before joining the threads
  *               (rtr_solve_robust.c:361-370), were all still zero -- what the threaded reference does
  *               on most runs; default 0: the sums are complete, as the code was meant
+ *   "admm_lm"   sagefit_visibilities_admm solves with this library's LM instead of the robust RTR
  *   "cp_rows"   timeslots per CTA of the gradient-carrying cluster pass (0: one wave over the SMs);
  *               the parity tests use it to drive the multi-row TMA ring on small problems */
 int dirac_b200_set_option(const char *name, int value);

@@ -69,13 +69,14 @@ class Oracle:
         L.orc_bfgsfit.restype = i
         L.orc_bfgsfit.argtypes = [pp, dp, dp, i, i, i, d, dp, dp]
         if self.H is not None:
-            self.H.harness_rtr_solve.argtypes = [pp, i, i, i, i, i, dp, i, dp, i, i, d, d, dp, dp, i]
-            self.H.harness_rtr_solve.restype = None
+            self.H.harness_rtr_solve_admm.argtypes = [pp, i, i, i, i, i, dp, i, dp, i, i, d, d, dp, dp,
+                                                      i, dp, dp, d]
+            self.H.harness_rtr_solve_admm.restype = None
         # the arithmetic of the product's RTR kernels (rtr_math.cuh) on the CPU
         self.HT = C.CDLL(RTR_TENSOR_PATH) if os.path.exists(RTR_TENSOR_PATH) else None
         if self.HT is not None:
             self.HT.harness_rtr_solve_tensor.argtypes = [pp, i, i, i, dp, i, dp, i, i, d, d, dp, dp,
-                                                         i]
+                                                         i, dp, dp, d]
             self.HT.harness_rtr_solve_tensor.restype = None
         L.orc_generate_baselines.argtypes = [i, i, i, ip, ip]
         L.orc_preset_flags_and_data.argtypes = [i, dp, up, dp]
@@ -159,21 +160,25 @@ class Oracle:
         return p, info, nu.value
 
     def rtr_chunk(self, k, t0, ntiles, pblk, xd, kind, itmax_a, itmax_b, nulow=2.0, nuhigh=30.0,
-                  nu0=2.0, nu_joined=True, tensor=False):
+                  nu0=2.0, nu_joined=True, tensor=False, Y=None, BZ=None, rho=0.0):
         """RTR (kind 4), robust RTR (5), NSD (6) of one chunk on hidden data xd.  tensor: with the
         per-baseline tensor arithmetic of the product's kernels instead of the per-row evaluators"""
         p = np.ascontiguousarray(pblk, dtype=np.float64).copy()
         info = np.zeros(10)
         nu = C.c_double(nu0)
         xd = np.ascontiguousarray(xd)
+        if Y is not None:  # consensus terms of this block (rtr_solve_nocuda_robust_admm)
+            Y = np.ascontiguousarray(Y, dtype=np.float64)
+            BZ = np.ascontiguousarray(BZ, dtype=np.float64)
+        yp, zp = (_d(Y), _d(BZ)) if Y is not None else (None, None)
         if tensor:
             self.HT.harness_rtr_solve_tensor(C.byref(self.P), k, t0, ntiles, _d(xd), kind, _d(p),
                                              itmax_a, itmax_b, nulow, nuhigh, C.byref(nu),
-                                             _d(info), int(nu_joined))
+                                             _d(info), int(nu_joined), yp, zp, rho)
             return p, info, nu.value
-        self.H.harness_rtr_solve(C.byref(self.P), self.pr.N, self.pr.Nbase, k, t0, ntiles, _d(xd),
-                                 kind, _d(p), itmax_a, itmax_b, nulow, nuhigh, C.byref(nu),
-                                 _d(info), int(nu_joined))
+        self.H.harness_rtr_solve_admm(C.byref(self.P), self.pr.N, self.pr.Nbase, k, t0, ntiles,
+                                      _d(xd), kind, _d(p), itmax_a, itmax_b, nulow, nuhigh,
+                                      C.byref(nu), _d(info), int(nu_joined), yp, zp, rho)
         return p, info, nu.value
 
     def update_w_and_nu(self, nu0, ed, nulow=2.0, nuhigh=30.0):

@@ -14,4 +14,8 @@ static int ser_create(pthread_t *t, const pthread_attr_t *a, void *(*fn)(void *)
 }
 #define pthread_create ser_create
 #define pthread_join(t, r) 0
+#ifdef SHIM_ADMM
+#include "rtr_solve_robust_admm.c" /* same race, rtr_solve_robust_admm.c:381-390 */
+#else
 #include "rtr_solve_robust.c"
+#endif

@@ -63,6 +63,8 @@ class RefDirac(DiracAPI):
         L.rtr_solve_nocuda_robust.argtypes = [dp, dp, i, i, i, i, d, d, d, d, dp, vp]
         L.nsd_solve_nocuda_robust.restype = i
         L.nsd_solve_nocuda_robust.argtypes = [dp, dp, i, i, i, d, d, dp, vp]
+        L.rtr_solve_nocuda_robust_admm.restype = i
+        L.rtr_solve_nocuda_robust_admm.argtypes = [dp, dp, dp, dp, i, i, i, i, d, d, d, d, d, dp, vp]
         L.update_w_and_nu.restype = d
         L.update_w_and_nu.argtypes = [d, dp, dp, i, i, d, d]
 
@@ -162,6 +164,17 @@ class RefDirac(DiracAPI):
         else:
             self.lib.nsd_solve_nocuda_robust(dptr(p), dptr(xd), N, nrows, itmax_a, nulow, nuhigh,
                                              dptr(info), md)
+        return p, info, self.lib.ref_get_robust_nu(md)
+
+    def rtr_admm(self, pblk, Y, BZ, xd, md, N, nrows, itmax_a, itmax_b, rho, nulow=2.0, nuhigh=30.0):
+        """rtr_solve_nocuda_robust_admm (rtr_solve_robust_admm.c:1424) on hidden data xd"""
+        p = np.ascontiguousarray(pblk, dtype=np.float64).copy()
+        info = np.zeros(10)
+        xd = np.ascontiguousarray(xd, dtype=np.float64).copy()
+        Y = np.ascontiguousarray(Y, dtype=np.float64).copy()
+        BZ = np.ascontiguousarray(BZ, dtype=np.float64).copy()
+        self.lib.rtr_solve_nocuda_robust_admm(dptr(p), dptr(Y), dptr(BZ), dptr(xd), N, nrows, itmax_a,
+                                              itmax_b, 2.0, 0.25, rho, nulow, nuhigh, dptr(info), md)
         return p, info, self.lib.ref_get_robust_nu(md)
 
 

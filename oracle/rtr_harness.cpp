@@ -46,15 +46,26 @@ struct CpuEval {
 };
 }  // namespace
 
-extern "C" void harness_rtr_solve(const void *P, int N, int Nbase, int k, int t0, int ntiles,
-                                  const double *y, int kind, double *x, int itmax_a, int itmax_b,
-                                  double nulow, double nuhigh, double *robust_nu, double *info,
-                                  int nu_joined) {
+// Y != NULL: consensus terms (rtr_solve_nocuda_robust_admm), kind 5 only
+extern "C" void harness_rtr_solve_admm(const void *P, int N, int Nbase, int k, int t0, int ntiles,
+                                       const double *y, int kind, double *x, int itmax_a,
+                                       int itmax_b, double nulow, double nuhigh, double *robust_nu,
+                                       double *info, int nu_joined, const double *Y,
+                                       const double *BZ, double rho) {
   CpuEval E;
   E.P = P; E.k = k; E.t0 = t0; E.ntiles = ntiles; E.N = N; E.y = y;
   E.nrow = (long)ntiles * Nbase;
   E.weighted = false;
-  rtr::solve_chunk(E, kind, x, itmax_a, itmax_b, nulow, nuhigh, robust_nu, info, nu_joined != 0);
+  rtr::Admm aug = {Y, BZ, rho};
+  rtr::solve_chunk(E, kind, x, itmax_a, itmax_b, nulow, nuhigh, robust_nu, info, nu_joined != 0,
+                   Y ? &aug : nullptr);
+}
+extern "C" void harness_rtr_solve(const void *P, int N, int Nbase, int k, int t0, int ntiles,
+                                  const double *y, int kind, double *x, int itmax_a, int itmax_b,
+                                  double nulow, double nuhigh, double *robust_nu, double *info,
+                                  int nu_joined) {
+  harness_rtr_solve_admm(P, N, Nbase, k, t0, ntiles, y, kind, x, itmax_a, itmax_b, nulow, nuhigh,
+                         robust_nu, info, nu_joined, nullptr, nullptr, 0.0);
 }
 
 // nu update of the robust solvers: 1 as meant (default), 0 "sums read before the join are zero"

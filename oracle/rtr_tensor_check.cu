@@ -104,9 +104,12 @@ struct TensorEval {
 extern "C" void harness_rtr_solve_tensor(const void *P, int k, int t0, int ntiles, const double *y,
                                          int kind, double *x, int itmax_a, int itmax_b,
                                          double nulow, double nuhigh, double *robust_nu,
-                                         double *info, int nu_joined) {
+                                         double *info, int nu_joined, const double *Y,
+                                         const double *BZ, double rho) {
   TensorEval E;
   E.P = (const OrcProblem *)P;
   E.k = k; E.t0 = t0; E.ntiles = ntiles; E.N = E.P->N; E.y = y;
-  rtr::solve_chunk(E, kind, x, itmax_a, itmax_b, nulow, nuhigh, robust_nu, info, nu_joined != 0);
+  rtr::Admm aug = {Y, BZ, rho};
+  rtr::solve_chunk(E, kind, x, itmax_a, itmax_b, nulow, nuhigh, robust_nu, info, nu_joined != 0,
+                   Y ? &aug : nullptr);
 }

@@ -80,24 +80,37 @@ class ConsensusSubband:
                                                self.Npoly, C.byref(pr), C.byref(du))
         return pr.value, du.value
 
-    def jupdate(self, pp, max_emiter=1, max_iter=2, first=False):
-        """first ADMM iteration: plain calibration; later ones carry the consensus terms"""
+    def jupdate(self, pp, max_emiter=1, max_iter=2, first=False, solver="lm"):
+        """first ADMM iteration: plain calibration; later ones carry the consensus terms.
+        solver: "rtr" = the reference's robust Riemannian trust-region J-update
+        (dirac_b200_sagefit_admm_rtr), "lm" = this library's LM on the augmented cost"""
         if first:
             rv, _, r0, r1 = self.dp.sagefit(pp, None, max_emiter=max_emiter, max_iter=max_iter,
                                             max_lbfgs=0, solver_mode=1)
             return rv, r0, r1
         r0, r1 = C.c_double(0.0), C.c_double(0.0)
+        if solver == "rtr":
+            nu = C.c_double(0.0)
+            L = self.api.lib
+            L.dirac_b200_sagefit_admm_rtr.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p,
+                                                      c_double_p, c_double_p, C.c_int, C.c_int,
+                                                      C.c_double, C.c_double, C.c_int, c_double_p,
+                                                      c_double_p, c_double_p]
+            rv = L.dirac_b200_sagefit_admm_rtr(self.dp.h, dptr(pp), None, dptr(self.Y),
+                                               dptr(self.BZ), dptr(self.rho), max_emiter, max_iter,
+                                               2.0, 30.0, 0, C.byref(nu), C.byref(r0), C.byref(r1))
+            return rv, r0.value, r1.value
         rv = self.api.lib.dirac_b200_sagefit_admm(self.dp.h, dptr(pp), None, dptr(self.Y), dptr(self.BZ),
                                                   dptr(self.rho), max_emiter, max_iter, 0, 0,
                                                   C.byref(r0), C.byref(r1))
         return rv, r0.value, r1.value
 
-    def run(self, pp, admm_iters=5, max_emiter=1, max_iter=2):
+    def run(self, pp, admm_iters=5, max_emiter=1, max_iter=2, solver="lm"):
         """ADMM loop (sagecal_slave.cpp:700-900 without the master); returns per-iteration
         (res_0, res_1, primal, dual)"""
         hist = []
         for it in range(admm_iters):
-            rv, r0, r1 = self.jupdate(pp, max_emiter, max_iter, first=(it == 0))
+            rv, r0, r1 = self.jupdate(pp, max_emiter, max_iter, first=(it == 0), solver=solver)
             pr, du = self.exchange(pp)
             hist.append((r0, r1, pr, du))
         return hist

@@ -276,6 +276,25 @@ extern "C" int dirac_b200_sagefit_admm(dirac_b200_problem *pr, double *pp, doubl
   return rv;
 }
 
+// The J-update as the reference does it (admm_solve.c:221-420): every cluster visit is the robust
+// Riemannian trust-region solver on the consensus-augmented cost (rtr_solve_nocuda_robust_admm: the
+// flow of solver_mode 5 in Euclidean space, rtr_algo.h), whatever solver_mode the caller names; no
+// LBFGS stage; mean nu as in the robust modes.
+extern "C" int dirac_b200_sagefit_admm_rtr(dirac_b200_problem *pr, double *pp, double *x_out,
+                                           const double *Y, const double *BZ,
+                                           const double *admm_rho, int max_emiter, int max_iter,
+                                           double nulow, double nuhigh, int randomize,
+                                           double *mean_nu, double *res_0, double *res_1) {
+  pr->aug_y_host = Y;
+  pr->aug_bz_host = BZ;
+  pr->aug_rho = admm_rho;
+  const int rv = dirac_b200_sagefit(pr, pp, x_out, max_emiter, max_iter, 0, 0, 0, 7 /* SM_RTR_ADMM_ */,
+                                    nulow, nuhigh, randomize, mean_nu, res_0, res_1);
+  db_stream_sync(pr->d.stream);
+  pr->aug_y_host = pr->aug_bz_host = pr->aug_rho = nullptr;
+  return rv;
+}
+
 extern "C" int sagefit_visibilities_admm(double *u, double *v, double *w, double *x, int N, int Nbase,
                                          int tilesz, baseline_t *barr, clus_source_t *carr,
                                          double *coh, int M, int Mt, double freq0, double fdelta,
@@ -285,11 +304,17 @@ extern "C" int sagefit_visibilities_admm(double *u, double *v, double *w, double
                                          double nuhigh, int randomize, double *admm_rho,
                                          double *mean_nu, double *res_0, double *res_1) {
   (void)u; (void)v; (void)w; (void)freq0; (void)fdelta; (void)uvmin; (void)Nt; (void)max_lbfgs;
-  (void)lbfgs_m; (void)gpu_threads; (void)solver_mode; (void)nuhigh;
+  (void)lbfgs_m; (void)gpu_threads; (void)solver_mode;
   dirac_b200_problem *pr = dirac_b200_create(N, Nbase, tilesz, barr, carr, M, Mt, coh, x);
-  const int rv = dirac_b200_sagefit_admm(pr, pp, x, Y, BZ, admm_rho, max_emiter, max_iter, linsolv,
-                                         randomize, res_0, res_1);
-  *mean_nu = nulow;
+  int rv;
+  if (db_opt(DB_OPT_ADMM_LM)) {  // this library's LM on the augmented cost (round-2 default until RTR)
+    rv = dirac_b200_sagefit_admm(pr, pp, x, Y, BZ, admm_rho, max_emiter, max_iter, linsolv, randomize,
+                                 res_0, res_1);
+    *mean_nu = nulow;
+  } else {
+    rv = dirac_b200_sagefit_admm_rtr(pr, pp, x, Y, BZ, admm_rho, max_emiter, max_iter, nulow, nuhigh,
+                                     randomize, mean_nu, res_0, res_1);
+  }
   dirac_b200_destroy(pr);
   return rv;
 }

@@ -371,7 +371,7 @@ struct BatchAssembleArgs {
 
 // test / tuning options (dirac_b200_set_option): 0 = default
 enum { DB_OPT_CP_ROWS = 0, DB_OPT_LINE_DIRECT = 1, DB_OPT_OS_CONSISTENT = 2,
-       DB_OPT_RTR_NU_UNJOINED = 3, DB_OPT_COUNT = 8 };
+       DB_OPT_RTR_NU_UNJOINED = 3, DB_OPT_ADMM_LM = 4, DB_OPT_COUNT = 8 };
 int db_opt(int id);
 int db_sm_count();  // SMs of the current device
 // slices of the time axis the linear-mapped gradient pass may use (sizes LMWork::jte_part)

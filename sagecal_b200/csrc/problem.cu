@@ -79,6 +79,8 @@ extern "C" int dirac_b200_set_option(const char *name, int value) {
   // robust RTR / NSD: nu update as if the reference's unjoined thread sums were all still zero
   // (rtr_algo.h: update_weights)
   if (!strcmp(name, "rtr_nu_unjoined")) { g_opt[DB_OPT_RTR_NU_UNJOINED] = value; return 0; }
+  // sagefit_visibilities_admm: LM on the augmented cost instead of the reference's robust RTR
+  if (!strcmp(name, "admm_lm")) { g_opt[DB_OPT_ADMM_LM] = value; return 0; }
   return -1;
 }
 // SMs of the current device (grids of the one-wave kernels are sized from it)

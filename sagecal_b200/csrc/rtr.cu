@@ -202,9 +202,12 @@ struct RtrDevEval {
 // one (cluster, chunk) visit.  kind: 4 RSD+RTR, 5 robust RTR, 6 robust NSD.  robust_nu: in/out
 // (lmdata.robust_nu of the reference persists from visit to visit, lmfit.c:938-957).
 // ------------------------------------------------------------------------------------------------
+// aug_y / aug_bz != null (kind 5): the consensus-augmented cost of the ADMM J-update
+// (rtr_solve_nocuda_robust_admm); host vectors of this block.
 void db_rtr_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int kind,
                   int itmax_a, int itmax_b, double nulow, double nuhigh, double *robust_nu,
-                  double *info, bool hidden_ready) {
+                  double *info, bool hidden_ready, const double *aug_y, const double *aug_bz,
+                  double aug_rho) {
   DevProblem &d = pr->d;
   db_lm_init(pr);
   LMWork &lw = pr->lm;
@@ -233,8 +236,9 @@ void db_rtr_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, doubl
   DB_CHECK(cudaMemcpyAsync(w->h, pblk_dev, sizeof(double) * n8, cudaMemcpyDeviceToHost, d.stream));
   db_stream_sync(d.stream);
   memcpy(x.data(), w->h, sizeof(double) * n8);
+  rtr::Admm aug = {aug_y, aug_bz, aug_rho};
   rtr::solve_chunk(E, kind, x.data(), itmax_a, itmax_b, nulow, nuhigh, robust_nu, info,
-                   !db_opt(DB_OPT_RTR_NU_UNJOINED));
+                   !db_opt(DB_OPT_RTR_NU_UNJOINED), aug_y ? &aug : nullptr);
   memcpy(w->h, x.data(), sizeof(double) * n8);
   DB_CHECK(cudaMemcpyAsync(pblk_dev, w->h, sizeof(double) * n8, cudaMemcpyHostToDevice, d.stream));
   // residual of the chunk with the final Jones: r = d - f(p)  (lmfit.c:980-981)

@@ -147,14 +147,38 @@ inline double digamma(double x) {
   return result;
 }
 
-// the fns_* callbacks of the reference on top of an evaluator's raw sums
+// consensus (ADMM) terms of one (cluster, chunk): cost + y^H (J - BZ) + rho/2 |J - BZ|^2
+// (rtr_solve_robust_admm.c:199-214); Y, BZ: 8N doubles in the parameter layout
+struct Admm {
+  const double *Y, *BZ;
+  double rho;
+};
+
+// the fns_* callbacks of the reference on top of an evaluator's raw sums.  With consensus terms
+// (rtr_solve_robust_admm.c) the search space is Euclidean: the projection is the identity (:425-430)
 template <class EV>
 struct Ops {
   EV &ev;
   int N, n8;
+  const Admm *aug;
   std::vector<double> iw;   // per-station inverse baseline counts, max 1 (fns_fcount)
   std::vector<double> rawv;
-  explicit Ops(EV &e) : ev(e), N(e.N), n8(8 * e.N), iw(e.N, 0.0), rawv(8 * e.N, 0.0) {}
+  explicit Ops(EV &e, const Admm *a = nullptr)
+      : ev(e), N(e.N), n8(8 * e.N), aug(a), iw(e.N, 0.0), rawv(8 * e.N, 0.0) {}
+  void project(const double *x, const double *z, double *out) const {
+    if (aug) memcpy(out, z, sizeof(double) * n8);
+    else proj(N, x, z, out);
+  }
+  // 2 Re(Y^H (x - BZ)) + rho/2 |x - BZ|^2  (rtr_solve_robust_admm.c:205-212)
+  double aug_cost(const double *x) const {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < n8; i++) {
+      const double dlt = x[i] - aug->BZ[i];
+      a += aug->Y[i] * dlt;
+      b += dlt * dlt;
+    }
+    return 2.0 * a + 0.5 * aug->rho * b;
+  }
   // fns_fcount (rtr_solve.c:99-180): inverse of the unflagged rows per station, scaled to max 1
   void count() {
     std::vector<double> c(N);
@@ -170,22 +194,31 @@ struct Ops {
   double f(const double *x) {  // fns_f (rtr_solve.c:251, rtr_solve_robust.c:135)
     double c;
     ev.raw(x, nullptr, &c, nullptr);
+    if (aug) c += aug_cost(x);
     return c;
   }
   // fns_fgrad (rtr_solve.c:539-636): station sums scaled by iw, optionally negated, projected.
   // fx != null: the cost at x rides along in the same evaluation.
   void fgrad(const double *x, double *g, bool negate, double *fx = nullptr) {
     ev.raw(x, nullptr, fx, rawv.data());
+    if (fx && aug) *fx += aug_cost(x);
     for (int s = 0; s < N; s++) {
       const double sc = negate ? -iw[s] : iw[s];
       for (int i = 0; i < 8; i++) rawv[8 * s + i] *= sc;
     }
-    proj(N, x, rawv.data(), g);
+    if (aug) {  // +-(Y/2 + rho/2 (x - BZ))  (rtr_solve_robust_admm.c:679-687)
+      const double sg = negate ? 0.5 : -0.5;
+      for (int i = 0; i < n8; i++)
+        rawv[i] += sg * (aug->Y[i] + aug->rho * (x[i] - aug->BZ[i]));
+    }
+    project(x, rawv.data(), g);
   }
   // fns_fhess (rtr_solve.c:774-870): NOT scaled by iw (see the file header), projected
   void fhess(const double *x, const double *eta, double *h) {
     ev.raw(x, eta, nullptr, rawv.data());
-    proj(N, x, rawv.data(), h);
+    if (aug)  // + rho/2 eta  (rtr_solve_robust_admm.c:949)
+      for (int i = 0; i < n8; i++) rawv[i] += 0.5 * aug->rho * eta[i];
+    project(x, rawv.data(), h);
   }
 };
 
@@ -440,14 +473,17 @@ static double itrr(Ops<EV> &E, double *x, double *eta, double *Heta, double *s, 
 
 
 // ------------------------------------------------------------------------------------------------
-// one (cluster, chunk) solve.  kind: 4 RSD+RTR, 5 robust RTR, 6 robust NSD.  x: in/out (kept only if
+// one (cluster, chunk) solve.  kind: 4 RSD+RTR, 5 robust RTR, 6 robust NSD; aug != null (kind 5 only):
+// rtr_solve_nocuda_robust_admm (rtr_solve_robust_admm.c:1424-1899, the same flow as kind 5 on the
+// consensus-augmented cost in Euclidean space).  x: in/out (kept only if
 // the cost went down).  robust_nu: in/out (lmdata.robust_nu persists from visit to visit,
 // lmfit.c:938-957).  info[0] / info[1]: initial / final cost.
 // ------------------------------------------------------------------------------------------------
 template <class EV>
 void solve_chunk(EV &ev, int kind, double *xio, int itmax_a, int itmax_b, double nulow,
-                 double nuhigh, double *robust_nu, double *info, bool nu_joined = true) {
-  Ops<EV> E(ev);
+                 double nuhigh, double *robust_nu, double *info, bool nu_joined = true,
+                 const Admm *aug = nullptr) {
+  Ops<EV> E(ev, aug);
   const int n8 = E.n8;
   std::vector<double> x(xio, xio + n8), fgradx(n8, 0.0), eta(n8, 0.0), Heta(n8, 0.0),
       x_prop(n8, 0.0);

@@ -23,11 +23,15 @@ void db_lbfgs_fit(dirac_b200_problem *pr, double *p, int m, int itmax, int M, in
                   double nu);
 void db_rtr_chunk(dirac_b200_problem *pr, int k, int ck, double *pblk_dev, double2 *r, int kind,
                   int itmax_a, int itmax_b, double nulow, double nuhigh, double *robust_nu,
-                  double *info, bool hidden_ready);
+                  double *info, bool hidden_ready, const double *aug_y, const double *aug_bz,
+                  double aug_rho);
+// internal solver mode of dirac_b200_sagefit_admm_rtr: every visit by rtr_solve_nocuda_robust_admm
+#define SM_RTR_ADMM_ 7
 
 static bool is_robust_mode(int solver_mode) {
   return solver_mode == SM_OSLM_OSRLM_RLBFGS || solver_mode == SM_RLM_RLBFGS ||
-         solver_mode == SM_RTR_OSRLM_RLBFGS || solver_mode == SM_NSD_RLBFGS;
+         solver_mode == SM_RTR_OSRLM_RLBFGS || solver_mode == SM_NSD_RLBFGS ||
+         solver_mode == SM_RTR_ADMM_;
 }
 
 // SAGE/EM on an already resident problem.  pp: host, in/out.  If x_out != NULL the final residual is
@@ -36,7 +40,7 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
                                   int max_emiter, int max_iter, int max_lbfgs, int lbfgs_m,
                                   int linsolv, int solver_mode, double nulow, double nuhigh,
                                   int randomize, double *mean_nu, double *res_0, double *res_1) {
-  if (solver_mode < 0 || solver_mode > 6) {
+  if (solver_mode < 0 || solver_mode > 6 + (pr->aug_rho ? 1 : 0)) {
     fprintf(stderr, "%s: %d: undefined solver mode\n", __FILE__, __LINE__);  // lmfit.c:957-962
     exit(1);
   }
@@ -124,6 +128,18 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
           const int poff = d.h_chunk_poff[hc[cj].chunk0 + ck];
           double *pblk = d.pp + poff;
           const bool last = (ci == max_emiter - 1);
+          if (solver_mode == SM_RTR_ADMM_) {
+            // ADMM J-update as the reference does it (admm_solve.c:331-352): robust RTR on the
+            // consensus-augmented cost, whatever solver_mode the caller named
+            if (!ci) rtr_nu = robust_nu0;
+            db_rtr_chunk(pr, cj, ck, pblk, r, 5, this_itermax + 5, this_itermax + 10, nulow, nuhigh,
+                         &rtr_nu, info, hr, pr->aug_y_host + poff, pr->aug_bz_host + poff,
+                         pr->aug_rho[cg]);
+            if (last) robust_nuM[cg] += rtr_nu;
+            init_res += info[0];
+            final_res += info[1];
+            continue;
+          }
           if (pr->aug_rho)  // consensus terms of this block (dirac_b200_sagefit_admm)
             db_lm_set_aug(pr->aug_dev + poff, pr->aug_dev + d.npar + poff, pr->aug_y_host + poff,
                           pr->aug_bz_host + poff, pr->aug_rho[cg]);
@@ -144,18 +160,18 @@ extern "C" int dirac_b200_sagefit(dirac_b200_problem *pr, double *pp, double *x_
           } else if (solver_mode == SM_RTR_OSLM_LBFGS) {
             // RSD + RTR (lmfit.c:934-937)
             db_rtr_chunk(pr, cj, ck, pblk, r, 4, this_itermax + 5, this_itermax + 10, nulow,
-                         nuhigh, &rtr_nu, info, hr);
+                         nuhigh, &rtr_nu, info, hr, nullptr, nullptr, 0.0);
           } else if (solver_mode == SM_RTR_OSRLM_RLBFGS) {
             // robust RTR; nu persists from visit to visit after the first sweep (lmfit.c:938-947)
             if (!ci) rtr_nu = robust_nu0;
             db_rtr_chunk(pr, cj, ck, pblk, r, 5, this_itermax + 5, this_itermax + 10, nulow,
-                         nuhigh, &rtr_nu, info, hr);
+                         nuhigh, &rtr_nu, info, hr, nullptr, nullptr, 0.0);
             if (last) robust_nuM[cg] += rtr_nu;
           } else if (solver_mode == SM_NSD_RLBFGS) {
             // Nesterov's accelerated descent (lmfit.c:948-957)
             if (!ci) rtr_nu = robust_nu0;
             db_rtr_chunk(pr, cj, ck, pblk, r, 6, this_itermax + 15, 0, nulow, nuhigh, &rtr_nu,
-                         info, hr);
+                         info, hr, nullptr, nullptr, 0.0);
             if (last) robust_nuM[cg] += rtr_nu;
           } else {  // SM_OSLM_OSRLM_RLBFGS
             if (last) {

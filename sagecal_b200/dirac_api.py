@@ -281,3 +281,17 @@ class DiracAPI:
             sky.M, sky.Mt, freq0, fdelta, dptr(pp), uvmin, Nt, max_lbfgs, lbfgs_m, gpu_threads,
             solver_mode, mean_nu, C.byref(res0), C.byref(res1))
         return rv, res0.value, res1.value
+
+    def sagefit_visibilities_admm(self, u, v, w, x, N, Nbase, tilesz, barr, sky, coh, pp, Y, BZ, rho,
+                                  max_emiter=3, max_iter=2, nulow=2.0, nuhigh=30.0, Nt=4,
+                                  solver_mode=5):
+        """sagefit_visibilities_admm (Dirac.h:1521, admm_solve.c:221): x -> residual, pp in/out"""
+        nu, r0, r1 = C.c_double(0), C.c_double(0), C.c_double(0)
+        self.lib.sagefit_visibilities_admm.restype = C.c_int
+        rv = self.lib.sagefit_visibilities_admm(
+            dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, cptr(coh), sky.M,
+            sky.Mt, C.c_double(150e6), C.c_double(195.3e3), dptr(pp), dptr(Y), dptr(BZ),
+            C.c_double(0.0), Nt, max_emiter, max_iter, 0, 7, 128, 0, solver_mode, C.c_double(nulow),
+            C.c_double(nuhigh), 0, dptr(rho), C.byref(nu), C.byref(r0), C.byref(r1))
+        return rv, nu.value, r0.value, r1.value
+

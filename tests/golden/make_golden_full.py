@@ -23,7 +23,11 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "full")
 SOLVE = dict(max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, linsolv=0, nulow=2.0, nuhigh=30.0)
 CASES = {"C2": ("C2", 1), "C3": ("C3", 2), "C3os": ("C3", 3),
          # RTR family (oracle/rtr_harness.cpp: rtr_algo.h on the per-row evaluators)
-         "C2rtr": ("C2", 4), "C3rtr": ("C3", 5), "C3nsd": ("C3", 6)}
+         "C2rtr": ("C2", 4), "C3rtr": ("C3", 5), "C3nsd": ("C3", 6),
+         # the SAGE stage alone (no LBFGS): the Gaussian LBFGS stage differentiates the cost
+         # numerically with a step of 1e-9..1e-6 (lbfgs.c:546), so its iterates carry the rounding of
+         # the cost sum; the stage before it is reproducible to 1e-12
+         "C2lm": ("C2", 1, dict(max_lbfgs=0))}
 
 
 def fingerprint(pr):
@@ -36,14 +40,16 @@ def main():
     from sagecal_b200 import synth
     os.makedirs(OUT, exist_ok=True)
     for name in sys.argv[1:]:
-        cfg, mode = CASES[name]
+        cfg, mode = CASES[name][:2]
+        over = CASES[name][2] if len(CASES[name]) > 2 else {}
         pr = synth.make_config(cfg)
         o = orcdirac.Oracle(pr)
         x, pp = pr.x.copy(), pr.pp0.copy()
         t0 = time.time()
-        out = o.sagefit(x, pp, solver_mode=mode, **SOLVE)
         kw = dict(SOLVE)
+        kw.update(over)
         kw["solver_mode"] = mode
+        out = o.sagefit(x, pp, **kw)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), config=np.array(cfg),
                             args=np.array(repr(kw)), out_pp=pp,
                             out_scalars=np.array(out, dtype=np.float64),

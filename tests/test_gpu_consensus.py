@@ -42,7 +42,52 @@ def test_consensus_step_matches_numpy(api):
         assert abs(pri - p2) <= 1e-12 * p2 and abs(dua - d2) <= 1e-12 * d2
 
 
-def test_admm_with_zero_rho_is_the_plain_solve(api):
+@pytest.fixture
+def admm_lm(api):
+    """the drop-in entry point with this library's LM on the augmented cost (default: robust RTR)"""
+    api.set_option("admm_lm", 1)
+    yield
+    api.set_option("admm_lm", 0)
+
+
+ADMM_CASES = [
+    ("admm", dict(N=10, M=3, tilesz=8, seed=6, kmean=1.0, outliers=0.02), dict(max_iter=2)),
+    ("admm-hybrid", dict(N=12, M=4, tilesz=10, seed=7, nchunk=[1, 2, 1, 5], outliers=0.02),
+     dict(max_iter=3)),
+    ("admm-62", dict(N=62, M=2, tilesz=3, seed=8), dict(max_iter=2, max_emiter=2)),
+]
+
+
+@pytest.mark.parametrize("name,prob,args", ADMM_CASES, ids=[c[0] for c in ADMM_CASES])
+def test_sagefit_admm_matches_reference(api, refser, name, prob, args):
+    """sagefit_visibilities_admm (admm_solve.c:221-420: every visit by rtr_solve_nocuda_robust_admm)
+    against the compiled reference (serialised-thread build: the nu update of the threaded one
+    races)"""
+    b = small_problem(**prob)
+    pr = b.pr
+    rng = np.random.default_rng(11)
+    BZ = pr.jones_true + 0.03 * rng.normal(0, 1, b.m)
+    Y = 0.2 * rng.normal(0, 1, b.m)
+    rho = rng.uniform(2.0, 30.0, pr.M)
+    kw = dict(max_emiter=3, max_iter=2)
+    kw.update(args)
+    out = []
+    for lib in (refser, api):
+        x, pp = pr.x.copy(), pr.pp0.copy()
+        r = lib.sagefit_visibilities_admm(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz,
+                                          b.fresh_barr(), b.sky, pr.coh, pp, Y.copy(), BZ.copy(), rho,
+                                          **kw)
+        out.append((r, x, pp))
+    (rr, xr, ppr), (rg, xg, ppg) = out
+    assert rr[0] == rg[0]
+    assert abs(rr[1] - rg[1]) < 1e-9                    # mean nu
+    assert abs(rr[2] - rg[2]) <= 1e-10 * rr[2]
+    assert relerr(ppg, ppr) < 1e-5, (name, relerr(ppg, ppr))
+    assert relerr(xg, xr) < 1e-5
+    assert abs(rr[3] - rg[3]) <= 1e-5 * rr[3]
+
+
+def test_admm_with_zero_rho_is_the_plain_solve(api, admm_lm):
     b = small_problem(N=10, M=3, tilesz=6, seed=4, kmean=1.0)
     pr = b.pr
     Y = np.zeros(b.m)

@@ -79,3 +79,40 @@ def test_sagefit_rtr_modes_match_reference(ref, refser, mode):
     assert abs(ro[2] - rr[2]) <= 1e-12 * rr[2]
     assert relerr(ppo, ppr) < 1e-6, relerr(ppo, ppr)
     assert abs(ro[3] - rr[3]) <= 1e-6 * rr[3]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_rtr_admm_chunk_matches_reference(refser, case):
+    """rtr_solve_nocuda_robust_admm (the J-update of the reference's consensus calibration) per
+    chunk: the control flow of rtr_algo.h with consensus terms on the per-row evaluators and on the
+    per-baseline tensor arithmetic of the product's kernels"""
+    b = small_problem(**CASES[case])
+    pr = b.pr
+    orc = orcdirac.Oracle(pr)
+    rng = np.random.default_rng(4 + case)
+    pp = perturbed_jones(pr, seed=9, amp=0.05)
+    res = pr.x - orc.predict_full(pp)
+    n8 = 8 * pr.N
+    off = 0
+    for k in range(pr.M):
+        hidden = res + orc.predict_cluster(k, pp)
+        for ck in range(pr.nchunk[k]):
+            t0, nt = orc.chunk_tiles(k, ck)
+            pblk = pp[off:off + n8].copy()
+            off += n8
+            if nt <= 0:
+                continue
+            Y = 0.3 * rng.normal(0, 1, n8)
+            BZ = pblk + 0.05 * rng.normal(0, 1, n8)
+            rho = float(rng.uniform(2.0, 40.0))
+            xd = hidden[8 * t0 * pr.Nbase: 8 * (t0 + nt) * pr.Nbase]
+            md = refser.me_data(pr.N, pr.Nbase, nt, b.barr, b.sky, pr.coh, clus=k, tileoff=t0,
+                                robust_nu=3.0)
+            pw, iw, nuw = refser.rtr_admm(pblk, Y, BZ, xd, md, pr.N, nt * pr.Nbase, 7, 12, rho)
+            for tensor, tol in ((False, 1e-9), (True, 1e-8)):
+                pg, ig, nug = orc.rtr_chunk(k, t0, nt, pblk, xd, 5, 7, 12, nu0=3.0, tensor=tensor,
+                                            Y=Y, BZ=BZ, rho=rho)
+                assert relerr(pg, pw) < tol, (k, ck, tensor, relerr(pg, pw))
+                assert abs(ig[0] - iw[0]) <= 1e-9 * abs(iw[0])
+                assert abs(ig[1] - iw[1]) <= 10 * tol * abs(iw[1])
+                assert nug == nuw

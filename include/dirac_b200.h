@@ -313,6 +313,44 @@ int dirac_b200_set_option(const char *name, int value);
  * path included; parity of the solved Jones is defined for runs where this stays 0. */
 long dirac_b200_noise_decisions(int reset);
 
+/* ---- multi-channel minibatch (stochastic) robust LBFGS, SURVEY.md 8f-3 ------------------------------
+ * persistent_data_t: the reference declares it twice (Dirac.h:86-110 without HAVE_CUDA, :196-226 with);
+ * the two layouts agree up to `Nt`, and this library touches nothing beyond that prefix (the running
+ * averages and the iteration count of the on-line variance live behind the curvature pairs in `s`), so
+ * a caller compiled against either reference header can pass its own struct. */
+typedef struct persistent_data_t_ {
+  double *y, *s; /* curvature pairs, lbfgs_m x m each (allocated by lbfgs_persist_init) */
+  double *rho;   /* 1 / y^T s */
+  int nfilled;   /* pairs in use, 0..lbfgs_m */
+  int vacant;    /* next slot, cycles through 0..lbfgs_m-1 */
+  int lbfgs_m;
+  int m;
+  int Nt;
+  /* (the reference's further fields differ between its builds and are not used) */
+} persistent_data_t;
+/* lbfgs.c:954-1045 */
+int lbfgs_persist_init(persistent_data_t *pt, int Nminibatch, int m, int n, int lbfgs_m, int Nt);
+int lbfgs_persist_clear(persistent_data_t *pt);
+int lbfgs_persist_reset(persistent_data_t *pt);
+/* Dirac.h:317,343 (robust_batchmode_lbfgs.c:1446-1577): x and coh hold Nf channels
+ * ([channel][row][8] and [channel][row][cluster][4] complex), ONE set of Jones p for all of them;
+ * Student's-t cost with fixed robust_nu, LBFGS with Armijo backtracking, curvature pairs and the
+ * gradient's on-line variance carried from minibatch to minibatch in *indata.  res = cost / n.
+ * _consensus adds y^T (p - z) + rho/2 |p - z|^2 per (cluster, chunk) block. */
+int bfgsfit_minibatch_visibilities(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                   int tilesz, baseline_t *barr, clus_source_t *carr, double *coh,
+                                   int M, int Mt, double *freqs, int Nf, double fdelta, double *p,
+                                   int Nt, int max_lbfgs, int lbfgs_m, int gpu_threads,
+                                   int solver_mode, double robust_nu, double *res_0, double *res_1,
+                                   persistent_data_t *indata, int nminibatch, int totalminibatch);
+int bfgsfit_minibatch_consensus(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                int tilesz, baseline_t *barr, clus_source_t *carr, double *coh, int M,
+                                int Mt, double *freqs, int Nf, double fdelta, double *p, double *y,
+                                double *z, double *rho, int Nt, int max_lbfgs, int lbfgs_m,
+                                int gpu_threads, int solver_mode, double robust_nu, double *res_0,
+                                double *res_1, persistent_data_t *indata, int nminibatch,
+                                int totalminibatch);
+
 /* Device memory freed by dirac_b200_destroy is kept (up to a quarter of the device's memory,
  * $DIRAC_B200_CACHE_GB overrides, 0 disables) and handed out again when a problem of the same shape
  * is created: the driver calls tile after tile with the same sizes, and cudaMalloc / cudaFree of the

@@ -282,6 +282,34 @@ class DiracAPI:
             solver_mode, mean_nu, C.byref(res0), C.byref(res1))
         return rv, res0.value, res1.value
 
+    # ---- multi-channel minibatch LBFGS (Dirac.h:86-147,317-350) ----
+    def persist_init(self, nminibatch, m, n, lbfgs_m, Nt=4):
+        """a persistent_data_t owned by THIS library (the struct's layout is the library's business:
+        a generous buffer takes either of the reference's two layouts)"""
+        pt = C.create_string_buffer(1024)
+        self.lib.lbfgs_persist_init(pt, nminibatch, m, n, lbfgs_m, Nt)
+        return pt
+
+    def persist_clear(self, pt):
+        self.lib.lbfgs_persist_clear(pt)
+
+    def bfgsfit_minibatch(self, u, v, w, x, N, Nbase, tilesz, barr, sky, coh, pp, freqs, pt,
+                          fdelta=195.3e3, Nt=4, max_lbfgs=4, lbfgs_m=5, robust_nu=5.0, nmb=0,
+                          totalmb=1, Y=None, Z=None, rho=None):
+        """bfgsfit_minibatch_visibilities, or _consensus when Y / Z / rho are given.  x:
+        [chan][row][8], coh: [chan][row][M][4] complex.  returns (res_0, res_1); pp in/out"""
+        r0, r1 = C.c_double(0.0), C.c_double(0.0)
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        head = (dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, cptr(coh),
+                sky.M, sky.Mt, dptr(freqs), len(freqs), C.c_double(fdelta), dptr(pp))
+        tail = (Nt, max_lbfgs, lbfgs_m, 128, 2, C.c_double(robust_nu), C.byref(r0), C.byref(r1), pt,
+                nmb, totalmb)
+        if Y is None:
+            self.lib.bfgsfit_minibatch_visibilities(*head, *tail)
+        else:
+            self.lib.bfgsfit_minibatch_consensus(*head, dptr(Y), dptr(Z), dptr(rho), *tail)
+        return r0.value, r1.value
+
     def sagefit_visibilities_admm(self, u, v, w, x, N, Nbase, tilesz, barr, sky, coh, pp, Y, BZ, rho,
                                   max_emiter=3, max_iter=2, nulow=2.0, nuhigh=30.0, Nt=4,
                                   solver_mode=5):

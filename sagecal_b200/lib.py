@@ -29,7 +29,8 @@ EXPORTED = [
     "dirac_b200_consensus_prod_inverse", "dirac_b200_consensus_step", "dirac_b200_sagefit_admm",
     "sagefit_visibilities_admm", "sagefit_visibilities_admm_dual_pt_flt",
     "calculate_residuals_multifreq", "dirac_b200_bigtri_solve", "dirac_b200_release_cache",
-    "dirac_b200_sagefit_admm_rtr",
+    "dirac_b200_sagefit_admm_rtr", "lbfgs_persist_init", "lbfgs_persist_clear",
+    "lbfgs_persist_reset", "bfgsfit_minibatch_visibilities", "bfgsfit_minibatch_consensus",
 ]
 
 

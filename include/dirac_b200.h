@@ -313,6 +313,75 @@ int dirac_b200_set_option(const char *name, int value);
  * path included; parity of the solved Jones is defined for runs where this stays 0. */
 long dirac_b200_noise_decisions(int reset);
 
+/* ---- station beams -------------------------------------------------------------------
+ * Dirac_common.h:94-162 */
+#define ELEM_LBA 0
+#define ELEM_HBA 1
+#define STAT_NONE 0
+#define STAT_SINGLE 1
+#define STAT_TILE 2
+#define HBA_TILE_SIZE 16
+#define DOBEAM_NONE 0
+#define DOBEAM_ARRAY 1
+#define DOBEAM_FULL 2
+#define DOBEAM_ELEMENT 3
+#define DOBEAM_ARRAY_WB 4
+#define DOBEAM_FULL_WB 5
+#define DOBEAM_ELEMENT_WB 6
+typedef struct elementcoff_ {
+  int M;      /* model order */
+  int Nmodes; /* M (M+1) / 2 */
+  int Nf;     /* frequencies of the wide-band tables (1 otherwise) */
+  double beta;
+  double *pattern_phi;   /* complex, Nmodes*Nf */
+  double *pattern_theta; /* complex, Nmodes*Nf */
+  double *preamble;      /* Nmodes */
+} elementcoeff;
+/* Dirac_radio.h:472,485,489 and their GPU-build twins :516,521,525 (predict_withbeam.c:553-723,
+ * 1219-1440, 1989-2315): the three coherency / prediction calls with the station beam towards every
+ * source folded in.  Array factor (STAT_SINGLE, STAT_TILE) and element beam (the caller's
+ * elementcoeff tables, set_elementcoeffs stays in the reference library) per timeslot and channel;
+ * doBeam DOBEAM_ARRAY / _FULL / _ELEMENT and their wide-band variants.  The lunar element beam
+ * (DOBEAM_ALO, needs CSPICE) is refused. */
+int precalculate_coherencies_withbeam(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double freq0, double fdelta, double tdelta, double dec0, double uvmin,
+    double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0,
+    double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz, int *Nelem,
+    double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt);
+int precalculate_coherencies_withbeam_gpu(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double freq0, double fdelta, double tdelta, double dec0, double uvmin,
+    double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0,
+    double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz, int *Nelem,
+    double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt);
+int predict_visibilities_multifreq_withbeam(
+    double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0, double ph_freq0,
+    double *longitude, double *latitude, double *time_utc, int *Nelem, double **xx, double **yy,
+    double **zz, elementcoeff *ecoeff, int doBeam, int Nt, int add_to_data);
+int predict_visibilities_multifreq_withbeam_gpu(
+    double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0, double ph_freq0,
+    double *longitude, double *latitude, double *time_utc, int *Nelem, double **xx, double **yy,
+    double **zz, elementcoeff *ecoeff, int doBeam, int Nt, int add_to_data);
+int calculate_residuals_multifreq_withbeam(
+    double *u, double *v, double *w, double *p, double *x, int N, int Nbase, int tilesz,
+    baseline_t *barr, clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta,
+    double tdelta, double dec0, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt,
+    int ccid, double rho, int phase_only);
+int calculate_residuals_multifreq_withbeam_gpu(
+    double *u, double *v, double *w, double *p, double *x, int N, int Nbase, int tilesz,
+    baseline_t *barr, clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta,
+    double tdelta, double dec0, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt,
+    int ccid, double rho, int phase_only);
+
 /* ---- multi-channel minibatch (stochastic) robust LBFGS, SURVEY.md 8f-3 ------------------------------
  * persistent_data_t: the reference declares it twice (Dirac.h:86-110 without HAVE_CUDA, :196-226 with);
  * the two layouts agree up to `Nt`, and this library touches nothing beyond that prefix (the running

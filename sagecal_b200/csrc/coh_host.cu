@@ -13,6 +13,7 @@ struct SkyDev {
   double *modes;
   CohSegment *segs;
   int nseg;
+  int nsrc;
 };
 
 static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream_t st) {
@@ -28,6 +29,8 @@ static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream
       d.ll = c.ll[s]; d.mm = c.mm[s]; d.nn = c.nn[s];
       d.sI = c.sI[s]; d.sQ = c.sQ[s]; d.sU = c.sU[s]; d.sV = c.sV[s];
       d.stype = (double)c.stype[s];
+      d.ra = c.ra ? c.ra[s] : 0.0;
+      d.dec = c.dec ? c.dec[s] : 0.0;
       if (c.stype[s] == STYPE_SHAPELET && c.ex && c.ex[s]) {
         const exinfo_shapelet *g = (const exinfo_shapelet *)c.ex[s];
         if (g->n0 < 1 || g->n0 > COH_SHAPELET_MAX_N0) {
@@ -88,6 +91,7 @@ static void sky_upload(const clus_source_t *carr, int M, SkyDev *sky, cudaStream
                            cudaMemcpyHostToDevice, st));
   db_stream_sync(st);  // the vectors go out of scope
   sky->nseg = (int)segs.size();
+  sky->nsrc = (int)src.size();
 }
 
 static void sky_free(SkyDev *sky) {
@@ -101,6 +105,120 @@ static double *upload_doubles(const double *h, size_t n, cudaStream_t st) {
   DB_CHECK(cudaMalloc((void **)&d, sizeof(double) * (n ? n : 1)));
   DB_CHECK(cudaMemcpyAsync(d, h, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   return d;
+}
+
+
+// ---- station beams (precalculate_coherencies_withbeam & co, predict_withbeam.c) -----------------------
+struct BeamSpec {
+  int bf_type;
+  double b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0;
+  const double *longitude, *latitude, *time_utc;
+  int tilesz;
+  const int *Nelem;
+  double **xx, **yy, **zz;
+  const elementcoeff *ecoeff;
+  int doBeam;
+};
+struct BeamDev {
+  double *af;
+  double2 *E;
+  std::vector<void *> owned;
+};
+// builds the per (timeslot, channel, source, station) tables on the device and points the coherency
+// kernel at them.  doBeam: Dirac_common.h:120-151
+static void beam_prepare(const BeamSpec *b, const SkyDev &sky, int N, int Nbase_slot,
+                         const double *freqs_host, int Nf, const double *freqs_dev,
+                         const baseline_t *barr, long long R, cudaStream_t st, CohArgs *a,
+                         BeamDev *bd) {
+  bd->af = nullptr;
+  bd->E = nullptr;
+  if (!b || b->doBeam == DOBEAM_NONE) return;
+  const bool wide = b->doBeam == DOBEAM_ARRAY_WB || b->doBeam == DOBEAM_FULL_WB ||
+                    b->doBeam == DOBEAM_ELEMENT_WB;
+  const bool do_array = b->doBeam == DOBEAM_ARRAY || b->doBeam == DOBEAM_FULL ||
+                        b->doBeam == DOBEAM_ARRAY_WB || b->doBeam == DOBEAM_FULL_WB;
+  const bool do_elem = b->doBeam == DOBEAM_ELEMENT || b->doBeam == DOBEAM_FULL ||
+                       b->doBeam == DOBEAM_ELEMENT_WB || b->doBeam == DOBEAM_FULL_WB;
+  if (!do_array && !do_elem) {
+    fprintf(stderr, "dirac_b200: beam mode %d is not supported (the lunar element beam needs "
+                    "CSPICE)\n", b->doBeam);
+    exit(1);
+  }
+  (void)freqs_host;
+  auto keep = [&](void *p) { bd->owned.push_back(p); return p; };
+  BeamArgs g;
+  memset(&g, 0, sizeof(g));
+  g.src = sky.src; g.S = sky.nsrc; g.freqs = freqs_dev; g.Nf = Nf; g.f0 = b->ph_freq0;
+  g.T = b->tilesz; g.N = N; g.bf_type = b->bf_type; g.b_ra0 = b->b_ra0; g.b_dec0 = b->b_dec0;
+  g.ra0 = b->ph_ra0; g.dec0 = b->ph_dec0; g.wideband = wide ? 1 : 0;
+  g.time_jd = (double *)keep(upload_doubles(b->time_utc, b->tilesz, st));
+  g.lon = (double *)keep(upload_doubles(b->longitude, N, st));
+  g.lat = (double *)keep(upload_doubles(b->latitude, N, st));
+  const size_t ntab = (size_t)b->tilesz * Nf * sky.nsrc * N;
+  if (do_array) {
+    if (b->bf_type != STAT_SINGLE && b->bf_type != STAT_TILE) {
+      fprintf(stderr, "dirac_b200: array beam needs bf_type STAT_SINGLE or STAT_TILE\n");
+      exit(1);
+    }
+    std::vector<int> off(N), ne(N);
+    std::vector<double> ex, ey, ez;
+    for (int n = 0; n < N; n++) {
+      off[n] = (int)ex.size();
+      ne[n] = b->Nelem[n];
+      const int len = b->Nelem[n] + (b->bf_type == STAT_TILE ? HBA_TILE_SIZE : 0);
+      ex.insert(ex.end(), b->xx[n], b->xx[n] + len);
+      ey.insert(ey.end(), b->yy[n], b->yy[n] + len);
+      ez.insert(ez.end(), b->zz[n], b->zz[n] + len);
+    }
+    int *doff = nullptr, *dne = nullptr;
+    DB_CHECK(cudaMalloc((void **)&doff, sizeof(int) * N));
+    DB_CHECK(cudaMalloc((void **)&dne, sizeof(int) * N));
+    DB_CHECK(cudaMemcpyAsync(doff, off.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    DB_CHECK(cudaMemcpyAsync(dne, ne.data(), sizeof(int) * N, cudaMemcpyHostToDevice, st));
+    keep(doff); keep(dne);
+    g.elem_off = doff; g.Nelem = dne;
+    g.ex = (double *)keep(upload_doubles(ex.data(), (long long)ex.size(), st));
+    g.ey = (double *)keep(upload_doubles(ey.data(), (long long)ey.size(), st));
+    g.ez = (double *)keep(upload_doubles(ez.data(), (long long)ez.size(), st));
+    DB_CHECK(cudaMalloc((void **)&bd->af, sizeof(double) * ntab));
+    g.af = bd->af;
+    db_stream_sync(st);  // the host vectors go out of scope
+  }
+  if (do_elem) {
+    const elementcoeff *ec = b->ecoeff;
+    const int nfc = wide ? ec->Nf : 1;
+    g.ecM = ec->M; g.ecNmodes = ec->Nmodes; g.ecbeta = ec->beta;
+    g.pat_phi = (double2 *)keep(upload_doubles(ec->pattern_phi, 2ll * ec->Nmodes * nfc, st));
+    g.pat_theta = (double2 *)keep(upload_doubles(ec->pattern_theta, 2ll * ec->Nmodes * nfc, st));
+    g.preamble = (double *)keep(upload_doubles(ec->preamble, ec->Nmodes, st));
+    DB_CHECK(cudaMalloc((void **)&bd->E, sizeof(double2) * 4 * ntab));
+    g.E = bd->E;
+  }
+  db_launch_beam_tables(&g, st);
+  db_count_launch(1);
+  // the coherency kernel needs the stations of every row now
+  if (!a->sta1) {
+    std::vector<int> s1(R), s2(R);
+    for (long long r = 0; r < R; r++) {
+      s1[r] = barr[r].sta1;
+      s2[r] = barr[r].sta2;
+    }
+    int *ds1 = nullptr, *ds2 = nullptr;
+    DB_CHECK(cudaMalloc((void **)&ds1, sizeof(int) * R));
+    DB_CHECK(cudaMalloc((void **)&ds2, sizeof(int) * R));
+    DB_CHECK(cudaMemcpyAsync(ds1, s1.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+    DB_CHECK(cudaMemcpyAsync(ds2, s2.data(), sizeof(int) * R, cudaMemcpyHostToDevice, st));
+    db_stream_sync(st);
+    keep(ds1); keep(ds2);
+    a->sta1 = ds1; a->sta2 = ds2;
+  }
+  a->beam_af = bd->af; a->beam_E = bd->E; a->beam_S = sky.nsrc; a->Nbase = Nbase_slot; a->N = N;
+}
+static void beam_free(BeamDev *bd) {
+  if (bd->af) cudaFree(bd->af);
+  if (bd->E) cudaFree(bd->E);
+  for (void *p : bd->owned) cudaFree(p);
+  bd->owned.clear();
 }
 
 extern "C" void dirac_b200_precalculate(dirac_b200_problem *pr, const double *u, const double *v,
@@ -137,11 +255,9 @@ extern "C" void dirac_b200_precalculate(dirac_b200_problem *pr, const double *u,
 
 // Dirac_radio.h:209 — here Nbase is already Nbase*tilesz (predict.c:503-578); rows need not be in
 // canonical order for this call (no station indexing), only flags are read/written.
-extern "C" int precalculate_coherencies(double *u, double *v, double *w, double *x, int N,
-                                        int Nbase, baseline_t *barr, clus_source_t *carr, int M,
-                                        double freq0, double fdelta, double tdelta, double dec0,
-                                        double uvmin, double uvmax, int Nt) {
-  (void)N; (void)tdelta; (void)dec0; (void)Nt;
+static int precalculate_impl(double *u, double *v, double *w, double *x, int N, int Nbase,
+                            baseline_t *barr, clus_source_t *carr, int M, double freq0,
+                            double fdelta, double uvmin, double uvmax, const BeamSpec *beam) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     fprintf(stderr, "dirac_b200: no CUDA device available. This library has no CPU fallback.\n");
@@ -166,6 +282,8 @@ extern "C" int precalculate_coherencies(double *u, double *v, double *w, double 
   a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.modes = sky.modes; a.segs = sky.segs; a.nseg = sky.nseg;
   a.freqs = df; a.Nchan = 1; a.fdelta2 = fdelta * 0.5; a.uvmin = uvmin; a.uvmax = uvmax;
   a.R = R; a.coh = dcoh; a.flag = dflag; a.xout = nullptr;
+  BeamDev bd;
+  beam_prepare(beam, sky, N, N * (N - 1) / 2, &freq0, 1, df, barr, R, st, &a, &bd);
   db_launch_coherencies(&a, st);
   db_count_launch(1);
   // planar -> API layout in row blocks, D2H
@@ -187,20 +305,51 @@ extern "C" int precalculate_coherencies(double *u, double *v, double *w, double 
   for (long long r = 0; r < R; r++) barr[r].flag = hf[r];
   cudaFree(stage); cudaFree(dcoh); cudaFree(dflag);
   cudaFree(du); cudaFree(dv); cudaFree(dw); cudaFree(df);
+  beam_free(&bd);
   sky_free(&sky);
   cudaStreamDestroy(st);
   return 0;
+}
+extern "C" int precalculate_coherencies(double *u, double *v, double *w, double *x, int N,
+                                        int Nbase, baseline_t *barr, clus_source_t *carr, int M,
+                                        double freq0, double fdelta, double tdelta, double dec0,
+                                        double uvmin, double uvmax, int Nt) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  return precalculate_impl(u, v, w, x, N, Nbase, barr, carr, M, freq0, fdelta, uvmin, uvmax, nullptr);
+}
+// Dirac_radio.h:472,516 (predict_withbeam.c:553-723): the same with the station beam towards every
+// source folded in: array factor (a real gain per station) and / or element beam (a 2x2 E-Jones per
+// station), evaluated per timeslot.  Nbase is Nbase*tilesz here too; rows in time order.
+extern "C" int precalculate_coherencies_withbeam(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double freq0, double fdelta, double tdelta, double dec0, double uvmin,
+    double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0,
+    double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz, int *Nelem,
+    double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  BeamSpec b = {bf_type, b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0, longitude, latitude, time_utc,
+                tilesz, Nelem, xx, yy, zz, ecoeff, doBeam};
+  return precalculate_impl(u, v, w, x, N, Nbase, barr, carr, M, freq0, fdelta, uvmin, uvmax, &b);
+}
+extern "C" int precalculate_coherencies_withbeam_gpu(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double freq0, double fdelta, double tdelta, double dec0, double uvmin,
+    double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0,
+    double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz, int *Nelem,
+    double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt) {
+  return precalculate_coherencies_withbeam(u, v, w, x, N, Nbase, barr, carr, M, freq0, fdelta, tdelta,
+                                           dec0, uvmin, uvmax, bf_type, b_ra0, b_dec0, ph_ra0,
+                                           ph_dec0, ph_freq0, longitude, latitude, time_utc, tilesz,
+                                           Nelem, xx, yy, zz, ecoeff, doBeam, Nt);
 }
 
 // Dirac_radio.h:659 (residual.c:1257-1340): x[chan][row][8] += sum over clusters; add_to_data ==
 // SIMUL_ONLY (1, Dirac_radio.h:78) clears x first, every other value accumulates onto the input
 // (the thread function only ever adds, residual.c:1238-1245).  No Jones, no flags.
-extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, double *x, int N,
-                                              int Nbase, int tilesz, baseline_t *barr,
-                                              clus_source_t *carr, int M, double *freqs, int Nchan,
-                                              double fdelta, double tdelta, double dec0, int Nt,
-                                              int add_to_data) {
-  (void)N; (void)barr; (void)tdelta; (void)dec0; (void)Nt;
+static int predict_multifreq_impl(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                  int tilesz, baseline_t *barr, clus_source_t *carr, int M,
+                                  double *freqs, int Nchan, double fdelta, int add_to_data,
+                                  const BeamSpec *beam) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     fprintf(stderr, "dirac_b200: no CUDA device available. This library has no CPU fallback.\n");
@@ -226,15 +375,52 @@ extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, d
   a.u = du; a.v = dv; a.w = dw; a.src = sky.src; a.modes = sky.modes; a.segs = sky.segs; a.nseg = sky.nseg;
   a.freqs = df; a.Nchan = Nchan; a.fdelta2 = (fdelta / (double)Nchan) * 0.5;
   a.R = R; a.xout = dx;
+  BeamDev bd;
+  beam_prepare(beam, sky, N, Nbase, freqs, Nchan, df, barr, R, st, &a, &bd);
   db_launch_predict_multifreq(&a, st);
   db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(x, dx, sizeof(double2) * nx, cudaMemcpyDeviceToHost, st));
   db_stream_sync(st);
   DB_CHECK(cudaGetLastError());
   cudaFree(dx); cudaFree(du); cudaFree(dv); cudaFree(dw); cudaFree(df);
+  beam_free(&bd);
   sky_free(&sky);
   cudaStreamDestroy(st);
   return 0;
+}
+extern "C" int predict_visibilities_multifreq(double *u, double *v, double *w, double *x, int N,
+                                              int Nbase, int tilesz, baseline_t *barr,
+                                              clus_source_t *carr, int M, double *freqs, int Nchan,
+                                              double fdelta, double tdelta, double dec0, int Nt,
+                                              int add_to_data) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  return predict_multifreq_impl(u, v, w, x, N, Nbase, tilesz, barr, carr, M, freqs, Nchan, fdelta,
+                                add_to_data, nullptr);
+}
+// Dirac_radio.h:485,521 (predict_withbeam.c:1219-1440): per-channel station beams
+extern "C" int predict_visibilities_multifreq_withbeam(
+    double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0, double ph_freq0,
+    double *longitude, double *latitude, double *time_utc, int *Nelem, double **xx, double **yy,
+    double **zz, elementcoeff *ecoeff, int doBeam, int Nt, int add_to_data) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  BeamSpec b = {bf_type, b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0, longitude, latitude, time_utc,
+                tilesz, Nelem, xx, yy, zz, ecoeff, doBeam};
+  return predict_multifreq_impl(u, v, w, x, N, Nbase, tilesz, barr, carr, M, freqs, Nchan, fdelta,
+                                add_to_data, &b);
+}
+extern "C" int predict_visibilities_multifreq_withbeam_gpu(
+    double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0, double ph_freq0,
+    double *longitude, double *latitude, double *time_utc, int *Nelem, double **xx, double **yy,
+    double **zz, elementcoeff *ecoeff, int doBeam, int Nt, int add_to_data) {
+  return predict_visibilities_multifreq_withbeam(u, v, w, x, N, Nbase, tilesz, barr, carr, M, freqs,
+                                                 Nchan, fdelta, tdelta, dec0, bf_type, b_ra0, b_dec0,
+                                                 ph_ra0, ph_dec0, ph_freq0, longitude, latitude,
+                                                 time_utc, Nelem, xx, yy, zz, ecoeff, doBeam, Nt,
+                                                 add_to_data);
 }
 
 // 2x2 inverse of (J + rho I) with the reference's guard on a small determinant (mat_invert,
@@ -258,12 +444,10 @@ static void jones_invert(const double xx[8], double yy[8], double rho) {
 // re-predicted from the sources at every channel frequency; then, if a cluster has id == ccid, every
 // row is corrected by that cluster's inverse Jones (J + rho I)^-1.  phase_only != 0 (correction by the
 // phases of a joint diagonalisation, manifold_average.c) is not implemented: returns -1.
-extern "C" int calculate_residuals_multifreq(double *u, double *v, double *w, double *p, double *x,
-                                             int N, int Nbase, int tilesz, baseline_t *barr,
-                                             clus_source_t *carr, int M, double *freqs, int Nchan,
-                                             double fdelta, double tdelta, double dec0, int Nt,
-                                             int ccid, double rho, int phase_only) {
-  (void)tdelta; (void)dec0; (void)Nt;
+static int residuals_multifreq_impl(double *u, double *v, double *w, double *p, double *x, int N,
+                                    int Nbase, int tilesz, baseline_t *barr, clus_source_t *carr,
+                                    int M, double *freqs, int Nchan, double fdelta, int ccid,
+                                    double rho, int phase_only, const BeamSpec *beam) {
   if (phase_only) {
     fprintf(stderr, "dirac_b200: calculate_residuals_multifreq: phase_only correction is not "
                     "implemented\n");
@@ -335,6 +519,8 @@ extern "C" int calculate_residuals_multifreq(double *u, double *v, double *w, do
   a.R = R; a.xout = dx; a.sta1 = ds1; a.sta2 = ds2; a.p = dp; a.clus_nchunk = dn;
   a.clus_chunk0 = dc0; a.chunk_poff = dpo; a.clus_sub = dsub; a.pinv = dpinv;
   a.pinv_nchunk = cm >= 0 ? carr[cm].nchunk : 1; a.N = N;
+  BeamDev bd;
+  beam_prepare(beam, sky, N, Nbase, freqs, Nchan, df, barr, R, st, &a, &bd);
   db_launch_residual_multifreq(&a, st);
   db_count_launch(1);
   DB_CHECK(cudaMemcpyAsync(x, dx, sizeof(double2) * nx, cudaMemcpyDeviceToHost, st));
@@ -343,7 +529,44 @@ extern "C" int calculate_residuals_multifreq(double *u, double *v, double *w, do
   cudaFree(dx); cudaFree(du); cudaFree(dv); cudaFree(dw); cudaFree(df); cudaFree(dp);
   if (dpinv) cudaFree(dpinv);
   cudaFree(dn); cudaFree(dc0); cudaFree(dpo); cudaFree(ds1); cudaFree(ds2); cudaFree(dsub);
+  beam_free(&bd);
   sky_free(&sky);
   cudaStreamDestroy(st);
   return 0;
+}
+extern "C" int calculate_residuals_multifreq(double *u, double *v, double *w, double *p, double *x,
+                                             int N, int Nbase, int tilesz, baseline_t *barr,
+                                             clus_source_t *carr, int M, double *freqs, int Nchan,
+                                             double fdelta, double tdelta, double dec0, int Nt,
+                                             int ccid, double rho, int phase_only) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  return residuals_multifreq_impl(u, v, w, p, x, N, Nbase, tilesz, barr, carr, M, freqs, Nchan, fdelta,
+                                  ccid, rho, phase_only, nullptr);
+}
+// Dirac_radio.h:489,525 (predict_withbeam.c:1989-2315): per-channel station beams in the re-prediction
+extern "C" int calculate_residuals_multifreq_withbeam(
+    double *u, double *v, double *w, double *p, double *x, int N, int Nbase, int tilesz,
+    baseline_t *barr, clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta,
+    double tdelta, double dec0, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt,
+    int ccid, double rho, int phase_only) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  BeamSpec b = {bf_type, b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0, longitude, latitude, time_utc,
+                tilesz, Nelem, xx, yy, zz, ecoeff, doBeam};
+  return residuals_multifreq_impl(u, v, w, p, x, N, Nbase, tilesz, barr, carr, M, freqs, Nchan, fdelta,
+                                  ccid, rho, phase_only, &b);
+}
+extern "C" int calculate_residuals_multifreq_withbeam_gpu(
+    double *u, double *v, double *w, double *p, double *x, int N, int Nbase, int tilesz,
+    baseline_t *barr, clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta,
+    double tdelta, double dec0, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt,
+    int ccid, double rho, int phase_only) {
+  return calculate_residuals_multifreq_withbeam(u, v, w, p, x, N, Nbase, tilesz, barr, carr, M, freqs,
+                                                Nchan, fdelta, tdelta, dec0, bf_type, b_ra0, b_dec0,
+                                                ph_ra0, ph_dec0, ph_freq0, longitude, latitude,
+                                                time_utc, Nelem, xx, yy, zz, ecoeff, doBeam, Nt, ccid,
+                                                rho, phase_only);
 }

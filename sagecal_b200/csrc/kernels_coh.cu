@@ -156,11 +156,12 @@ k_sky_predict(CohArgs a) {
     w = a.w[r];
   }
   const int nchan = (MODE == 0) ? 1 : a.Nchan;
-  int s1 = 0, s2 = 0;
-  if (MODE == 2 && active) {
+  int s1 = 0, s2 = 0, tslot = 0;
+  if ((MODE == 2 || a.sta1) && active) {
     s1 = a.sta1[r];
     s2 = a.sta2[r];
   }
+  if (a.beam_af || a.beam_E) tslot = (int)(r / a.Nbase);
   // prologue: stage segment 0
   if (threadIdx.x == 0 && a.nseg > 0) {
     const CohSegment sg = a.segs[0];
@@ -200,7 +201,14 @@ k_sky_predict(CohArgs a) {
       if (active) {
         for (int s = 0; s < sg.count; s++) {
           const DevSource &S = sbuf[b][s];
-          const double2 ph = source_phase(S, a.modes, u, v, w, freq, a.fdelta2);
+          double2 ph = source_phase(S, a.modes, u, v, w, freq, a.fdelta2);
+          // station beams towards this source at this timeslot and channel
+          const size_t bt = ((size_t)tslot * nchan + cf) * a.beam_S + (size_t)(sg.first + s);
+          if (a.beam_af) {  // array factor of both stations (predict_withbeam.c:336-343)
+            const double af = a.beam_af[bt * a.N + s1] * a.beam_af[bt * a.N + s2];
+            ph.x *= af;
+            ph.y *= af;
+          }
           double I = S.sI, Q = S.sQ, U = S.sU, V = S.sV;
           if (MODE >= 1 && S.spec_idx != 0.0) {
             const double fr = log(freq / S.f0);
@@ -211,7 +219,22 @@ k_sky_predict(CohArgs a) {
             U = spec_flux(S.sU0, tf);
             V = spec_flux(S.sV0, tf);
           }
-          add_stokes(C, ph, I, Q, U, V);
+          if (a.beam_E) {  // E_p (Stokes coherency) E_q^H  (predict_withbeam.c:381-404)
+            double2 C0[4], T1[4], E1[4], E2[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              C0[c] = make_double2(0.0, 0.0);
+              E1[c] = a.beam_E[(bt * a.N + s1) * 4 + c];
+              E2[c] = a.beam_E[(bt * a.N + s2) * 4 + c];
+            }
+            add_stokes(C0, ph, I, Q, U, V);
+            mat_ab(E1, C0, T1);
+            mat_abh(T1, E2, C0);
+#pragma unroll
+            for (int c = 0; c < 4; c++) C[c] = cadd(C[c], C0[c]);
+          } else {
+            add_stokes(C, ph, I, Q, U, V);
+          }
         }
         if (sg.last) {
           if (MODE == 0) {
@@ -267,7 +290,157 @@ k_sky_predict(CohArgs a) {
   }
 }
 
+// ---- station beam tables ----------------------------------------------------------------------------
+// JD -> Greenwich mean sidereal angle in degrees (jd2gmst, transforms.c:139-146)
+__device__ __forceinline__ double jd2gmst_deg(double time_jd) {
+  const double t = (time_jd - 2451545.0) / 36525.0;
+  const double theta =
+      67310.54841 + t * ((876600.0 * 3600.0 + 8640184.812866) + t * (0.093104 - (6.2 * 10e-6) * t));
+  return fmod(fmod(theta, 86400.0 * (theta / fabs(theta))) / 240.0, 360.0);
+}
+// (ra, dec) -> (az, el) at a station (radec2azel_gmst, transforms.c:157-180)
+__device__ __forceinline__ void radec2azel(double ra, double dec, double lon, double lat,
+                                           double gmst, double *az, double *el) {
+  const double lst = gmst + lon * 180.0 * M_1_PI;
+  const double LHA = fmod(lst - ra * 180.0 * M_1_PI, 360.0);
+  double sinlat, coslat, sindec, cosdec, sinL, cosL;
+  sincos(lat, &sinlat, &coslat);
+  sincos(dec, &sindec, &cosdec);
+  sincos(LHA * M_PI / 180.0, &sinL, &cosL);
+  const double tmp = sinlat * sindec + coslat * cosdec * cosL;
+  *el = asin(tmp);
+  double sinel, cosel;
+  sincos(*el, &sinel, &cosel);
+  double a = fmod(atan2(-sinL * cosdec / cosel, (sindec - sinel * sinlat) / (cosel * coslat)),
+                  2.0 * M_PI);
+  if (a < 0) a += 2.0 * M_PI;
+  *az = a;
+}
+// generalised Laguerre polynomial L_p^q(x) (L_g1, elementbeam.c:341-356)
+__device__ __forceinline__ double laguerre(int p, int q, double x) {
+  if (p == 0) return 1.0;
+  if (p == 1) return 1.0 - x + (double)q;
+  double Lp = 0.0, Lp1 = 1.0 - x + (double)q, Lp2 = 1.0;
+  for (int i = 2; i <= p; i++) {
+    const double p1 = 1.0 / (double)i;
+    Lp = (2.0 + p1 * ((double)q - 1.0 - x)) * Lp1 - (1.0 + p1 * (q - 1)) * Lp2;
+    Lp2 = Lp1;
+    Lp1 = Lp;
+  }
+  return Lp;
+}
+// element pattern (theta, phi components) at zenith angle r and azimuth th (eval_elementcoeffs[_wb],
+// elementbeam.c:384-460); coefficient set `fi` of the wide-band tables
+__device__ __forceinline__ void element_eval(const BeamArgs &a, double r, double th, int fi,
+                                             double2 *e_theta, double2 *e_phi) {
+  const double rb = pow(r / a.ecbeta, 2);
+  const double ex = exp(-0.5 * rb);
+  double2 ph = make_double2(0.0, 0.0), tt = make_double2(0.0, 0.0);
+  int idx = 0;
+  for (int n = 0; n < a.ecM; n++)
+    for (int m = -n; m <= n; m += 2) {
+      const int absm = m >= 0 ? m : -m;
+      const double Lg = laguerre((n - absm) / 2, absm, rb);
+      const double rm = pow(M_PI_4 + r, (double)absm);
+      double s, c;
+      sincos(-(double)m * th, &s, &c);
+      const double pr = rm * Lg * ex * a.preamble[idx];
+      const double2 basis = make_double2(pr * c, pr * s);
+      cfma(ph, a.pat_phi[(size_t)fi * a.ecNmodes + idx], basis);
+      cfma(tt, a.pat_theta[(size_t)fi * a.ecNmodes + idx], basis);
+      idx++;
+    }
+  *e_theta = tt;
+  *e_phi = ph;
+}
+
+// one thread per (timeslot, channel, source, station): array factor (arraybeam / array_element_beam,
+// stationbeam.c:49-330) and element E-Jones (element_beam, :372-430)
+__global__ void __launch_bounds__(128) k_beam_tables(BeamArgs a) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)a.T * a.Nf * a.S * a.N;
+  if (gid >= total) return;
+  const int sta = (int)(gid % a.N);
+  size_t q = gid / a.N;
+  const int s = (int)(q % a.S);
+  q /= a.S;
+  const int cf = (int)(q % a.Nf);
+  const int t = (int)(q / a.Nf);
+  const double gmst = jd2gmst_deg(a.time_jd[t]);
+  const double ra = a.src[s].ra, dec = a.src[s].dec;
+  const double f = a.freqs[cf];
+  double az, el;
+  radec2azel(ra, dec, a.lon[sta], a.lat[sta], gmst, &az, &el);
+  const double theta = M_PI_2 - el;
+  if (a.af) {
+    double gain = 0.0;
+    if (el >= 0.0) {
+      const double tpc = 2.0 * M_PI / 299792458.0;
+      const double beam_f = a.wideband ? f : a.f0;
+      double az0, el0;
+      radec2azel(a.ra0, a.dec0, a.lon[sta], a.lat[sta], gmst, &az0, &el0);
+      double sint, cost, sinph, cosph, sint0, cost0, sinph0, cosph0;
+      sincos(theta, &sint, &cost);
+      sincos(-az, &sinph, &cosph);
+      sincos(M_PI_2 - el0, &sint0, &cost0);
+      sincos(-az0, &sinph0, &cosph0);
+      double rat1 = beam_f * sint0;
+      const double rat2 = f * sint;
+      double r1 = rat1 * cosph0 - rat2 * cosph, r2 = rat1 * sinph0 - rat2 * sinph;
+      double r3 = beam_f * cost0 - f * cost;
+      const int K = a.Nelem[sta];
+      const double *px = a.ex + a.elem_off[sta], *py = a.ey + a.elem_off[sta];
+      const double *pz = a.ez + a.elem_off[sta];
+      const int skip = a.bf_type == 2 ? 16 : 0;  // STAT_TILE: tile centroids follow the 16 dipoles
+      double csum = 0.0, ssum = 0.0;
+      for (int j = 0; j < K; j++) {
+        double sn, cs;
+        sincos(-tpc * (r1 * px[j + skip] + r2 * py[j + skip] + r3 * pz[j + skip]), &sn, &cs);
+        ssum += sn;
+        csum += cs;
+      }
+      if (a.bf_type == 2) {
+        double azb, elb;
+        radec2azel(a.b_ra0, a.b_dec0, a.lon[sta], a.lat[sta], gmst, &azb, &elb);
+        sincos(M_PI_2 - elb, &sint0, &cost0);
+        sincos(-azb, &sinph0, &cosph0);
+        rat1 = beam_f * sint0;
+        r1 = rat1 * cosph0 - rat2 * cosph;
+        r2 = rat1 * sinph0 - rat2 * sinph;
+        r3 = beam_f * cost0 - f * cost;
+        double cb = 0.0, sb = 0.0;
+        for (int j = 0; j < 16; j++) {
+          double sn, cs;
+          sincos(-tpc * (r1 * px[j] + r2 * py[j] + r3 * pz[j]), &sn, &cs);
+          sb += sn;
+          cb += cs;
+        }
+        gain = sqrt(csum * csum + ssum * ssum) * sqrt(cb * cb + sb * sb) / (double)(K * 16);
+      } else {
+        gain = sqrt(csum * csum + ssum * ssum) / (double)K;
+      }
+    }
+    a.af[gid] = gain;
+  }
+  if (a.E) {
+    double2 e[4];
+    e[0] = e[1] = e[2] = e[3] = make_double2(0.0, 0.0);
+    if (el >= 0.0) {
+      const int fi = a.wideband ? cf : 0;
+      // E = [E_theta(az - pi/4) E_phi(az - pi/4); E_theta(az + pi/4) E_phi(az + pi/4)]
+      element_eval(a, theta, az - M_PI_4, fi, &e[0], &e[1]);
+      element_eval(a, theta, az - M_PI_4 + M_PI_2, fi, &e[2], &e[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) a.E[gid * 4 + c] = e[c];
+  }
+}
+
 extern "C" {
+void db_launch_beam_tables(const BeamArgs *a, cudaStream_t st) {
+  const size_t total = (size_t)a->T * a->Nf * a->S * a->N;
+  k_beam_tables<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(*a);
+}
 void db_launch_coherencies(const CohArgs *a, cudaStream_t st) {
   unsigned grid = (unsigned)((a->R + COH_THREADS - 1) / COH_THREADS);
   k_sky_predict<0><<<grid, COH_THREADS, 0, st>>>(*a);

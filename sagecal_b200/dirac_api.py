@@ -168,6 +168,44 @@ class SkyModel:
         self.nparam = off - int(p_base)
 
 
+class elementcoeff(C.Structure):
+    """Dirac_common.h:153-162 — element beam coefficient tables (filled by the REFERENCE library's
+    set_elementcoeffs / set_elementcoeffs_wb; this library only evaluates them)"""
+    _fields_ = [("M", C.c_int), ("Nmodes", C.c_int), ("Nf", C.c_int), ("beta", C.c_double),
+                ("pattern_phi", C.c_void_p), ("pattern_theta", C.c_void_p),
+                ("preamble", C.c_void_p)]
+
+
+class BeamSetup:
+    """the beam arguments of the *_withbeam calls, with the numpy buffers behind them"""
+
+    def __init__(self, bf_type, b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0, longitude, latitude,
+                 time_utc, elem_xyz, ecoeff, doBeam, Nelem=None):
+        """elem_xyz: per station an array [n][3] of element positions (STAT_TILE: the 16 dipoles of a
+        tile first, then the tile centroids; Nelem then counts the tiles)"""
+        self.bf_type, self.doBeam = int(bf_type), int(doBeam)
+        self.s = [C.c_double(float(v)) for v in (b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0)]
+        self.lon = np.ascontiguousarray(longitude, dtype=np.float64)
+        self.lat = np.ascontiguousarray(latitude, dtype=np.float64)
+        self.t = np.ascontiguousarray(time_utc, dtype=np.float64)
+        self.tilesz = len(self.t)
+        N = len(self.lon)
+        self.xyz = [np.ascontiguousarray(np.asarray(e, dtype=np.float64).T) for e in elem_xyz]
+        extra = 16 if self.bf_type == 2 else 0
+        self.Nelem = np.ascontiguousarray(
+            Nelem if Nelem is not None else [e.shape[1] - extra for e in self.xyz], dtype=np.int32)
+        mk = lambda axis: (c_double_p * N)(*[dptr(e[axis]) for e in self.xyz])
+        self.xx, self.yy, self.zz = mk(0), mk(1), mk(2)
+        self.ecoeff = ecoeff
+
+    def head(self):
+        return (self.bf_type, *self.s, dptr(self.lon), dptr(self.lat), dptr(self.t))
+
+    def tail(self):
+        ec = C.byref(self.ecoeff) if self.ecoeff is not None else None
+        return (self.Nelem.ctypes.data_as(c_int_p), self.xx, self.yy, self.zz, ec, self.doBeam)
+
+
 def make_barr(sta1, sta2, flag):
     n = len(sta1)
     barr = (baseline_t * n)()
@@ -254,6 +292,34 @@ class DiracAPI:
         return self.lib.calculate_residuals_multifreq(
             dptr(u), dptr(v), dptr(w), dptr(p), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M,
             dptr(freqs), len(freqs), fdelta, tdelta, dec0, Nt, ccid, rho, phase_only)
+
+    # ---- station beams (Dirac_radio.h:472-490) ----
+    def precalculate_coherencies_withbeam(self, u, v, w, N, Nbase1, barr, sky, freq0, fdelta, beam,
+                                          tdelta=10.0, dec0=1.0, uvmin=0.0, uvmax=1e9, Nt=4):
+        coh = np.zeros(4 * sky.M * Nbase1, dtype=np.complex128)
+        self.lib.precalculate_coherencies_withbeam(
+            dptr(u), dptr(v), dptr(w), cptr(coh), N, Nbase1, barr, sky.arr, sky.M,
+            C.c_double(freq0), C.c_double(fdelta), C.c_double(tdelta), C.c_double(dec0),
+            C.c_double(uvmin), C.c_double(uvmax), *beam.head(), beam.tilesz, *beam.tail(), Nt)
+        return coh
+
+    def predict_visibilities_multifreq_withbeam(self, u, v, w, x, N, Nbase, tilesz, barr, sky, freqs,
+                                                fdelta, beam, tdelta=10.0, dec0=1.0, Nt=4,
+                                                add_to_data=1):
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        return self.lib.predict_visibilities_multifreq_withbeam(
+            dptr(u), dptr(v), dptr(w), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M, dptr(freqs),
+            len(freqs), C.c_double(fdelta), C.c_double(tdelta), C.c_double(dec0), *beam.head(),
+            *beam.tail(), Nt, add_to_data)
+
+    def calculate_residuals_multifreq_withbeam(self, u, v, w, p, x, N, Nbase, tilesz, barr, sky,
+                                               freqs, fdelta, beam, tdelta=10.0, dec0=1.0, Nt=4,
+                                               ccid=-99999, rho=1e-9, phase_only=0):
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        return self.lib.calculate_residuals_multifreq_withbeam(
+            dptr(u), dptr(v), dptr(w), dptr(p), dptr(x), N, Nbase, tilesz, barr, sky.arr, sky.M,
+            dptr(freqs), len(freqs), C.c_double(fdelta), C.c_double(tdelta), C.c_double(dec0),
+            *beam.head(), *beam.tail(), Nt, ccid, C.c_double(rho), phase_only)
 
     def sagefit_visibilities(self, u, v, w, x, N, Nbase, tilesz, barr, sky: SkyModel, coh, pp,
                              freq0=150e6, fdelta=195.3e3, uvmin=0.0, Nt=4, max_emiter=3,

@@ -31,6 +31,9 @@ EXPORTED = [
     "calculate_residuals_multifreq", "dirac_b200_bigtri_solve", "dirac_b200_release_cache",
     "dirac_b200_sagefit_admm_rtr", "lbfgs_persist_init", "lbfgs_persist_clear",
     "lbfgs_persist_reset", "bfgsfit_minibatch_visibilities", "bfgsfit_minibatch_consensus",
+    "precalculate_coherencies_withbeam", "precalculate_coherencies_withbeam_gpu",
+    "predict_visibilities_multifreq_withbeam", "predict_visibilities_multifreq_withbeam_gpu",
+    "calculate_residuals_multifreq_withbeam", "calculate_residuals_multifreq_withbeam_gpu",
 ]
 
 

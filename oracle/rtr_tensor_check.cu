@@ -60,29 +60,45 @@ struct TensorEval {
     }
     return slw;
   }
-  // what k_rtr_eval does, station by station
+  // what k_rtr_eval does: station by station, every baseline end spread over 16 lanes, the lanes'
+  // terms summed over the ends, folded once per station
   void raw(const double *x, const double *eta, double *fcost, double *vec) {
     double cost = 0.0;
     for (int s = 0; s < N; s++) {
-      double2 Gs[4], Es[4], acc[4];
+      double2 Gs[4], Es[4], tP[16], tQ[16];
       jones(x, s, Gs);
       if (eta) jones(eta, s, Es);
-      for (int i = 0; i < 4; i++) acc[i] = make_double2(0, 0);
+      for (int i = 0; i < 16; i++) tP[i] = tQ[i] = make_double2(0, 0);
       for (int o = 0; o < N; o++) {
         if (o == s) continue;
         const bool sp = s < o;
         const int p = sp ? s : o, q = sp ? o : s;
         const size_t b = (size_t)baseline_index(p, q, N);
         if (!vec && !(fcost && sp)) continue;
-        double2 Go[4], Eo[4], Tb[16], W[16];
+        double2 Go[4], Eo[4];
         jones(x, o, Go);
         if (eta) jones(eta, o, Eo);
-        for (int i = 0; i < 16; i++) { Tb[i] = T[b * 16 + i]; W[i] = D[b * 16 + i]; }
-        rtr_eval_baseline(sp, Gs, Go, Es, Eo, Tb, W, c0[b], eta != nullptr, fcost != nullptr,
-                          vec != nullptr, acc, &cost);
+        if (fcost && sp) cost += c0[b];
+        for (int lane = 0; lane < 16; lane++) {
+          const int mj = lane & 3, ab = lane >> 2;
+          double2 Tc[4];
+          for (int k = 0; k < 4; k++) Tc[k] = T[b * 16 + 4 * k + mj];
+          double2 term = make_double2(0, 0);
+          const int la = (lane >> 3) & 1, lb = (lane >> 2) & 1;
+          const double2 *Gp = sp ? Gs : Go, *Gq = sp ? Go : Gs, *Ep = sp ? Es : Eo, *Eq = sp ? Eo : Es;
+          rtr_lane_terms(lane, sp, Gp + 2 * la, Gq + 2 * lb, Ep + 2 * la, Eq + 2 * lb, Tc,
+                         D[b * 16 + 4 * ab + mj], eta != nullptr, fcost != nullptr, vec != nullptr,
+                         &term, &cost);
+          if (sp) tP[lane] = cadd(tP[lane], term);
+          else tQ[lane] = cadd(tQ[lane], term);
+        }
       }
       if (vec)
-        for (int i = 0; i < 4; i++) { vec[8 * s + 2 * i] = acc[i].x; vec[8 * s + 2 * i + 1] = acc[i].y; }
+        for (int e = 0; e < 4; e++) {
+          const double2 v = rtr_lane_fold(tP, tQ, e);
+          vec[8 * s + 2 * e] = v.x;
+          vec[8 * s + 2 * e + 1] = v.y;
+        }
     }
     if (fcost) *fcost = cost;
   }

@@ -78,77 +78,143 @@ __global__ void k_rtr_reduce(const double *in, double *out, size_t n, int ns) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_rtr_eval: CTA = station s, threads = the other stations o (one baseline per thread up to 257
-// stations, a short loop beyond).  o > s: baseline (s,o), s plays p; o < s: baseline (o,s), s plays q.
-// Every baseline is visited from both ends: no atomics, and the sums are bit-reproducible.
+// k_rtr_eval: CTA = station s; every baseline end of s is spread over 16 lanes (one tensor entry
+// [(ab),(mj)] each, rtr_math.cuh: rtr_lane_terms), two ends per warp.  o > s: baseline (s,o), s plays
+// p; o < s: baseline (o,s), s plays q.  The lanes' terms are summed over the ends in registers, over
+// the half-warps by one shuffle, over the warps in shared memory in a fixed order, and folded (4
+// lanes per 2x2 entry) once per station: no atomics, bit-reproducible.  Every baseline is visited from
+// both ends.  The dependent chain per thread is ~40 DFMA (12 complex MACs for a Hessian product)
+// instead of ~1000 when one thread evaluated a whole end.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_rtr_eval(RtrEvalArgs a) {
+__device__ __forceinline__ const RtrEvalArgs &rtr_base(const RtrEvalArgs &P) { return P; }
+__device__ __forceinline__ const RtrEvalArgs &rtr_base(const RtrEvalInl &P) { return P.a; }
+__device__ __forceinline__ const double2 *rtr_x(const RtrEvalArgs &P) {
+  return reinterpret_cast<const double2 *>(P.x);
+}
+__device__ __forceinline__ const double2 *rtr_x(const RtrEvalInl &P) {
+  return reinterpret_cast<const double2 *>(P.xin);
+}
+__device__ __forceinline__ const double2 *rtr_e(const RtrEvalArgs &P) {
+  return reinterpret_cast<const double2 *>(P.eta);
+}
+__device__ __forceinline__ const double2 *rtr_e(const RtrEvalInl &P) {
+  return reinterpret_cast<const double2 *>(P.ein);
+}
+
+// ARGS = RtrEvalArgs: Jones / tangent vector in device memory; RtrEvalInl: in the parameter block
+// (read through the constant bank, no copy in front of the launch)
+template <class ARGS>
+__global__ void __launch_bounds__(512) k_rtr_eval(const __grid_constant__ ARGS P) {
+  const RtrEvalArgs &a = rtr_base(P);
   const int s = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  double2 Gs[4], Es[4];
-  load_jones(a.x, s, Gs);
+  const int lane16 = threadIdx.x & 15, grp = threadIdx.x >> 4, ngrp = blockDim.x >> 4;
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int mj = lane16 & 3, ab = lane16 >> 2;
+  const int la = ab >> 1, lb = ab & 1;
   const bool hess = a.eta != nullptr;
-  if (hess) load_jones(a.eta, s, Es);
-  double2 acc[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) acc[i] = make_double2(0, 0);
+  const double2 *X = rtr_x(P);
+  const double2 *Et = rtr_e(P);
+  const bool want_cost = a.cost != nullptr, want_vec = a.out != nullptr;
+  double2 tP = make_double2(0, 0), tQ = make_double2(0, 0);
   double cost = 0.0, cnt = 0.0;
-  for (int o = threadIdx.x; o < a.N; o += blockDim.x) {
+  for (int o = grp; o < a.N; o += ngrp) {
     if (o == s) continue;
     const bool sp = s < o;  // s plays p
     const int p = sp ? s : o, q = sp ? o : s;
     const size_t b = (size_t)baseline_index(p, q, a.N);
-    if (a.count) cnt += a.sc[2 * (size_t)a.Nbase + b];
-    if (!a.out && !(a.cost && sp)) continue;
-    double2 Go[4], Eo[4];
-    load_jones(a.x, o, Go);
-    if (hess) load_jones(a.eta, o, Eo);
-    double2 T[16], W[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-      T[i] = a.TD[(size_t)i * a.Nbase + b];
-      W[i] = a.TD[(size_t)(16 + i) * a.Nbase + b];
+    if (a.count && lane16 == 0) cnt += a.sc[2 * (size_t)a.Nbase + b];
+    if (!want_vec && !(want_cost && sp)) continue;
+    // row a of the p station's Jones, row b of the q station's (and of the tangent vector)
+    double2 Gpa[2], Gqb[2], Epa[2], Eqb[2];
+    Gpa[0] = X[4 * p + 2 * la];
+    Gpa[1] = X[4 * p + 2 * la + 1];
+    Gqb[0] = X[4 * q + 2 * lb];
+    Gqb[1] = X[4 * q + 2 * lb + 1];
+    if (hess) {
+      Epa[0] = Et[4 * p + 2 * la];
+      Epa[1] = Et[4 * p + 2 * la + 1];
+      Eqb[0] = Et[4 * q + 2 * lb];
+      Eqb[1] = Et[4 * q + 2 * lb + 1];
     }
-    rtr_eval_baseline(sp, Gs, Go, Es, Eo, T, W, a.sc[b], hess, a.cost != nullptr,
-                      a.out != nullptr, acc, &cost);
-  }
-  // 10 sums per station: warp butterflies, then the warps' partials in order through shared memory
-  __shared__ double part[8][10];
-  double v[10] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, acc[3].x, acc[3].y,
-                  cost, cnt};
+    double2 Tc[4];
 #pragma unroll
-  for (int i = 0; i < 10; i++) {
-    v[i] = warp_sum(v[i]);
-    if (lane == 0) part[warp][i] = v[i];
+    for (int k = 0; k < 4; k++) Tc[k] = a.TD[(size_t)(4 * k + mj) * a.Nbase + b];
+    const double2 Dv = a.TD[(size_t)(16 + 4 * ab + mj) * a.Nbase + b];
+    if (want_cost && sp && lane16 == 0) cost += a.sc[b];
+    double2 term = make_double2(0, 0);
+    rtr_lane_terms(lane16, sp, Gpa, Gqb, Epa, Eqb, Tc, Dv, hess, want_cost, want_vec, &term, &cost);
+    if (sp) tP = cadd(tP, term);
+    else tQ = cadd(tQ, term);
+  }
+  // the two half-warps (two ends) of a warp, then the warps in order
+  __shared__ double2 shP[16][16], shQ[16][16];
+  __shared__ double shc[16][2];
+  tP.x += __shfl_xor_sync(0xffffffffu, tP.x, 16);
+  tP.y += __shfl_xor_sync(0xffffffffu, tP.y, 16);
+  tQ.x += __shfl_xor_sync(0xffffffffu, tQ.x, 16);
+  tQ.y += __shfl_xor_sync(0xffffffffu, tQ.y, 16);
+  cost = warp_sum(cost);
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) < 16) {
+    shP[warp][lane16] = tP;
+    shQ[warp][lane16] = tQ;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    shc[warp][0] = cost;
+    shc[warp][1] = cnt;
   }
   __syncthreads();
-  if (threadIdx.x < 10) {
-    double t = 0.0;
-    for (int w = 0; w < nwarp; w++) t += part[w][threadIdx.x];
-    const int i = threadIdx.x;
-    if (i < 8) {
-      if (a.out) a.out[8 * (size_t)s + i] = t;
-    } else if (i == 8) {
-      if (a.cost) a.cost[s] = t;
-    } else if (a.count) {
-      a.count[s] = t;
+  if (threadIdx.x < 16) {  // lane sums over the warps
+    double2 p = make_double2(0, 0), q = make_double2(0, 0);
+    for (int w = 0; w < nwarp; w++) {
+      p = cadd(p, shP[w][threadIdx.x]);
+      q = cadd(q, shQ[w][threadIdx.x]);
     }
-    if (a.flag) __threadfence_system();
+    shP[0][threadIdx.x] = p;
+    shQ[0][threadIdx.x] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    if (a.out) {
+      const double2 v = rtr_lane_fold(shP[0], shQ[0], (int)threadIdx.x);
+      a.out[8 * (size_t)s + 2 * threadIdx.x] = v.x;
+      a.out[8 * (size_t)s + 2 * threadIdx.x + 1] = v.y;
+    }
+  } else if (threadIdx.x == 4) {
+    double c = 0.0, n = 0.0;
+    for (int w = 0; w < nwarp; w++) {
+      c += shc[w][0];
+      n += shc[w][1];
+    }
+    if (a.cost) a.cost[s] = c;
+    if (a.count) a.count[s] = n;
   }
   if (a.flag) {
-    // publish: every CTA's results are fenced out to the host before it checks in; the last one in
-    // raises the flag
+    // publish: results are fenced to device scope before the CTA checks in; the last CTA in copies
+    // all of them to the host mailbox, fences system-wide once and raises the flag
     __shared__ unsigned int last;
+    if (threadIdx.x < 5) __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      last = (atomicAdd(a.arrive, 1u) == gridDim.x - 1) ? 1u : 0u;
-    }
+    if (threadIdx.x == 0) last = (atomicAdd(a.arrive, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
-    if (last && threadIdx.x == 0) {
-      *a.arrive = 0u;
+    if (last) {
+      __threadfence();
+      const int n8 = 8 * a.N;
+      // [8N | N | N] device -> host-mapped, only the parts this launch produced
+      for (int i = threadIdx.x; i < n8 + 2 * a.N; i += blockDim.x) {
+        const bool live = i < n8 ? (a.out != nullptr)
+                                 : (i < n8 + a.N ? (a.cost != nullptr) : (a.count != nullptr));
+        if (!live) continue;
+        const double *src = i < n8 ? a.out + i
+                                   : (i < n8 + a.N ? a.cost + (i - n8) : a.count + (i - n8 - a.N));
+        a.hmail[i] = __ldcg(src);
+      }
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long *>(a.flag) = a.epoch;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *a.arrive = 0u;
+        *reinterpret_cast<volatile unsigned long long *>(a.flag) = a.epoch;
+      }
     }
   }
 }
@@ -176,10 +242,16 @@ void db_launch_rtr_stats(const RtrStatsArgs *a, int nslice, cudaStream_t st) {
 void db_launch_rtr_reduce(const double *in, double *out, size_t n, int ns, cudaStream_t st) {
   k_rtr_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n, ns);
 }
+static int rtr_eval_warps(int N) {
+  int nwarp = (N + 1) / 2;     // 16 lanes per baseline end, two ends per warp: half of the ends at once
+  if (nwarp > 16) nwarp = 16;  // at 62 stations, a loop beyond
+  return nwarp < 1 ? 1 : nwarp;
+}
 void db_launch_rtr_eval(const RtrEvalArgs *a, cudaStream_t st) {
-  int nwarp = (a->N + 31) / 32;  // one baseline per thread where a CTA can hold them
-  if (nwarp > 8) nwarp = 8;
-  k_rtr_eval<<<a->N, 32 * nwarp, 0, st>>>(*a);
+  k_rtr_eval<RtrEvalArgs><<<a->N, 32 * rtr_eval_warps(a->N), 0, st>>>(*a);
+}
+void db_launch_rtr_eval_inl(const RtrEvalInl *a, cudaStream_t st) {
+  k_rtr_eval<RtrEvalInl><<<a->a.N, 32 * rtr_eval_warps(a->a.N), 0, st>>>(*a);
 }
 void db_launch_rtr_plane_sum(const double *sc, int Nbase, int which, double *dst, cudaStream_t st) {
   k_rtr_plane_sum<<<1, 256, 0, st>>>(sc, Nbase, which, dst);

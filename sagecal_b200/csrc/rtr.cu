@@ -43,9 +43,11 @@ static RtrWork *rtr_init(dirac_b200_problem *pr) {
   RtrWork *w = new RtrWork();
   w->N = d.N;
   w->Nbase = d.Nbase;
-  // enough (baseline block, time slice) CTAs to fill the device
+  // (baseline block, time slice) CTAs: about one per SM.  More slices shorten the rows per thread but
+  // every slice writes (and the reduction re-reads) 528 B of partial tensors per baseline, against
+  // 128 B per row streamed: at 62 stations x 120 timeslots 10 slices already add 35 % of traffic
   const int nbb = (d.Nbase + 127) / 128;
-  int ns = (4 * db_sm_count() + nbb - 1) / nbb;
+  int ns = (db_sm_count() + nbb - 1) / nbb;
   if (ns > d.tilesz) ns = d.tilesz;
   if (ns < 1) ns = 1;
   w->nslice = ns;
@@ -151,25 +153,35 @@ struct RtrDevEval {
   // one launch of k_rtr_eval
   void launch(const double *x, const double *eta, double *fcost, double *vec, double *cnt) {
     DevProblem &d = pr->d;
-    double *he = w->h + n8;
-    upload_x(x);
-    if (eta) {
-      memcpy(he, eta, sizeof(double) * n8);
-      DB_CHECK(cudaMemcpyAsync(w->edev, he, sizeof(double) * n8, cudaMemcpyHostToDevice,
-                               d.stream));
-    }
     // results come back through the mailbox: no device-to-host copy, no stream synchronisation
-    RtrEvalArgs a;
+    const bool inl = N <= RTR_INLINE_MAXN;
+    RtrEvalInl P;
+    RtrEvalArgs &a = P.a;
     a.TD = w->TD; a.sc = w->sc; a.x = w->xdev; a.eta = eta ? w->edev : nullptr;
-    a.out = vec ? w->mbox_dev : nullptr;
-    a.cost = fcost ? w->mbox_dev + n8 : nullptr;
-    a.count = cnt ? w->mbox_dev + n8 + N : nullptr;
+    a.out = vec ? w->outdev : nullptr;
+    a.cost = fcost ? w->outdev + n8 : nullptr;
+    a.count = cnt ? w->outdev + n8 + N : nullptr;
     a.N = N; a.Nbase = d.Nbase;
     a.arrive = w->arrive;
+    a.hmail = w->mbox_dev;
     a.flag = reinterpret_cast<unsigned long long *>(w->mbox_dev + n8 + 2 * N + 2);
     a.epoch = ++w->epoch;
+    if (inl) {
+      // Jones and tangent vector ride in the parameter block: the evaluation is one launch
+      memcpy(P.xin, x, sizeof(double) * n8);
+      if (eta) memcpy(P.ein, eta, sizeof(double) * n8);
+    } else {
+      double *he = w->h + n8;
+      upload_x(x);
+      if (eta) {
+        memcpy(he, eta, sizeof(double) * n8);
+        DB_CHECK(cudaMemcpyAsync(w->edev, he, sizeof(double) * n8, cudaMemcpyHostToDevice,
+                                 d.stream));
+      }
+    }
     db_prof_begin(10, 2.0 * d.Nbase * (512.0 + 24.0), d.stream);
-    db_launch_rtr_eval(&a, d.stream);
+    if (inl) db_launch_rtr_eval_inl(&P, d.stream);
+    else db_launch_rtr_eval(&a, d.stream);
     db_prof_end(d.stream);
     db_count_launch(1);
     db_flag_wait(reinterpret_cast<volatile unsigned long long *>(w->mbox + n8 + 2 * N + 2),

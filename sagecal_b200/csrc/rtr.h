@@ -26,15 +26,28 @@ struct RtrEvalArgs {
   double *cost;               // [N] per-station partial costs, may be null
   double *count;              // [N] unflagged rows per station, may be null
   int N, Nbase;
-  // mailbox: out / cost / count point into HOST-mapped memory; the last CTA to finish publishes
-  // `epoch` in *flag (also host-mapped) after a system-wide fence, the host spins on it instead of
-  // waiting for a device-to-host copy and a stream synchronisation
+  // mailbox: out / cost / count are DEVICE buffers laid out back to back [8N | N | N]; the last CTA
+  // to finish copies them to the host-mapped `hmail`, fences system-wide ONCE and publishes `epoch` in
+  // *flag (host-mapped too); the host spins on the flag instead of waiting for a device-to-host copy
+  // and a stream synchronisation
   unsigned int *arrive;       // device counter, zero between launches
+  double *hmail;              // host-mapped [8N + 2N]
   unsigned long long *flag;   // null: no mailbox
   unsigned long long epoch;
 };
 
+// up to RTR_INLINE_MAXN stations the Jones and the tangent vector travel in the kernel's parameter
+// block (2 x 4 KB; CUDA 12.1+ takes 32 KB of parameters): an evaluation is then ONE launch, no
+// host-to-device copy in front of it
+#define RTR_INLINE_MAXN 64
+struct RtrEvalInl {
+  RtrEvalArgs a;   // a.x / a.eta are ignored (a.eta only says: Hessian product or gradient)
+  double xin[8 * RTR_INLINE_MAXN];
+  double ein[8 * RTR_INLINE_MAXN];
+};
+
 extern "C" {
+void db_launch_rtr_eval_inl(const RtrEvalInl *a, cudaStream_t st);
 void db_launch_rtr_stats(const RtrStatsArgs *a, int nslice, cudaStream_t st);
 void db_launch_rtr_reduce(const double *in, double *out, size_t n, int ns, cudaStream_t st);
 void db_launch_rtr_eval(const RtrEvalArgs *a, cudaStream_t st);

@@ -205,3 +205,71 @@ RTR_UNROLL
     }
   }
 }
+
+// ---- the same evaluation spread over 16 lanes per baseline end (k_rtr_eval) ---------------------------
+// lane l of a baseline end: a = l>>3 & 1, b = l>>2 & 1, m = l>>1 & 1, j = l & 1 owns the tensor entry
+// [(ab),(mj)].  Tc[2i+j'] = T[(i j'),(mj)] (the lane's column of T), Dv = D[(ab),(mj)].
+//   *term: the lane's addend of the station sums: seen from p (sp) it belongs to entry (a,m) of the
+//          station's 2x2 block and is summed over the 4 lanes (b,j); seen from q it belongs to entry
+//          (b,j) and is summed over the 4 lanes (a,m) -- sums are linear, so the caller adds the lanes'
+//          terms over all ends first and folds the 4 lanes once at the end
+//   *cost: the lane's share of sum_t w |d - Gp C Gq^H|^2 without c0 (p end only)
+// rows: Gpa = row a of Gp, Gqb = row b of Gq, Epa / Eqb likewise (two entries each; the lane-dependent
+// picks below are selects, not indexed register arrays)
+__host__ __device__ __forceinline__ double2 rtr_lane_M(const double2 *A1row, const double2 *A2row,
+                                                       const double2 *Tc) {
+  // sum_{i,j'} A1_ai conj(A2_bj') T[(ij'),(mj)]
+  const double2 z0 = cdot2(A1row[0], Tc[0], A1row[1], Tc[2]);  // j' = 0
+  const double2 z1 = cdot2(A1row[0], Tc[1], A1row[1], Tc[3]);  // j' = 1
+  double2 v = make_double2(0.0, 0.0);
+  cfmacl(v, A2row[0], z0);
+  cfmacl(v, A2row[1], z1);
+  return v;
+}
+__host__ __device__ __forceinline__ void rtr_lane_terms(int lane, bool sp, const double2 *Gpa,
+                                                        const double2 *Gqb, const double2 *Epa,
+                                                        const double2 *Eqb, const double2 *Tc,
+                                                        double2 Dv, bool hess, bool want_cost,
+                                                        bool want_vec, double2 *term,
+                                                        double *cost) {
+  const int m = (lane >> 1) & 1, j = lane & 1;
+  const double2 Gpm = m ? Gpa[1] : Gpa[0], Gqj = j ? Gqb[1] : Gqb[0];
+  const double2 Mg = rtr_lane_M(Gpa, Gqb, Tc);
+  if (want_cost && sp) {
+    const double2 K = cmulc(Gpm, Gqj);  // Gp_ai conj(Gq_bj), (ij) = (mj)
+    const double vr = 2.0 * Dv.x - Mg.x, vi = 2.0 * Dv.y - Mg.y;
+    *cost -= K.x * vr + K.y * vi;
+  }
+  if (!want_vec) return;
+  const double2 W = csub(Dv, Mg);  // Wres[(ab),(mj)]
+  double2 t = make_double2(0.0, 0.0);
+  if (!hess) {
+    if (sp) cfma(t, Gqj, W);         // grad_p[a,m] += Gq_bj Wres[(ab),(mj)]
+    else cfmac(t, Gpm, W);           // grad_q[b,m'] += Gp_ai conj(Wres[(ab),(i m')]), i = m bit
+  } else {
+    const double2 W1 = cadd(rtr_lane_M(Gpa, Eqb, Tc), rtr_lane_M(Epa, Gqb, Tc));
+    if (sp) {
+      const double2 Eqj = j ? Eqb[1] : Eqb[0];
+      cfma(t, Eqj, W);
+      cfma(t, make_double2(-Gqj.x, -Gqj.y), W1);
+    } else {
+      const double2 Epm = m ? Epa[1] : Epa[0];
+      cfmac(t, Epm, W);
+      cfmac(t, make_double2(-Gpm.x, -Gpm.y), W1);
+    }
+  }
+  *term = t;
+}
+// entry e = 2 row + col of the station's 2x2 block from the 16 lane sums of the p ends (tP) and of the
+// q ends (tQ): p ends fold the lanes (b,j), q ends the lanes (a,m)
+__host__ __device__ __forceinline__ double2 rtr_lane_fold(const double2 *tP, const double2 *tQ,
+                                                          int e) {
+  const int r = e >> 1, c = e & 1;
+  double2 v = make_double2(0.0, 0.0);
+  for (int x = 0; x < 2; x++)
+    for (int y = 0; y < 2; y++) {
+      v = cadd(v, tP[r * 8 + x * 4 + c * 2 + y]);   // a = r, m = c, over b = x, j = y
+      v = cadd(v, tQ[x * 8 + r * 4 + y * 2 + c]);   // b = r, j = c, over a = x, m = y
+    }
+  return v;
+}

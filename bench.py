@@ -79,7 +79,7 @@ def solve_args(name):
         a["solver_mode"] = 3
     elif name == "C2rtr":      # RSD + RTR per cluster (rtr_solve.c), plain LBFGS
         a["solver_mode"] = 4
-    elif name == "C3rtr":      # robust RTR: the reference driver's default -j 5 (data.cpp:69)
+    elif name in ("C3rtr", "C4rtr"):   # robust RTR: the reference driver's default -j 5 (data.cpp:69)
         a["solver_mode"] = 5
     elif name == "C3nsd":      # Nesterov's accelerated descent
         a["solver_mode"] = 6
@@ -112,6 +112,8 @@ def workload_shape(name):
         name = "C3"
     if name == "C2rtr":
         name = "C2"
+    if name == "C4rtr":
+        name = "C4"
     if name in synth.CONFIGS:
         c = synth.CONFIGS[name]
         return dict(N=c["N"], M=c["M"], tilesz=c["tilesz"], radius=c["radius"], seed=c["seed"],
@@ -338,13 +340,13 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # own arm
 # ---------------------------------------------------------------------------------------------
-def n512_parity(api):
+def n512_parity(api, variant="lm"):
     """reduced-interval problem at the station count of C4 (512 stations, 2 timeslots, 2 clusters)
     against the committed golden of the CPU restatement (tests/golden/n512): the parity evidence for
     the 8N = 4096 code paths next to a C4 bench line (no CPU code can produce a full-shape C4 golden)"""
-    path = os.path.join(ROOT, "tests", "golden", "n512", "lm.npz")
+    path = os.path.join(ROOT, "tests", "golden", "n512", variant + ".npz")
     if not os.path.exists(path):
-        return {"checked": False, "why": "tests/golden/n512/lm.npz missing"}
+        return {"checked": False, "why": "tests/golden/n512/%s.npz missing" % variant}
     import ast
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_golden_n512 as gen
@@ -359,8 +361,8 @@ def n512_parity(api):
                                    pr.coh, pp, **kw)
     want = g["out_scalars"]
     err = float(np.max(np.abs(pp - g["out_pp"])) / np.max(np.abs(g["out_pp"])))
-    return {"checked": True, "against": "oracle/liboracle.so golden tests/golden/n512/lm.npz "
-                                        "(N=512, 2 clusters, 2 timeslots)",
+    return {"checked": True, "against": "oracle/liboracle.so golden tests/golden/n512/%s.npz "
+                                        "(N=512, 2 clusters, 2 timeslots)" % variant,
             "same_inputs": same_inputs, "jones_max_relerr": err, "tolerance": 1e-5,
             "ok": bool(same_inputs and err < 1e-5), "res_1": [out[3], float(want[3])]}
 
@@ -384,8 +386,9 @@ def run_workload(name, args, ctx, with_cpu=True):
     # C4 (512 stations): the coherencies of one GPU's 32 clusters are 32 GB (257 GB for all 256
     # clusters) and never exist on the host: they are generated on the device from the sky model
     # (dirac_b200_precalculate, the device-side precalculate_coherencies), as SURVEY.md 8e prescribes
-    devgen = name == "C4" or args.devgen
-    if name == "C4":
+    is_c4 = name in ("C4", "C4rtr")
+    devgen = is_c4 or args.devgen
+    if is_c4:
         shape["M"] = args.c4_clusters_per_gpu
     coh_h = None
     if world == 1 and not devgen:
@@ -450,7 +453,7 @@ def run_workload(name, args, ctx, with_cpu=True):
         for it in range(W):
             pp = pr.pp0.copy()
             res = dp.sagefit(pp, None, **SOLVE_W)
-            if it == 0 and world == 1 and rank == 0 and name != "C4":
+            if it == 0 and world == 1 and rank == 0 and not is_c4:
                 parity = golden_parity(name, pr, pp, res)
                 if name == "C2" and parity.get("checked") and os.path.exists(
                         os.path.join(ROOT, "tests", "golden", "full", "C2lm.npz")):
@@ -617,10 +620,10 @@ def run_workload(name, args, ctx, with_cpu=True):
     if world > 1:
         par = {"checked": True, "sharded_vs_single_gpu": ctx.get("shard_check"),
                "ok": bool(ctx.get("shard_check") and ctx["shard_check"]["ok"])}
-        if name == "C4":
+        if is_c4:
             par["n512_reduced"] = ctx.get("n512")
             par["ok"] = bool(par["ok"] and ctx.get("n512", {}).get("ok"))
-    elif name == "C4":
+    elif is_c4:
         par = ctx.get("n512")
     else:
         par = parity
@@ -826,8 +829,8 @@ def main():
             # prove the sharded path right on this very box (small problem, sharded vs single GPU
             # on every rank; sagecal_b200.dist.verify_sharding)
             ctx["shard_check"] = sdist.verify_sharding(api, rank, world)
-        if args.workload == "C4" and rank == 0:
-            ctx["n512"] = n512_parity(api)
+        if args.workload in ("C4", "C4rtr") and rank == 0:
+            ctx["n512"] = n512_parity(api, "rtr" if args.workload == "C4rtr" else "lm")
     if world > 1:
         dist.barrier()
 

@@ -4,7 +4,7 @@ restatement oracle/liboracle.so (pinned to the compiled reference by tests/test_
 tests/test_oracle_c2r.py; the compiled reference itself would need a 68 GB dense Jacobian here).
 Stored: solved Jones, scalars, input fingerprint; inputs are regenerated from the seed.
 
-    python tests/golden/make_golden_n512.py            (a few minutes: four 4096^3/3 factorisations
+    python tests/golden/make_golden_n512.py [lm] [rtr] [rtr4]   (a few minutes: four 4096^3/3 factorisations
                                                         per sweep in plain C)
 """
 import os
@@ -33,17 +33,25 @@ def build():
     return synth.make_problem(**SHAPE)
 
 
+#: the same problem under the reference driver's default solver (robust RTR, solver_mode 5) and under
+#: RSD + RTR (4): no 4096 x 4096 systems at all on this path
+VARIANTS = {"lm": SOLVE, "rtr": dict(SOLVE, solver_mode=5), "rtr4": dict(SOLVE, solver_mode=4)}
+
+
 def main():
     import orcdirac
     os.makedirs(OUT, exist_ok=True)
     pr = build()
     o = orcdirac.Oracle(pr)
-    x, pp = pr.x.copy(), pr.pp0.copy()
-    t0 = time.time()
-    out = o.sagefit(x, pp, **SOLVE)
-    np.savez_compressed(os.path.join(OUT, "lm.npz"), args=np.array(repr(SOLVE)), out_pp=pp,
-                        out_scalars=np.array(out, dtype=np.float64), fingerprint=fingerprint(pr))
-    print(out, "%.1f s" % (time.time() - t0), flush=True)
+    for name in (sys.argv[1:] or ["lm"]):
+        solve = VARIANTS[name]
+        x, pp = pr.x.copy(), pr.pp0.copy()
+        t0 = time.time()
+        out = o.sagefit(x, pp, **solve)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), args=np.array(repr(solve)), out_pp=pp,
+                            out_scalars=np.array(out, dtype=np.float64),
+                            fingerprint=fingerprint(pr))
+        print(name, out, "%.1f s" % (time.time() - t0), flush=True)
 
 
 if __name__ == "__main__":

@@ -43,6 +43,29 @@ def test_sagefit_n512_matches_golden(api, prob):
     assert abs(out[3] - want[3]) <= 1e-5 * want[3]
 
 
+@pytest.mark.parametrize("name", ["rtr", "rtr4"])
+def test_sagefit_n512_rtr_matches_golden(api, prob, name):
+    """robust RTR (the reference driver's default solver) and RSD + RTR at 512 stations: the Jones
+    travel through device memory (more than 64 stations) and a 16-lane group walks 8 baseline ends"""
+    from sagecal_b200.dirac_api import SkyModel, make_barr
+    gold = os.path.join(HERE, "golden", "n512", name + ".npz")
+    if not os.path.exists(gold):
+        pytest.skip("golden not generated")
+    gen, pr = prob
+    g = np.load(gold)
+    assert np.allclose(gen.fingerprint(pr), g["fingerprint"], rtol=1e-11, atol=0)
+    kw = ast.literal_eval(str(g["args"]))
+    x, pp = pr.x.copy(), pr.pp0.copy()
+    out = api.sagefit_visibilities(pr.u, pr.v, pr.w, x, pr.N, pr.Nbase, pr.tilesz,
+                                   make_barr(pr.sta1, pr.sta2, pr.flag), SkyModel(pr.clusters, pr.N),
+                                   pr.coh, pp, **kw)
+    want = g["out_scalars"]
+    assert out[0] == int(want[0])
+    assert abs(out[1] - want[1]) < 1e-9
+    assert relerr(pp, g["out_pp"]) < 1e-5, relerr(pp, g["out_pp"])
+    assert abs(out[3] - want[3]) <= 1e-5 * want[3]
+
+
 def test_normal_equations_n512(api, prob):
     """J^T J (4096 x 4096) and J^T e of one cluster at N=512 against the O(rows) restatement"""
     import orcdirac

@@ -25,6 +25,11 @@ CASES = [
     ("rrtr-hybrid", 5, dict(N=13, M=4, tilesz=20, seed=78, kmean=1.0, outliers=0.02,
                             nchunk=[1, 2, 1, 4]), dict(max_iter=2)),
     ("rrtr-62", 5, dict(N=62, M=3, tilesz=4, seed=79, outliers=0.02), dict(max_iter=2, max_lbfgs=4)),
+    # more than 64 stations: Jones through device memory instead of the parameter block, several
+    # baseline ends per 16-lane group
+    ("rtr-70", 4, dict(N=70, M=2, tilesz=2, seed=82), dict(max_iter=2, max_emiter=2, max_lbfgs=2)),
+    ("rrtr-70", 5, dict(N=70, M=2, tilesz=2, seed=83, outliers=0.02),
+     dict(max_iter=2, max_emiter=2, max_lbfgs=0)),
     ("nsd", 6, dict(N=10, M=3, tilesz=10, seed=80, outliers=0.02), dict(max_iter=3)),
     ("nsd-hybrid", 6, dict(N=11, M=3, tilesz=12, seed=81, outliers=0.02, nchunk=[2, 1, 3]),
      dict(max_iter=2)),

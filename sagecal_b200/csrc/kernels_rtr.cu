@@ -41,15 +41,37 @@ __global__ void __launch_bounds__(128) k_rtr_stats(RtrStatsArgs a) {
   }
   RtrAcc A;
   rtr_acc_zero(A);
-  for (int t = t_lo; t < t_hi; t++) {
-    const long long r = (long long)t * a.Nbase + b;
-    if (a.flag[r]) continue;
-    double2 C[4], dd[4];
+  // the next row's 8 loads are in flight while the current row's ~250 DFMA run (one thread owns a
+  // baseline for all its timeslots: without the prefetch a warp has nothing to hide the latency with)
+  double2 Cn[4], dn[4];
+  unsigned char fn = 1;
+  if (t_lo < t_hi) {
+    const long long r = (long long)t_lo * a.Nbase + b;
+    fn = a.flag[r];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      C[c] = ld_stream(a.coh_k + (long long)c * a.R + r);
-      dd[c] = ld_stream(a.d + (long long)c * a.R + r);
+      Cn[c] = ld_stream(a.coh_k + (long long)c * a.R + r);
+      dn[c] = ld_stream(a.d + (long long)c * a.R + r);
     }
+  }
+  for (int t = t_lo; t < t_hi; t++) {
+    double2 C[4], dd[4];
+    const unsigned char f = fn;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      C[c] = Cn[c];
+      dd[c] = dn[c];
+    }
+    if (t + 1 < t_hi) {
+      const long long r = (long long)(t + 1) * a.Nbase + b;
+      fn = a.flag[r];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        Cn[c] = ld_stream(a.coh_k + (long long)c * a.R + r);
+        dn[c] = ld_stream(a.d + (long long)c * a.R + r);
+      }
+    }
+    if (f) continue;
     rtr_acc_row(A, C, dd, weighted, Gp, Gq, a.nu, a.tensors != 0);
   }
   const size_t sl = blockIdx.y;
@@ -58,13 +80,13 @@ __global__ void __launch_bounds__(128) k_rtr_stats(RtrStatsArgs a) {
   sc[(size_t)a.Nbase + b] = A.slw;
   sc[2 * (size_t)a.Nbase + b] = A.cnt;
   if (!a.tensors) return;
-  double2 *TD = a.TD + sl * 32 * (size_t)a.Nbase;
+  double2 *TD = a.TD + (sl * (size_t)a.Nbase + b) * 32;  // one baseline = 512 contiguous bytes
   double2 T[16], D[16];
   rtr_acc_expand(A, T, D);
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    TD[(size_t)i * a.Nbase + b] = T[i];
-    TD[(size_t)(16 + i) * a.Nbase + b] = D[i];
+    TD[i] = T[i];
+    TD[16 + i] = D[i];
   }
 }
 
@@ -138,8 +160,8 @@ __global__ void __launch_bounds__(512) k_rtr_eval(const __grid_constant__ ARGS P
     }
     double2 Tc[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) Tc[k] = a.TD[(size_t)(4 * k + mj) * a.Nbase + b];
-    const double2 Dv = a.TD[(size_t)(16 + 4 * ab + mj) * a.Nbase + b];
+    for (int k = 0; k < 4; k++) Tc[k] = a.TD[b * 32 + (4 * k + mj)];
+    const double2 Dv = a.TD[b * 32 + (16 + 4 * ab + mj)];
     if (want_cost && sp && lane16 == 0) cost += a.sc[b];
     double2 term = make_double2(0, 0);
     rtr_lane_terms(lane16, sp, Gpa, Gqb, Epa, Eqb, Tc, Dv, hess, want_cost, want_vec, &term, &cost);

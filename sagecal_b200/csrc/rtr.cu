@@ -26,7 +26,7 @@ void db_chunk_range(const DevProblem &d, int k, int ck, int *t0, int *t1);
 
 struct RtrWork {
   int N, Nbase, nslice;
-  double2 *TDpart, *TD;   // [nslice][32][Nbase], [32][Nbase]
+  double2 *TDpart, *TD;   // [nslice][Nbase][32], [Nbase][32]
   double *scpart, *sc;    // [nslice][3][Nbase], [3][Nbase]
   double *xdev, *edev;    // [8N] each
   double *outdev;         // [8N | N | N | 4]

@@ -9,7 +9,7 @@ struct RtrStatsArgs {
   const short2 *blpq;         // [Nbase]
   const double *xw;           // 8N Jones the robust weights are evaluated at; null: w = 1
   double nu;
-  double2 *TD;                // [nslice][32][Nbase]: planes 0-15 T (row-major 4x4), 16-31 D
+  double2 *TD;                // [nslice][Nbase][32]: per baseline 0-15 T (row-major 4x4), 16-31 D
   double *sc;                 // [nslice][3][Nbase]: c0, sum(log w - w), unflagged rows
   long long R;
   int N, Nbase;
@@ -18,7 +18,7 @@ struct RtrStatsArgs {
 };
 
 struct RtrEvalArgs {
-  const double2 *TD;          // [32][Nbase]
+  const double2 *TD;          // [Nbase][32]
   const double *sc;           // [3][Nbase]
   const double *x;            // 8N Jones
   const double *eta;          // 8N tangent vector: Hessian-vector product; null: gradient

@@ -56,4 +56,4 @@ def test_sagefit_rtr_modes(api, ref, refser, name, mode, prob, args):
     assert relerr(ppg, ppr) < JONES_TOL, (name, relerr(ppg, ppr))
     assert relerr(xg, xr) < 1e-5 * max(1.0, np.max(np.abs(pr.x)) / np.max(np.abs(xr)))
     assert abs(rr[3] - rg[3]) <= 1e-5 * rr[3]           # res_1
-    assert rg[3] < rg[2]
+    assert rg[3] <= rg[2]   # (the robust solvers may discard every visit)

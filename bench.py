@@ -190,6 +190,8 @@ def ncu_traffic(workload="C2"):
     if os.path.exists(p):
         with open(p) as f:
             t = json.load(f)
+        if workload in ("C3rtr", "C3nsd"):
+            return t.get("k_rtr_stats_dram_bytes_per_launch_C3")
         return t.get("k_cluster_pass_dram_bytes_per_launch_" + workload,
                      t.get("k_cluster_pass_dram_bytes_per_launch") if workload == "C2" else None)
     return None
@@ -589,7 +591,9 @@ def run_workload(name, args, ctx, with_cpu=True):
     # `roofline` is quoted for the dominant HBM-streaming kernel.  The damped solves take a large
     # share of the step, are latency (N=62: a chain of 496 pivots on a 16-CTA cluster) or FP64 bound
     # (N=512: 23 GFLOP per factorisation), not HBM or tensor bound: reported next to it.
-    own = {k: v for k, v in shares.items() if not k.startswith("damped")}
+    # (k_rtr_eval, the O(Nbase) evaluation of the RTR family, is latency bound like the solves: it
+    # works on 512 bytes per BASELINE, not on the rows)
+    own = {k: v for k, v in shares.items() if not k.startswith("damped") and k != "k_rtr_eval"}
     dom = max(own, key=lambda k: own[k]["ms_per_step"])
     n8 = 8 * pr.N
     sv = shares["damped_solve"]

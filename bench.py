@@ -60,10 +60,14 @@ def parse():
     ap.add_argument("--devgen", action="store_true", help="generate the coherencies on the device "
                     "(always for C4)")
     ap.add_argument("--c4-clusters-per-gpu", type=int, default=32)
-    ap.add_argument("--c5-solver", default="rtr", choices=["rtr", "lm"],
-                    help="J-update of the consensus workload: rtr = the reference's robust Riemannian "
-                         "trust-region solver on the augmented cost (admm_solve.c:331-352), lm = this "
-                         "library's LM on the same cost")
+    ap.add_argument("--c5-solver", default="lm", choices=["rtr", "lm"],
+                    help="J-update of the consensus workload: lm = this library's LM on the augmented "
+                         "cost (default: it keeps improving from a good starting point), rtr = the "
+                         "reference's robust Riemannian trust-region solver on the same cost "
+                         "(admm_solve.c:331-352; what sagefit_visibilities_admm runs): it keeps a "
+                         "visit only if the WEIGHTED final cost beats the UNWEIGHTED entry cost, and "
+                         "its weights exceed 1, so after the plain first iteration of this synthetic "
+                         "workload it discards every visit (DESIGN.md 9b)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -676,6 +680,11 @@ def run_consensus(args, ctx):
     api, stream, rank, world, local = ctx["api"], ctx["stream"], ctx["rank"], ctx["world"], ctx["local"]
     c = synth.CONFIGS["C5"]
     ADMM, NPOLY, RHO = 5, 3, 5.0
+    # SAGE sweeps per J-update.  The reference's robust RTR J-update restarts nu at nulow in the first
+    # sweep of every call (admm_solve.c:333-335); its row weights (nu+2)/(nu+e^2) are then ~2 and a
+    # visit is only kept if it halves the cost, so a one-sweep J-update stalls near the solution; the
+    # driver's default of 3 sweeps (data.cpp:61) lets the later sweeps run with the updated nu.
+    EMIT = 3 if args.c5_solver == "rtr" else 1
     freqs = np.linspace(115e6, 185e6, 8)[:max(world, 1)] if world <= 8 else np.linspace(115e6, 185e6, world)
     f = float(freqs[rank])
     pr = synth.make_problem(N=c["N"], M=c["M"], tilesz=c["tilesz"], radius=c["radius"], seed=c["seed"],
@@ -707,7 +716,8 @@ def run_consensus(args, ctx):
             sb = cons.ConsensusSubband(api, dpx, rank, freqs, 150e6, min(NPOLY, max(1, world - 1)) if world > 1 else 1,
                                        rho, ptype=1)
             pp = pr.pp0.copy()
-            return sb, pp, sb.run(pp, admm_iters=ADMM, max_emiter=1, max_iter=2, solver=args.c5_solver)
+            return sb, pp, sb.run(pp, admm_iters=ADMM, max_emiter=EMIT, max_iter=2,
+                                  solver=args.c5_solver)
 
         K, W = args.steps, max(args.warmup, 3)
         hist = None
@@ -746,7 +756,7 @@ def run_consensus(args, ctx):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step, ms_e2e = float(t[0].item()) / K, float(t[1].item()) / K
-    units = R * M * ADMM * world
+    units = R * M * ADMM * EMIT * world
     if rank != 0:
         return None
     return {
@@ -754,12 +764,12 @@ def run_consensus(args, ctx):
         "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C5: N=%d stations x %d subbands (one per GPU), M=%d clusters, tilesz=%d; "
-                               "%d ADMM iterations (1 SAGE sweep each; J-update: %s), Npoly=%d, rho=%g"
-                               % (pr.N, world, M, pr.tilesz, ADMM,
+                               "%d ADMM iterations (%d SAGE sweep(s) each; J-update: %s), Npoly=%d, rho=%g"
+                               % (pr.N, world, M, pr.tilesz, ADMM, EMIT,
                                   "robust RTR on the augmented cost as in the reference "
                                   "(rtr_solve_nocuda_robust_admm), max_iter=2" if args.c5_solver == "rtr"
                                   else "LM on the augmented cost, 2 iterations", sb.Npoly, RHO),
-                   "units_per_step": "rows*clusters*ADMM iterations*subbands",
+                   "units_per_step": "rows*clusters*SAGE sweeps*ADMM iterations*subbands",
                    "parallelism": "one subband per GPU, ONE all-reduce of Npoly*8*N*Mt doubles per ADMM "
                                   "iteration, called from C",
                    "coherencies": "generated on the device (dirac_b200_precalculate)"},

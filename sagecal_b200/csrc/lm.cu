@@ -667,17 +667,29 @@ static void lm_core(dirac_b200_problem *pr, int k, int ck, int t0, int t1, doubl
   double *hsc = w.h_vec + 4 * n + 4 * d.N + 8;  // [n: diag][4: |dp|^2, dp.jte, cost, -]
   double *hjte_new = hpnew;                     // the trial point itself is formed on the device
   int kiter;
+  std::vector<int> subI;
   for (kiter = 0; kiter < itmax && !stop; ++kiter) {
     if (!pending_entry && p_eL2 <= eps3) {
       stop = 6;
       break;
+    }
+    if (os && randomize) {
+      // random permutation of the subsets, drawn like the reference's (random_permutation,
+      // lmfit.c:1085-1099: inside-out shuffle on the caller-seeded rand()), once per LM iteration
+      // (clmfit.c:1376-1379)
+      subI.resize(Nsubsets);
+      for (int i = 0; i < Nsubsets; ++i) {
+        const int j = rand() % (i + 1);
+        subI[i] = subI[j];
+        subI[j] = i;
+      }
     }
     for (int ositer = 0; ositer < max_os_iter; ositer++) {
       int s0 = t0, s1 = t1;
       if (os) {
         int l;
         if (randomize) {
-          l = rand() % Nsubsets;  // the reference draws a random permutation (clmfit.c:1372)
+          l = subI[ositer];
         } else {
           l = (os_shift + kiter + ositer) % Nsubsets;
         }

@@ -148,7 +148,8 @@ int predict_visibilities_multifreq(double *u, double *v, double *w, double *x, i
  * residual_threadfn_multifreq :681-938): full-resolution residual, x[chan][row][8] -= sum over the
  * clusters with id >= 0 of J_p C_k(chan) J_q^H with the coherencies re-predicted from the sources at
  * every channel, then the correction of every row by the inverse Jones (J + rho I)^-1 of the cluster
- * whose id is ccid (none if no cluster has that id).  phase_only != 0 is not implemented: returns -1. */
+ * whose id is ccid (none if no cluster has that id).  phase_only != 0: the correction uses only the
+ * phases of the cluster's jointly diagonalised solutions (manifold_average.c:399-610). */
 int calculate_residuals_multifreq(double *u, double *v, double *w, double *p, double *x, int N,
                                   int Nbase, int tilesz, baseline_t *barr, clus_source_t *carr, int M,
                                   double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
@@ -312,6 +313,11 @@ int dirac_b200_set_option(const char *name, int value);
  * down to ~1e-15 |p|) the iterates of two correct implementations diverge, the reference's own CPU
  * path included; parity of the solved Jones is defined for runs where this stays 0. */
 long dirac_b200_noise_decisions(int reset);
+
+/* extract_phases (manifold_average.c:399-610): unit-modulus diagonal of the N Jones matrices of one
+ * (cluster, chunk) after niter rounds of joint diagonalisation by Jacobi rotations; what the
+ * phase_only correction of calculate_residuals_multifreq inverts.  Host arithmetic, no GPU needed. */
+int dirac_b200_extract_phases(const double *p, double *pout, int N, int niter);
 
 /* ---- station beams -------------------------------------------------------------------
  * Dirac_common.h:94-162 */

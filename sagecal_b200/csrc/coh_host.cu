@@ -439,20 +439,124 @@ static void jones_invert(const double xx[8], double yy[8], double rho) {
   yy[6] = a0r * ir - a0i * ii;      yy[7] = a0r * ii + a0i * ir;
 }
 
+// eigenvector of the largest eigenvalue of a real symmetric 3x3 matrix by cyclic Jacobi rotations
+// (stands in for dsyevx with IL = IU = 3, manifold_average.c:470,541)
+static void sym3_top_eigvec(const double Hin[3][3], double z[3]) {
+  double A[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) A[i][j] = Hin[i][j];
+  for (int sweep = 0; sweep < 60; sweep++) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-34 * dg || off == 0.0) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (A[p][q] == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 3; k++) {  // A <- A R
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {  // A <- R^T A
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; k++) {
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  int top = 0;
+  for (int i = 1; i < 3; i++)
+    if (A[i][i] > A[top][top]) top = i;
+  const double nrm = sqrt(V[0][top] * V[0][top] + V[1][top] * V[1][top] + V[2][top] * V[2][top]);
+  for (int i = 0; i < 3; i++) z[i] = V[i][top] / nrm;
+}
+
+// phases of the jointly diagonalised solutions of one (cluster, chunk): niter rounds of two Jacobi
+// rotations J <- J G^H common to all stations (towards diagonal J), then the unit-modulus diagonal
+// (extract_phases, manifold_average.c:399-610).  pin / pout: N x 8 doubles in the pp layout.
+static void extract_phases_host(const double *pin, double *pout, int N, int niter) {
+  struct cd { double r, i; };
+  auto mul = [](cd a, cd b) { return cd{a.r * b.r - a.i * b.i, a.r * b.i + a.i * b.r}; };
+  auto conj = [](cd a) { return cd{a.r, -a.i}; };
+  std::vector<cd> J00(N), J01(N), J10(N), J11(N);
+  for (int s = 0; s < N; s++) {
+    J00[s] = {pin[8 * s + 0], pin[8 * s + 1]};
+    J01[s] = {pin[8 * s + 2], pin[8 * s + 3]};
+    J10[s] = {pin[8 * s + 4], pin[8 * s + 5]};
+    J11[s] = {pin[8 * s + 6], pin[8 * s + 7]};
+  }
+  for (int ni = 0; ni < niter; ni++)
+    for (int pass = 0; pass < 2; pass++) {
+      double H[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int s = 0; s < N; s++) {
+        // pass 0: h = conj[a - d, b + c, i (c - b)]; pass 1: h = conj[d - a, c + b, i (b - c)]
+        const cd a = J00[s], b = J01[s], c = J10[s], d = J11[s];
+        const double sg = pass == 0 ? 1.0 : -1.0;
+        cd h[3];
+        h[0] = conj(cd{sg * (a.r - d.r), sg * (a.i - d.i)});
+        h[1] = conj(cd{b.r + c.r, b.i + c.i});
+        const cd cmb = {sg * (c.r - b.r), sg * (c.i - b.i)};
+        h[2] = conj(cd{-cmb.i, cmb.r});  // i (c - b)
+        for (int i = 0; i < 3; i++)
+          for (int j = 0; j < 3; j++) H[i][j] += h[i].r * h[j].r + h[i].i * h[j].i;  // Re(h h^H)
+      }
+      double Z[3];
+      sym3_top_eigvec(H, Z);
+      cd cc, ss;
+      if (Z[0] >= 0.0) {
+        cc = {sqrt(0.5 + Z[0] * 0.5), 0.0};
+        ss = {0.5 * Z[1] / cc.r, -0.5 * Z[2] / cc.r};
+      } else {
+        cc = {sqrt(0.5 - Z[0] * 0.5), 0.0};
+        ss = {-0.5 * Z[1] / cc.r, 0.5 * Z[2] / cc.r};
+      }
+      // G = [c, conj(s); -s, conj(c)] (column-major [c, -s, conj(s), conj(c)]);  J <- J G^H
+      // (G^H)(0,0) = conj(c), (G^H)(0,1) = conj(-s), (G^H)(1,0) = s, (G^H)(1,1) = c
+      const cd g00 = conj(cc), g01 = conj(cd{-ss.r, -ss.i}), g10 = ss, g11 = cc;
+      for (int s = 0; s < N; s++) {
+        const cd a = J00[s], b = J01[s], c = J10[s], d = J11[s];
+        const cd t0 = mul(a, g00), t1 = mul(b, g10), t2 = mul(a, g01), t3 = mul(b, g11);
+        const cd u0 = mul(c, g00), u1 = mul(d, g10), u2 = mul(c, g01), u3 = mul(d, g11);
+        J00[s] = {t0.r + t1.r, t0.i + t1.i};
+        J01[s] = {t2.r + t3.r, t2.i + t3.i};
+        J10[s] = {u0.r + u1.r, u0.i + u1.i};
+        J11[s] = {u2.r + u3.r, u2.i + u3.i};
+      }
+    }
+  memset(pout, 0, sizeof(double) * 8 * N);
+  for (int s = 0; s < N; s++) {
+    const double m0 = sqrt(J00[s].r * J00[s].r + J00[s].i * J00[s].i);
+    const double m1 = sqrt(J11[s].r * J11[s].r + J11[s].i * J11[s].i);
+    pout[8 * s + 0] = J00[s].r / m0;
+    pout[8 * s + 1] = J00[s].i / m0;
+    pout[8 * s + 6] = J11[s].r / m1;
+    pout[8 * s + 7] = J11[s].i / m1;
+  }
+}
+
+// host arithmetic, no GPU needed: exposed so that the CPU tests can pin it against the reference
+extern "C" int dirac_b200_extract_phases(const double *p, double *pout, int N, int niter) {
+  extract_phases_host(p, pout, N, niter);
+  return 0;
+}
+
 // Dirac_radio.h:652 (residual.c:940-1061): full-resolution residual per channel,
 // x[chan][row][8] -= sum over the clusters with id >= 0 of J_p C_k(chan) J_q^H, the coherencies
 // re-predicted from the sources at every channel frequency; then, if a cluster has id == ccid, every
-// row is corrected by that cluster's inverse Jones (J + rho I)^-1.  phase_only != 0 (correction by the
-// phases of a joint diagonalisation, manifold_average.c) is not implemented: returns -1.
+// row is corrected by that cluster's inverse Jones (J + rho I)^-1; phase_only != 0: by the inverse of
+// the phases of its jointly diagonalised solutions (extract_phases, manifold_average.c:399-610).
 static int residuals_multifreq_impl(double *u, double *v, double *w, double *p, double *x, int N,
                                     int Nbase, int tilesz, baseline_t *barr, clus_source_t *carr,
                                     int M, double *freqs, int Nchan, double fdelta, int ccid,
                                     double rho, int phase_only, const BeamSpec *beam) {
-  if (phase_only) {
-    fprintf(stderr, "dirac_b200: calculate_residuals_multifreq: phase_only correction is not "
-                    "implemented\n");
-    return -1;
-  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     fprintf(stderr, "dirac_b200: no CUDA device available. This library has no CPU fallback.\n");
@@ -488,9 +592,16 @@ static int residuals_multifreq_impl(double *u, double *v, double *w, double *p, 
   std::vector<double> pinv;
   if (cm >= 0) {
     pinv.resize((size_t)8 * N * carr[cm].nchunk);
-    for (int c = 0; c < carr[cm].nchunk; c++)
+    std::vector<double> pphase(phase_only ? (size_t)8 * N : 0);
+    for (int c = 0; c < carr[cm].nchunk; c++) {
+      const double *pm = p + carr[cm].p[c];
+      if (phase_only) {  // only the phases of the jointly diagonalised solutions (residual.c:975-990)
+        extract_phases_host(pm, pphase.data(), N, 10);
+        pm = pphase.data();
+      }
       for (int s = 0; s < N; s++)
-        jones_invert(p + carr[cm].p[c] + 8 * s, pinv.data() + (size_t)8 * N * c + 8 * s, rho);
+        jones_invert(pm + 8 * s, pinv.data() + (size_t)8 * N * c + 8 * s, rho);
+    }
   }
   int *dn = nullptr, *dc0 = nullptr, *dpo = nullptr, *ds1 = nullptr, *ds2 = nullptr;
   unsigned char *dsub = nullptr;

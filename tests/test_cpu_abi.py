@@ -66,3 +66,32 @@ def test_no_oracle_in_product():
                 for bad in ("import refdirac", "import orcdirac", "liboracle", "libdirac_ref",
                             "dirac_oracle"):
                     assert bad not in src, "%s references %s" % (os.path.join(dirpath, f), bad)
+
+
+def test_extract_phases_matches_reference(ref):
+    """host arithmetic of the phase_only correction (joint diagonalisation by Jacobi rotations,
+    manifold_average.c:399-610) against the compiled reference; runs without a GPU"""
+    import ctypes as C
+    from sagecal_b200 import lib as blib
+    from sagecal_b200.dirac_api import dptr
+    L = C.CDLL(blib.LIB_PATH)
+    rng = np.random.default_rng(5)
+    for N in (3, 8, 62):
+        # a common unitary ambiguity on top of nearly diagonal Jones
+        D = np.zeros((N, 2, 2), dtype=complex)
+        D[:, 0, 0] = np.exp(1j * rng.uniform(-3, 3, N)) * rng.uniform(0.5, 1.5, N)
+        D[:, 1, 1] = np.exp(1j * rng.uniform(-3, 3, N)) * rng.uniform(0.5, 1.5, N)
+        D += 0.05 * (rng.normal(0, 1, D.shape) + 1j * rng.normal(0, 1, D.shape))
+        th, ph = 0.7, 0.4
+        U = np.array([[np.cos(th), -np.sin(th) * np.exp(1j * ph)],
+                      [np.sin(th) * np.exp(-1j * ph), np.cos(th)]])
+        J = D @ U
+        p = np.zeros(8 * N)
+        p[0::8], p[1::8] = J[:, 0, 0].real, J[:, 0, 0].imag
+        p[2::8], p[3::8] = J[:, 0, 1].real, J[:, 0, 1].imag
+        p[4::8], p[5::8] = J[:, 1, 0].real, J[:, 1, 0].imag
+        p[6::8], p[7::8] = J[:, 1, 1].real, J[:, 1, 1].imag
+        want, got = np.zeros(8 * N), np.zeros(8 * N)
+        ref.lib.extract_phases(dptr(p.copy()), dptr(want), N, 10)
+        L.dirac_b200_extract_phases(dptr(p), dptr(got), N, 10)
+        assert np.max(np.abs(got - want)) < 1e-10, np.max(np.abs(got - want))

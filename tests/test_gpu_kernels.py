@@ -216,9 +216,11 @@ def test_predict_multifreq(api, ref, add):
     assert relerr(xb, xa) < 1e-11
 
 
-@pytest.mark.parametrize("ccid,nchunk", [(-99999, None), (1, None), (2, [1, 2, 3])],
-                         ids=["no-correction", "correct-by-1", "hybrid-correct-by-2"])
-def test_calculate_residuals_multifreq(api, ref, ccid, nchunk):
+@pytest.mark.parametrize("ccid,nchunk,phase_only", [(-99999, None, 0), (1, None, 0), (2, [1, 2, 3], 0),
+                                                    (1, None, 1), (2, [1, 2, 3], 1)],
+                         ids=["no-correction", "correct-by-1", "hybrid-correct-by-2",
+                              "phase-only-1", "phase-only-hybrid-2"])
+def test_calculate_residuals_multifreq(api, ref, ccid, nchunk, phase_only):
     """full-resolution residual with the solved Jones and the optional correction by one cluster's
     inverse Jones against the compiled reference (residual.c:940-1061)"""
     from util import perturbed_jones
@@ -239,9 +241,13 @@ def test_calculate_residuals_multifreq(api, ref, ccid, nchunk):
     pp = perturbed_jones(pr, amp=0.2)
     xa, xb = x0.copy(), x0.copy()
     ra = ref.calculate_residuals_multifreq(pr.u, pr.v, pr.w, pp.copy(), xa, pr.N, pr.Nbase, pr.tilesz,
-                                           b.fresh_barr(), sky, freqs, pr.fdelta * 4, ccid=ccid, rho=1e-9)
+                                           b.fresh_barr(), sky, freqs, pr.fdelta * 4, ccid=ccid, rho=1e-9,
+                                           phase_only=phase_only)
     rb = api.calculate_residuals_multifreq(pr.u, pr.v, pr.w, pp.copy(), xb, pr.N, pr.Nbase, pr.tilesz,
-                                           b.fresh_barr(), sky, freqs, pr.fdelta * 4, ccid=ccid, rho=1e-9)
+                                           b.fresh_barr(), sky, freqs, pr.fdelta * 4, ccid=ccid, rho=1e-9,
+                                           phase_only=phase_only)
     assert ra == rb == 0
-    assert relerr(xb, xa) < 1e-11
+    # (phase_only: the correction goes through a joint diagonalisation by Jacobi rotations,
+    # manifold_average.c:399-610, restated on the host with its own 3x3 eigen-solver)
+    assert relerr(xb, xa) < (1e-9 if phase_only else 1e-11)
     assert relerr(xa, x0) > 1e-3   # something was subtracted

@@ -361,6 +361,25 @@ int precalculate_coherencies_withbeam_gpu(
     double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0, double ph_dec0,
     double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz, int *Nelem,
     double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt);
+/* Dirac_radio.h:221,479,534 (predict.c:745-816): coherencies of Nchan channels,
+ * x[chan][row][cluster][4]: the input of bfgsfit_minibatch_*.  Flag 2 for rows shorter than uvmin at
+ * the first channel or longer than uvmax at the last. */
+int precalculate_coherencies_multifreq(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                       baseline_t *barr, clus_source_t *carr, int M, double *freqs,
+                                       int Nchan, double fdelta, double tdelta, double dec0,
+                                       double uvmin, double uvmax, int Nt);
+int precalculate_coherencies_multifreq_withbeam(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    double uvmin, double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt);
+int precalculate_coherencies_multifreq_withbeam_gpu(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    double uvmin, double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt);
 int predict_visibilities_multifreq_withbeam(
     double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, baseline_t *barr,
     clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,

@@ -343,6 +343,84 @@ extern "C" int precalculate_coherencies_withbeam_gpu(
                                            Nelem, xx, yy, zz, ecoeff, doBeam, Nt);
 }
 
+// Dirac_radio.h:221,479,534 (predict.c:745-816, predict_withbeam.c:726-900): coherencies of Nchan
+// channels, x[chan][row][cluster][4] -- what the minibatch drivers feed bfgsfit_minibatch_*.  Fluxes
+// are the catalogue's (no spectral index here, predict.c:690-696), the smearing width is
+// fdelta / Nchan per channel (:792), a row gets flag 2 if it is shorter than uvmin at the first
+// channel or longer than uvmax at the last (:731-735); the beam variant cuts both ways at the
+// beam-former's reference frequency instead (predict_withbeam.c:456-463,784).  One pass of the single-channel kernel per
+// channel; wide-band element beams see their channel's coefficient set.
+static int precalculate_multifreq_impl(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                       baseline_t *barr, clus_source_t *carr, int M, double *freqs,
+                                       int Nchan, double fdelta, double uvmin, double uvmax,
+                                       const BeamSpec *beam) {
+  const double HUGE_UV = 1e300;
+  for (int c = 0; c < Nchan; c++) {
+    // (the beam variant cuts on ONE frequency, ph_freq0: done on the host below)
+    const double lo = (c == 0 && !beam) ? uvmin : 0.0;
+    const double hi = (c == Nchan - 1 && !beam) ? uvmax : HUGE_UV;
+    BeamSpec bc;
+    elementcoeff ec;
+    const BeamSpec *bp = nullptr;
+    if (beam) {
+      bc = *beam;
+      const bool wide = beam->doBeam == DOBEAM_ARRAY_WB || beam->doBeam == DOBEAM_FULL_WB ||
+                        beam->doBeam == DOBEAM_ELEMENT_WB;
+      if (wide && beam->ecoeff) {  // this channel's coefficient set as a one-frequency table
+        ec = *beam->ecoeff;
+        ec.pattern_phi = beam->ecoeff->pattern_phi + (size_t)2 * ec.Nmodes * c;
+        ec.pattern_theta = beam->ecoeff->pattern_theta + (size_t)2 * ec.Nmodes * c;
+        ec.Nf = 1;
+        bc.ecoeff = &ec;
+      }
+      bp = &bc;
+    }
+    const int rv = precalculate_impl(u, v, w, x + (size_t)c * 8 * M * Nbase, N, Nbase, barr, carr, M,
+                                     freqs[c], fdelta / (double)Nchan, lo, hi, bp);
+    if (rv) return rv;
+  }
+  if (beam)  // predict_withbeam.c:456-463 with freq0 = ph_freq0 (:784)
+    for (long long r = 0; r < Nbase; r++)
+      if (!barr[r].flag) {
+        const double uvdist = sqrt(u[r] * u[r] + v[r] * v[r]) * beam->ph_freq0;
+        if (uvdist < uvmin || uvdist > uvmax) barr[r].flag = 2;
+      }
+  return 0;
+}
+extern "C" int precalculate_coherencies_multifreq(double *u, double *v, double *w, double *x, int N,
+                                                  int Nbase, baseline_t *barr, clus_source_t *carr,
+                                                  int M, double *freqs, int Nchan, double fdelta,
+                                                  double tdelta, double dec0, double uvmin,
+                                                  double uvmax, int Nt) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  return precalculate_multifreq_impl(u, v, w, x, N, Nbase, barr, carr, M, freqs, Nchan, fdelta, uvmin,
+                                     uvmax, nullptr);
+}
+extern "C" int precalculate_coherencies_multifreq_withbeam(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    double uvmin, double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt) {
+  (void)tdelta; (void)dec0; (void)Nt;
+  BeamSpec b = {bf_type, b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0, longitude, latitude, time_utc,
+                tilesz, Nelem, xx, yy, zz, ecoeff, doBeam};
+  return precalculate_multifreq_impl(u, v, w, x, N, Nbase, barr, carr, M, freqs, Nchan, fdelta, uvmin,
+                                     uvmax, &b);
+}
+extern "C" int precalculate_coherencies_multifreq_withbeam_gpu(
+    double *u, double *v, double *w, double *x, int N, int Nbase, baseline_t *barr,
+    clus_source_t *carr, int M, double *freqs, int Nchan, double fdelta, double tdelta, double dec0,
+    double uvmin, double uvmax, int bf_type, double b_ra0, double b_dec0, double ph_ra0,
+    double ph_dec0, double ph_freq0, double *longitude, double *latitude, double *time_utc, int tilesz,
+    int *Nelem, double **xx, double **yy, double **zz, elementcoeff *ecoeff, int doBeam, int Nt) {
+  return precalculate_coherencies_multifreq_withbeam(u, v, w, x, N, Nbase, barr, carr, M, freqs, Nchan,
+                                                     fdelta, tdelta, dec0, uvmin, uvmax, bf_type,
+                                                     b_ra0, b_dec0, ph_ra0, ph_dec0, ph_freq0,
+                                                     longitude, latitude, time_utc, tilesz, Nelem, xx,
+                                                     yy, zz, ecoeff, doBeam, Nt);
+}
+
 // Dirac_radio.h:659 (residual.c:1257-1340): x[chan][row][8] += sum over clusters; add_to_data ==
 // SIMUL_ONLY (1, Dirac_radio.h:78) clears x first, every other value accumulates onto the input
 // (the thread function only ever adds, residual.c:1238-1245).  No Jones, no flags.

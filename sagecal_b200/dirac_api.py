@@ -303,6 +303,22 @@ class DiracAPI:
             C.c_double(uvmin), C.c_double(uvmax), *beam.head(), beam.tilesz, *beam.tail(), Nt)
         return coh
 
+    def precalculate_coherencies_multifreq(self, u, v, w, N, Nbase1, barr, sky, freqs, fdelta,
+                                           beam=None, tdelta=10.0, dec0=1.0, uvmin=0.0, uvmax=1e9,
+                                           Nt=4):
+        """coh[chan][row][cluster][4] (predict.c:745); beam: the _withbeam variant"""
+        freqs = np.ascontiguousarray(freqs, dtype=np.float64)
+        coh = np.zeros(4 * sky.M * Nbase1 * len(freqs), dtype=np.complex128)
+        head = (dptr(u), dptr(v), dptr(w), cptr(coh), N, Nbase1, barr, sky.arr, sky.M, dptr(freqs),
+                len(freqs), C.c_double(fdelta), C.c_double(tdelta), C.c_double(dec0),
+                C.c_double(uvmin), C.c_double(uvmax))
+        if beam is None:
+            self.lib.precalculate_coherencies_multifreq(*head, Nt)
+        else:
+            self.lib.precalculate_coherencies_multifreq_withbeam(*head, *beam.head(), beam.tilesz,
+                                                                 *beam.tail(), Nt)
+        return coh
+
     def predict_visibilities_multifreq_withbeam(self, u, v, w, x, N, Nbase, tilesz, barr, sky, freqs,
                                                 fdelta, beam, tdelta=10.0, dec0=1.0, Nt=4,
                                                 add_to_data=1):

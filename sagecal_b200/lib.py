@@ -34,7 +34,8 @@ EXPORTED = [
     "precalculate_coherencies_withbeam", "precalculate_coherencies_withbeam_gpu",
     "predict_visibilities_multifreq_withbeam", "predict_visibilities_multifreq_withbeam_gpu",
     "calculate_residuals_multifreq_withbeam", "calculate_residuals_multifreq_withbeam_gpu",
-    "dirac_b200_extract_phases",
+    "dirac_b200_extract_phases", "precalculate_coherencies_multifreq",
+    "precalculate_coherencies_multifreq_withbeam", "precalculate_coherencies_multifreq_withbeam_gpu",
 ]
 
 

@@ -101,3 +101,27 @@ def test_predict_and_residual_withbeam(api, ref, mode, tile):
     api.calculate_residuals_multifreq_withbeam(pr.u, pr.v, pr.w, pp, rb, pr.N, pr.Nbase, pr.tilesz,
                                                b.barr, sky, freqs, pr.fdelta * 2, beam, ccid=1)
     assert relerr(rb, ra) < 1e-9, relerr(rb, ra)
+
+
+@pytest.mark.parametrize("mode,tile", [(None, False), ("full_wb", True), ("array", False)],
+                         ids=["nobeam", "full_wb-tile", "array-single"])
+def test_coherencies_multifreq(api, ref, mode, tile):
+    """precalculate_coherencies_multifreq(_withbeam): the [chan][row][cluster][4] coherencies the
+    minibatch drivers feed bfgsfit_minibatch_* (predict.c:745-816, predict_withbeam.c:726-900),
+    flags included (uvmin at the first channel, uvmax at the last)"""
+    from sagecal_b200.dirac_api import barr_to_numpy
+    freqs = np.array([144e6, 150e6, 157e6])
+    b, sky, beam = beam_problem(ref, mode or "array", tile, seed=41, freqs=freqs)
+    if mode is None:
+        beam = None
+    pr = b.pr
+    uvd = np.sqrt(pr.u ** 2 + pr.v ** 2) * freqs[0]
+    uvmin, uvmax = float(np.quantile(uvd, 0.1)), float(np.quantile(uvd, 0.93))
+    ba, bb = b.fresh_barr(), b.fresh_barr()
+    want = ref.precalculate_coherencies_multifreq(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, ba, sky, freqs,
+                                                  pr.fdelta * 3, beam, uvmin=uvmin, uvmax=uvmax)
+    got = api.precalculate_coherencies_multifreq(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, bb, sky, freqs,
+                                                 pr.fdelta * 3, beam, uvmin=uvmin, uvmax=uvmax)
+    assert relerr(got, want) < 1e-10, relerr(got, want)
+    fa, fb = barr_to_numpy(ba, pr.Nbase1)[2], barr_to_numpy(bb, pr.Nbase1)[2]
+    assert np.array_equal(fa, fb) and np.sum(fa == 2) > 0

@@ -17,8 +17,8 @@ pytestmark = pytest.mark.gpu
 DOBEAM = {"array": 1, "full": 2, "element": 3, "array_wb": 4, "full_wb": 5, "element_wb": 6}
 
 
-def beam_problem(ref, mode, tile, seed=31, freqs=(150e6,)):
-    b = small_problem(N=9, M=3, tilesz=5, seed=seed, kmean=2.0, gaussian_frac=0.3)
+def beam_problem(ref, mode, tile, seed=31, freqs=(150e6,), tilesz=5):
+    b = small_problem(N=9, M=3, tilesz=tilesz, seed=seed, kmean=2.0, gaussian_frac=0.3)
     pr = b.pr
     rng = np.random.default_rng(seed)
     ra0, dec0 = 1.2, np.deg2rad(58.0)
@@ -103,25 +103,55 @@ def test_predict_and_residual_withbeam(api, ref, mode, tile):
     assert relerr(rb, ra) < 1e-9, relerr(rb, ra)
 
 
-@pytest.mark.parametrize("mode,tile", [(None, False), ("full_wb", True), ("array", False)],
-                         ids=["nobeam", "full_wb-tile", "array-single"])
-def test_coherencies_multifreq(api, ref, mode, tile):
-    """precalculate_coherencies_multifreq(_withbeam): the [chan][row][cluster][4] coherencies the
-    minibatch drivers feed bfgsfit_minibatch_* (predict.c:745-816, predict_withbeam.c:726-900),
-    flags included (uvmin at the first channel, uvmax at the last)"""
+def test_coherencies_multifreq(api, ref):
+    """precalculate_coherencies_multifreq: the [chan][row][cluster][4] coherencies the minibatch
+    drivers feed bfgsfit_minibatch_* (predict.c:745-816), flags included (uvmin at the first
+    channel, uvmax at the last)"""
     from sagecal_b200.dirac_api import barr_to_numpy
     freqs = np.array([144e6, 150e6, 157e6])
-    b, sky, beam = beam_problem(ref, mode or "array", tile, seed=41, freqs=freqs)
-    if mode is None:
-        beam = None
+    b, sky, _ = beam_problem(ref, "array", False, seed=41, freqs=freqs)
     pr = b.pr
     uvd = np.sqrt(pr.u ** 2 + pr.v ** 2) * freqs[0]
     uvmin, uvmax = float(np.quantile(uvd, 0.1)), float(np.quantile(uvd, 0.93))
     ba, bb = b.fresh_barr(), b.fresh_barr()
     want = ref.precalculate_coherencies_multifreq(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, ba, sky, freqs,
-                                                  pr.fdelta * 3, beam, uvmin=uvmin, uvmax=uvmax)
+                                                  pr.fdelta * 3, None, uvmin=uvmin, uvmax=uvmax)
     got = api.precalculate_coherencies_multifreq(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, bb, sky, freqs,
-                                                 pr.fdelta * 3, beam, uvmin=uvmin, uvmax=uvmax)
+                                                 pr.fdelta * 3, None, uvmin=uvmin, uvmax=uvmax)
     assert relerr(got, want) < 1e-10, relerr(got, want)
     fa, fb = barr_to_numpy(ba, pr.Nbase1)[2], barr_to_numpy(bb, pr.Nbase1)[2]
     assert np.array_equal(fa, fb) and np.sum(fa == 2) > 0
+
+
+@pytest.mark.parametrize("mode,tile", [("full_wb", True), ("array", False), ("element", True)],
+                         ids=["full_wb-tile", "array-single", "element-tile"])
+def test_coherencies_multifreq_withbeam(api, ref, mode, tile):
+    """precalculate_coherencies_multifreq_withbeam.  The reference's CPU implementation of THIS call
+    cannot serve as the pin: it strides its channels by the baselines of one timeslot although the
+    rows span all timeslots (chanoff = 4 M N(N-1)/2, predict_withbeam.c:281,787) and reads the beam
+    tables without their channel index (:337-338,382-383), so every channel gets the first channel's
+    beam and the channels overlap.  What this library computes is the evident meaning -- channel c =
+    the single-channel call at freqs[c] with the smearing width fdelta / Nchan -- and that is what is
+    compared: against the reference's single-channel precalculate_coherencies_withbeam per channel."""
+    import ctypes as C
+    from sagecal_b200.dirac_api import barr_to_numpy, elementcoeff
+    freqs = np.array([144e6, 150e6, 157e6])
+    b, sky, beam = beam_problem(ref, mode, tile, seed=41, freqs=freqs)
+    pr = b.pr
+    got = api.precalculate_coherencies_multifreq(pr.u, pr.v, pr.w, pr.N, pr.Nbase1, b.fresh_barr(),
+                                                 sky, freqs, pr.fdelta * 3, beam, uvmin=30.0,
+                                                 uvmax=1e5)
+    n = 4 * sky.M * pr.Nbase1
+    for c, f in enumerate(freqs):
+        one = beam
+        if mode.endswith("_wb") and beam.ecoeff is not None:  # this channel's coefficient set
+            ec = elementcoeff()
+            fc = np.array([f])
+            ref.lib.set_elementcoeffs_wb(1 if tile else 0, dptr(fc), 1, C.byref(ec))
+            one = BeamSetup(beam.bf_type, beam.s[0].value, beam.s[1].value, beam.s[2].value,
+                            beam.s[3].value, beam.s[4].value, beam.lon, beam.lat, beam.t,
+                            [e.T for e in beam.xyz], ec, beam.doBeam)
+        want = ref.precalculate_coherencies_withbeam(pr.u, pr.v, pr.w, pr.N, pr.Nbase1,
+                                                     b.fresh_barr(), sky, f, pr.fdelta, one,
+                                                     uvmin=30.0, uvmax=1e5)
+        assert relerr(got[c * n:(c + 1) * n], want) < 1e-10, (c, relerr(got[c * n:(c + 1) * n], want))

@@ -2,6 +2,7 @@
 // Replaces the per-call H2D copies / cudaMalloc churn of the reference GPU path
 // (clmfit_fl.c:193-225, lbfgs_cuda.c:93-131, mderiv.cu:1402-1460) with one resident copy.
 #include <string.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/dirac_b200.h"
@@ -258,24 +259,50 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
   d.stream = db_new_stream(&pr->own_stream);
   const long long R = d.R;
 
+  // --- data first: its upload (1 GB at 512 stations) runs while the host checks the row order ---
+  d.x = dev_alloc<double2>((size_t)4 * R);
+  pr->vis_stage = dev_alloc<double2>((size_t)4 * R);
+  if (x) db_upload_vis(pr, x, d.x);
+
   // --- row order must be the canonical one (baseline_utils.c:445-461): checked, bit-exact ---
+  // (15.7 M rows at 512 stations x 120 timeslots: shared out over a few host threads by timeslot)
   std::vector<unsigned char> hflag(R);
   {
-    long long r = 0;
-    for (int t = 0; t < tilesz; t++)
-      for (int p = 0; p < N - 1; p++)
-        for (int q = p + 1; q < N; q++, r++) {
-          if (barr[r].sta1 != p || barr[r].sta2 != q) {
-            fprintf(stderr, "dirac_b200: barr[%lld]=(%d,%d) is not the canonical (%d,%d) of "
-                            "generate_baselines; unsupported row order\n",
-                    r, barr[r].sta1, barr[r].sta2, p, q);
-            exit(1);
+    const long long Nb = (long long)N * (N - 1) / 2;
+    int nthr = (R > (1 << 20)) ? 8 : 1;
+    if (nthr > tilesz) nthr = tilesz;
+    std::vector<long long> bad(nthr, -1);
+    auto work = [&](int th) {
+      for (int t = th; t < tilesz; t += nthr) {
+        long long r = (long long)t * Nb;
+        for (int p = 0; p < N - 1; p++)
+          for (int q = p + 1; q < N; q++, r++) {
+            if (barr[r].sta1 != p || barr[r].sta2 != q) {
+              if (bad[th] < 0) bad[th] = r;
+              return;
+            }
+            hflag[r] = barr[r].flag;
           }
-          hflag[r] = barr[r].flag;
-        }
+      }
+    };
+    if (nthr == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> pool;
+      for (int th = 0; th < nthr; th++) pool.emplace_back(work, th);
+      for (auto &th : pool) th.join();
+    }
+    for (int th = 0; th < nthr; th++)
+      if (bad[th] >= 0) {
+        const long long r = bad[th];
+        fprintf(stderr, "dirac_b200: barr[%lld]=(%d,%d) is not in the canonical order of "
+                        "generate_baselines; unsupported row order\n", r, barr[r].sta1, barr[r].sta2);
+        exit(1);
+      }
   }
   d.flag = dev_alloc<unsigned char>(R);
-  DB_CHECK(cudaMemcpy(d.flag, hflag.data(), R, cudaMemcpyHostToDevice));
+  DB_CHECK(cudaMemcpyAsync(d.flag, hflag.data(), R, cudaMemcpyHostToDevice, d.stream));
+  db_stream_sync(d.stream);  // data and flags are up (hflag goes out of scope)
 
   // --- cluster / chunk tables ---
   d.h_clus = (ClusterDesc *)malloc(sizeof(ClusterDesc) * M);
@@ -316,10 +343,7 @@ static dirac_b200_problem *create_impl(int N, int Nbase, int tilesz, const basel
 
   // --- Jones, data, coherencies ---
   d.pp = dev_alloc<double>((size_t)d.npar);
-  d.x = dev_alloc<double2>((size_t)4 * R);
   d.coh = dev_alloc<double2>((size_t)M * 4 * R);
-  pr->vis_stage = dev_alloc<double2>((size_t)4 * R);
-  if (x) dirac_b200_set_data(pr, x);
   if (coh) {
     // chunked upload through a device staging buffer, transposed to planar on the device
     long long rows_per = (128ll << 20) / ((long long)M * 64);

@@ -186,6 +186,11 @@ static void beam_prepare(const BeamSpec *b, const SkyDev &sky, int N, int Nbase_
   }
   if (do_elem) {
     const elementcoeff *ec = b->ecoeff;
+    if (!ec || !ec->pattern_phi || !ec->pattern_theta || !ec->preamble) {
+      fprintf(stderr, "dirac_b200: element beam requested (doBeam %d) without coefficient tables "
+                      "(set_elementcoeffs)\n", b->doBeam);
+      exit(1);
+    }
     const int nfc = wide ? ec->Nf : 1;
     g.ecM = ec->M; g.ecNmodes = ec->Nmodes; g.ecbeta = ec->beta;
     g.pat_phi = (double2 *)keep(upload_doubles(ec->pattern_phi, 2ll * ec->Nmodes * nfc, st));

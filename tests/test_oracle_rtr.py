@@ -116,3 +116,35 @@ def test_rtr_admm_chunk_matches_reference(refser, case):
                 assert abs(ig[0] - iw[0]) <= 1e-9 * abs(iw[0])
                 assert abs(ig[1] - iw[1]) <= 10 * tol * abs(iw[1])
                 assert nug == nuw
+
+
+EDGE = [
+    ("one-slot", dict(N=8, M=2, tilesz=1, seed=65), 4),
+    ("heavy-flags", dict(N=9, M=2, tilesz=6, seed=66, flag_frac=0.4, uvcut_frac=0.05), 5),
+    ("heavy-flags-nsd", dict(N=9, M=2, tilesz=6, seed=67, flag_frac=0.4), 6),
+    ("zero-budget", dict(N=8, M=2, tilesz=6, seed=68), 4),   # this_itermax = 0: 5 RSD + 10 RTR iterations
+]
+
+
+@pytest.mark.parametrize("name,prob,kind", EDGE, ids=[e[0] for e in EDGE])
+def test_rtr_chunk_edge_cases(ref, refser, name, prob, kind):
+    b = small_problem(**prob)
+    pr = b.pr
+    orc = orcdirac.Oracle(pr)
+    lib = ref if kind == 4 else refser
+    pp = perturbed_jones(pr, seed=2, amp=0.1)
+    res = pr.x - orc.predict_full(pp)
+    n8 = 8 * pr.N
+    ita, itb = ((5, 10) if name == "zero-budget" else (7, 12)) if kind != 6 else (17, 0)
+    for k in range(pr.M):
+        hidden = res + orc.predict_cluster(k, pp)
+        pblk = pp[k * n8:(k + 1) * n8].copy()
+        md = lib.me_data(pr.N, pr.Nbase, pr.tilesz, b.barr, b.sky, pr.coh, clus=k, robust_nu=4.0)
+        pw, iw, nuw = lib.rtr(pblk, hidden, md, pr.N, pr.Nbase1, kind, ita, itb)
+        for tensor, tol in ((False, 1e-9), (True, 1e-7)):
+            pg, ig, nug = orc.rtr_chunk(k, 0, pr.tilesz, pblk, hidden, kind, ita, itb, nu0=4.0,
+                                        tensor=tensor)
+            assert relerr(pg, pw) < tol, (name, k, tensor, relerr(pg, pw))
+            assert abs(ig[1] - iw[1]) <= 100 * tol * abs(iw[1])
+            if kind != 4:
+                assert nug == nuw

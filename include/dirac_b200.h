@@ -445,7 +445,7 @@ int bfgsfit_minibatch_consensus(double *u, double *v, double *w, double *x, int 
                                 double *res_1, persistent_data_t *indata, int nminibatch,
                                 int totalminibatch);
 
-/* Device memory freed by dirac_b200_destroy is kept (up to a quarter of the device's memory,
+/* Device memory freed by dirac_b200_destroy is kept (up to 40 % of the device's memory,
  * $DIRAC_B200_CACHE_GB overrides, 0 disables) and handed out again when a problem of the same shape
  * is created: the driver calls tile after tile with the same sizes, and cudaMalloc / cudaFree of the
  * coherencies alone cost 50-350 ms at 512 stations.  This returns all of it to the driver. */

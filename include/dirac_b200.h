@@ -159,6 +159,9 @@ int calculate_residuals_multifreq(double *u, double *v, double *w, double *p, do
  * (baseline_utils.c:469), preset_flags_and_data (baseline_utils.c:239).  Bit-exact index work. */
 int generate_baselines(int Nbase, int tilesz, int N, baseline_t *barr, int Nt);
 int preset_flags_and_data(int Nbase, double *flag, baseline_t *barr, double *x, int Nt);
+/* uv-distance taper of the data (driver option -W; src/lib/Dirac/Dirac.h:841, updatenu.c:339-420):
+ * x[8 row ..] *= 1 / (1 + 1.8 exp(-0.05 d)), d = |(u,v)| freq0 <= 400 wavelengths.  Host, bit-exact. */
+void whiten_data(int Nbase, double *x, double *u, double *v, double freq0, int Nt);
 
 /* ---- (2) thin device layer ------------------------------------------------------------------- */
 

@@ -6,6 +6,7 @@
 // and the host only sees scalars and the 8N-vectors the LM decisions need.
 #include <math.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 #include "../../include/dirac_b200.h"
@@ -375,4 +376,32 @@ extern "C" int preset_flags_and_data(int Nbase, double *flag, baseline_t *barr, 
     }
   }
   return 0;
+}
+
+// uv-distance taper of the data, the driver's -W option, applied between preset_flags_and_data and the
+// coherency prediction (fullbatch_mode.cpp:329-332): every row is scaled by 1 / (1 + 1.8 exp(-0.05 d)),
+// d = |(u,v)| freq0 in wavelengths (u, v arrive divided by c); rows beyond 400 wavelengths are left
+// alone (threadfn_setblweight / ncp_weight, updatenu.c:339-372).  A 1 GB pass at 512 stations: split
+// over Nt host threads like the reference's.
+extern "C" void whiten_data(int Nbase, double *x, double *u, double *v, double freq0, int Nt) {
+  auto taper = [=](long long r0, long long r1) {
+    for (long long r = r0; r < r1; r++) {
+      const double uu = u[r] * freq0, vv = v[r] * freq0;
+      const double ud = sqrt(uu * uu + vv * vv);
+      if (ud > 400.0) continue;  // weight exactly 1
+      const double a = 1.0 / (1.0 + 1.8 * exp(-0.05 * ud));
+      for (int c = 0; c < 8; c++) x[8 * r + c] *= a;
+    }
+  };
+  if (Nt < 1) Nt = 1;
+  const long long per = ((long long)Nbase + Nt - 1) / Nt;
+  if (Nt == 1 || Nbase < (1 << 16)) {
+    taper(0, Nbase);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (long long r0 = per; r0 < Nbase; r0 += per)
+    th.emplace_back(taper, r0, r0 + per < Nbase ? r0 + per : (long long)Nbase);
+  taper(0, per < Nbase ? per : (long long)Nbase);
+  for (auto &t : th) t.join();
 }

@@ -255,6 +255,9 @@ class DiracAPI:
         L.generate_baselines.argtypes = [i, i, i, bp, i]
         L.preset_flags_and_data.restype = i
         L.preset_flags_and_data.argtypes = [i, dp, bp, dp, i]
+        if hasattr(L, "whiten_data"):
+            L.whiten_data.restype = None
+            L.whiten_data.argtypes = [i, dp, dp, dp, d, i]
         if hasattr(L, "calculate_residuals_multifreq"):
             L.calculate_residuals_multifreq.restype = i
             L.calculate_residuals_multifreq.argtypes = [dp, dp, dp, dp, dp, i, i, i, bp, cp, i, dp,
@@ -268,6 +271,10 @@ class DiracAPI:
 
     def preset_flags_and_data(self, flag, barr, x, Nt=4):
         return self.lib.preset_flags_and_data(len(flag), dptr(flag), barr, dptr(x), Nt)
+
+    def whiten_data(self, x, u, v, freq0, Nt=4):
+        """uv taper of the data in place (Dirac.h:841); u, v in seconds as everywhere in the API"""
+        self.lib.whiten_data(len(u), dptr(x), dptr(u), dptr(v), freq0, Nt)
 
     def precalculate_coherencies(self, u, v, w, N, Nbase1, barr, sky: SkyModel, freq0, fdelta,
                                  tdelta=10.0, dec0=1.0, uvmin=0.0, uvmax=1e9, Nt=4):

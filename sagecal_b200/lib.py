@@ -17,7 +17,7 @@ EXPORTED = [
     "sagefit_visibilities", "sagefit_visibilities_dual_pt_flt", "sagefit_visibilities_dual_pt",
     "sagefit_visibilities_dual_pt_one_gpu", "bfgsfit_visibilities", "bfgsfit_visibilities_gpu",
     "precalculate_coherencies", "predict_visibilities_multifreq", "generate_baselines",
-    "preset_flags_and_data", "dirac_b200_create", "dirac_b200_destroy", "dirac_b200_set_data",
+    "preset_flags_and_data", "whiten_data", "dirac_b200_create", "dirac_b200_destroy", "dirac_b200_set_data",
     "dirac_b200_precalculate", "dirac_b200_get_coherencies", "dirac_b200_predict",
     "dirac_b200_grad", "dirac_b200_normal_eq", "dirac_b200_launch_count", "dirac_b200_sagefit",
     "dirac_b200_set_stream", "dirac_b200_profile_enable", "dirac_b200_profile_read",

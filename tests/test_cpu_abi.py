@@ -56,6 +56,27 @@ def test_preset_flags_bit_exact(product, ref):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
 
 
+def test_whiten_data_bit_exact(product, ref):
+    """uv taper (driver option -W): host arithmetic, same libm -> identical bits; threaded and not"""
+    rng = np.random.default_rng(3)
+    for n, Nt in ((1001, 3), (70001, 4), (70001, 1)):
+        # |(u,v)| f0 spread around the 400-wavelength cut-off, some rows exactly beyond it
+        u = rng.normal(0, 1.2e-6, n)
+        v = rng.normal(0, 1.2e-6, n)
+        xs = rng.normal(0, 1, 8 * n)
+        out = []
+        for lib in (ref, product):
+            x = xs.copy()
+            lib.whiten_data(x, u, v, 150e6, Nt)
+            out.append(x)
+        assert np.array_equal(out[0], out[1])
+        d = np.hypot(u, v) * 150e6
+        assert (d > 400).any() and (d < 400).any()
+        untouched = np.repeat(d > 400, 8)
+        assert np.array_equal(out[1][untouched], xs[untouched])
+        assert (np.abs(out[1][~untouched]) < np.abs(xs[~untouched])).all()
+
+
 def test_no_oracle_in_product():
     """the product package must not import, link or execute anything under oracle/"""
     pkg = os.path.join(ROOT, "sagecal_b200")

@@ -148,3 +148,31 @@ def test_rtr_chunk_edge_cases(ref, refser, name, prob, kind):
             assert abs(ig[1] - iw[1]) <= 100 * tol * abs(iw[1])
             if kind != 4:
                 assert nug == nuw
+
+
+@pytest.mark.parametrize("mode", [4, 5, 6])
+def test_sagefit_rtr_modes_match_reference_at_reduced_c3(ref, refser, mode):
+    """the whole SAGE call under the Riemannian solvers at the reduced C2/C3 shape of BASELINE.md 5.5
+    (62 stations, 1891 baselines, 8 clusters, 10 timeslots, the benchmark's solver settings): the
+    restatement with the product's control flow against the COMPILED REFERENCE, live (its RTR family is
+    matrix free, so it runs in seconds here).  This is the pin behind tests/golden/full/C3rtr, C2rtr,
+    C3nsd, which the restatement generated at the full 62-station shapes."""
+    from sagecal_b200 import synth
+    from util import Bound
+    ref = ref if mode == 4 else refser
+    b = Bound(synth.make_problem(N=62, M=8, tilesz=10, radius=40e3, kmean=2.0, seed=20260921 + 30 + mode,
+                                 outliers=0.02 if mode > 4 else 0.0))
+    pr = b.pr
+    orc = orcdirac.Oracle(pr)
+    kw = dict(max_emiter=3, max_iter=2, max_lbfgs=10, lbfgs_m=7, solver_mode=mode, randomize=0)
+    xr, ppr = pr.x.copy(), pr.pp0.copy()
+    rr = ref.sagefit_visibilities(pr.u, pr.v, pr.w, xr, pr.N, pr.Nbase, pr.tilesz, b.fresh_barr(),
+                                  b.sky, pr.coh, ppr, Nt=8, **kw)
+    xo, ppo = pr.x.copy(), pr.pp0.copy()
+    ro = orc.sagefit(xo, ppo, **kw)
+    assert ro[0] == rr[0]
+    assert abs(ro[1] - rr[1]) < 1e-9
+    assert abs(ro[2] - rr[2]) <= 1e-12 * rr[2]
+    assert relerr(ppo, ppr) < 1e-6, relerr(ppo, ppr)
+    assert abs(ro[3] - rr[3]) <= 1e-6 * rr[3]
+    assert relerr(xo, xr) < 1e-6

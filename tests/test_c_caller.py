@@ -31,3 +31,26 @@ def test_c_host_runs_the_solver(tmp_path):
     exe = build(tmp_path)
     out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "C_CALLER OK" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+def test_link_order_puts_the_hot_path_on_this_library(tmp_path):
+    """INTEGRATION.md section 2 on a CPU box: `-ldirac_b200` in front of the reference's library
+    (oracle/_ref, the reference CPU path compiled from its own sources) takes over the hot-path
+    symbols and leaves the rest with the reference."""
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.exists(os.path.join(refdir, "libdirac_ref.so")):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    exe = os.path.join(str(tmp_path), "link_order")
+    libdir = os.path.join(ROOT, "sagecal_b200")
+    cmd = ["gcc", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "c_caller", "link_order.c"),
+           "-I", os.path.join(ROOT, "include"), "-L", libdir, "-ldirac_b200", "-L", refdir,
+           "-ldirac_ref", "-ldl", "-lm", "-Wl,-rpath," + libdir, "-Wl,-rpath," + refdir,
+           "-Wl,--allow-shlib-undefined"]
+    subprocess.check_call(cmd)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.stdout, out.stderr)
+    got = dict(line.split() for line in out.stdout.strip().splitlines())
+    ours = [s for s, lib in got.items() if lib == "libdirac_b200.so"]
+    theirs = [s for s, lib in got.items() if lib == "libdirac_ref.so"]
+    assert sorted(theirs) == ["my_dnrm2", "my_dscal", "update_w_and_nu"], got
+    assert len(ours) == len(got) - 3 and "sagefit_visibilities" in ours and "whiten_data" in ours, got

@@ -447,6 +447,28 @@ int bfgsfit_minibatch_consensus(double *u, double *v, double *w, double *x, int 
                                 int gpu_threads, int solver_mode, double robust_nu, double *res_0,
                                 double *res_1, persistent_data_t *indata, int nminibatch,
                                 int totalminibatch);
+/* The same two calls with the argument list the reference declares under HAVE_CUDA (Dirac.h:315-319,
+ * 343-347; call sites minibatch_mode.cpp:438, minibatch_consensus_mode.cpp:536): `short *hbb`
+ * (2 shorts per row: stations, or -1 -1 for a flagged row; rearrange_baselines, baseline_utils.c:123-145)
+ * and `int *ptoclus` (2 ints per cluster: nchunk and the offset of its first chunk in p, the chunks of a
+ * cluster contiguous) in place of barr / carr.  One symbol cannot carry both signatures: a driver
+ * compiled with HAVE_CUDA binds these names. */
+int bfgsfit_minibatch_visibilities_hbb(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                       int tilesz, short *hbb, int *ptoclus, double *coh, int M, int Mt,
+                                       double *freqs, int Nf, double fdelta, double *p, int Nt,
+                                       int max_lbfgs, int lbfgs_m, int gpu_threads, int solver_mode,
+                                       double robust_nu, double *res_0, double *res_1,
+                                       persistent_data_t *indata, int nminibatch, int totalminibatch);
+int bfgsfit_minibatch_consensus_hbb(double *u, double *v, double *w, double *x, int N, int Nbase,
+                                    int tilesz, short *hbb, int *ptoclus, double *coh, int M, int Mt,
+                                    double *freqs, int Nf, double fdelta, double *p, double *y,
+                                    double *z, double *rho, int Nt, int max_lbfgs, int lbfgs_m,
+                                    int gpu_threads, int solver_mode, double robust_nu, double *res_0,
+                                    double *res_1, persistent_data_t *indata, int nminibatch,
+                                    int totalminibatch);
+/* host helper behind them: baseline_t rows from hbb (stations by position in the canonical order, flag 1
+ * where hbb marks the row); -1 if an unflagged row does not carry the canonical pair of its position. */
+int dirac_b200_barr_from_hbb(int N, int Nbase, int tilesz, const short *hbb, baseline_t *barr);
 
 /* Device memory freed by dirac_b200_destroy is kept (up to 40 % of the device's memory,
  * $DIRAC_B200_CACHE_GB overrides, 0 disables) and handed out again when a problem of the same shape

@@ -159,3 +159,83 @@ extern "C" int bfgsfit_minibatch_consensus(double *u, double *v, double *w, doub
   return minibatch_fit(x, N, Nbase, tilesz, barr, carr, coh, M, Mt, Nf, p, y, z, rho, max_lbfgs,
                        lbfgs_m, robust_nu, res_0, res_1, indata);
 }
+
+// ---- the same two calls with the GPU build's argument list ---------------------------------------------
+// Under HAVE_CUDA the reference declares bfgsfit_minibatch_visibilities / _consensus with
+// `short *hbb, int *ptoclus` in place of `baseline_t *barr, clus_source_t *carr` (Dirac.h:315-319,
+// 343-347; minibatch_mode.cpp:332-342,438): hbb[2 row] = (sta1, sta2) as shorts, (-1, -1) for a flagged
+// row (rearrange_baselines, baseline_utils.c:123-137), ptoclus[2 k] = (nchunk, p[0]) of cluster k with the
+// chunks of a cluster contiguous in the Jones vector.  One symbol cannot carry two signatures, so these
+// are exported under their own names; INTEGRATION.md says how a GPU-build driver binds them.
+//
+// dirac_b200_barr_from_hbb rebuilds the baseline_t rows: stations by position in the canonical order
+// (a flagged row has lost its pair), flag 1 where hbb marks the row.  Returns -1 if an unflagged row
+// does not carry the canonical pair of its position.  Host arithmetic, no GPU needed.
+extern "C" int dirac_b200_barr_from_hbb(int N, int Nbase, int tilesz, const short *hbb,
+                                        baseline_t *barr) {
+  generate_baselines(Nbase, tilesz, N, barr, 1);
+  const long long R = (long long)Nbase * tilesz;
+  for (long long r = 0; r < R; r++) {
+    const int a = hbb[2 * r], b = hbb[2 * r + 1];
+    if (a < 0 || b < 0) {
+      barr[r].flag = 1;
+    } else {
+      barr[r].flag = 0;
+      if (a != barr[r].sta1 || b != barr[r].sta2) return -1;
+    }
+  }
+  return 0;
+}
+
+namespace {
+struct HbbTables {
+  std::vector<baseline_t> barr;
+  std::vector<clus_source_t> carr;
+  std::vector<int> poff;
+  HbbTables(int N, int Nbase, int tilesz, const short *hbb, int M, int Mt, const int *ptoclus)
+      : barr((size_t)Nbase * tilesz), carr(M), poff(Mt > 0 ? Mt : 1) {
+    if (dirac_b200_barr_from_hbb(N, Nbase, tilesz, hbb, barr.data())) {
+      fprintf(stderr, "dirac_b200: hbb is not in the row order of generate_baselines; unsupported "
+                      "row order\n");
+      exit(1);
+    }
+    memset(carr.data(), 0, sizeof(clus_source_t) * M);
+    int mt = 0;
+    for (int k = 0; k < M; k++) {
+      carr[k].nchunk = ptoclus[2 * k];
+      if (mt + carr[k].nchunk > Mt) {
+        fprintf(stderr, "dirac_b200: ptoclus names more than Mt = %d chunks\n", Mt);
+        exit(1);
+      }
+      carr[k].p = poff.data() + mt;
+      for (int c = 0; c < carr[k].nchunk; c++) poff[mt + c] = ptoclus[2 * k + 1] + 8 * N * c;
+      mt += carr[k].nchunk;
+    }
+  }
+};
+}  // namespace
+
+extern "C" int bfgsfit_minibatch_visibilities_hbb(
+    double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, short *hbb, int *ptoclus,
+    double *coh, int M, int Mt, double *freqs, int Nf, double fdelta, double *p, int Nt, int max_lbfgs,
+    int lbfgs_m, int gpu_threads, int solver_mode, double robust_nu, double *res_0, double *res_1,
+    persistent_data_t *indata, int nminibatch, int totalminibatch) {
+  HbbTables t(N, Nbase, tilesz, hbb, M, Mt, ptoclus);
+  return bfgsfit_minibatch_visibilities(u, v, w, x, N, Nbase, tilesz, t.barr.data(), t.carr.data(),
+                                        coh, M, Mt, freqs, Nf, fdelta, p, Nt, max_lbfgs, lbfgs_m,
+                                        gpu_threads, solver_mode, robust_nu, res_0, res_1, indata,
+                                        nminibatch, totalminibatch);
+}
+
+extern "C" int bfgsfit_minibatch_consensus_hbb(
+    double *u, double *v, double *w, double *x, int N, int Nbase, int tilesz, short *hbb, int *ptoclus,
+    double *coh, int M, int Mt, double *freqs, int Nf, double fdelta, double *p, double *y, double *z,
+    double *rho, int Nt, int max_lbfgs, int lbfgs_m, int gpu_threads, int solver_mode,
+    double robust_nu, double *res_0, double *res_1, persistent_data_t *indata, int nminibatch,
+    int totalminibatch) {
+  HbbTables t(N, Nbase, tilesz, hbb, M, Mt, ptoclus);
+  return bfgsfit_minibatch_consensus(u, v, w, x, N, Nbase, tilesz, t.barr.data(), t.carr.data(), coh,
+                                     M, Mt, freqs, Nf, fdelta, p, y, z, rho, Nt, max_lbfgs, lbfgs_m,
+                                     gpu_threads, solver_mode, robust_nu, res_0, res_1, indata,
+                                     nminibatch, totalminibatch);
+}

@@ -36,6 +36,7 @@ EXPORTED = [
     "calculate_residuals_multifreq_withbeam", "calculate_residuals_multifreq_withbeam_gpu",
     "dirac_b200_extract_phases", "precalculate_coherencies_multifreq",
     "precalculate_coherencies_multifreq_withbeam", "precalculate_coherencies_multifreq_withbeam_gpu",
+    "bfgsfit_minibatch_visibilities_hbb", "bfgsfit_minibatch_consensus_hbb", "dirac_b200_barr_from_hbb",
 ]
 
 

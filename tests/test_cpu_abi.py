@@ -77,6 +77,35 @@ def test_whiten_data_bit_exact(product, ref):
         assert (np.abs(out[1][~untouched]) < np.abs(xs[~untouched])).all()
 
 
+def test_barr_from_hbb_inverts_the_reference_rearrangement(product, ref):
+    """the GPU-build argument list of the minibatch drivers: rows come as `short hbb[2]` written by
+    the reference's rearrange_baselines (baseline_utils.c:145); the library rebuilds baseline_t rows"""
+    import ctypes as C
+    from sagecal_b200.dirac_api import baseline_t
+    rng = np.random.default_rng(5)
+    N, T = 13, 4
+    Nbase = N * (N - 1) // 2
+    R = Nbase * T
+    barr = ref.generate_baselines(Nbase, T, N)
+    flags = rng.choice([0, 0, 0, 1, 2], R).astype(np.uint8)
+    for r in range(R):
+        barr[r].flag = int(flags[r])
+    hbb = np.zeros(2 * R, dtype=np.int16)
+    sp = C.POINTER(C.c_short)
+    ref.lib.rearrange_baselines.argtypes = [C.c_int, C.POINTER(baseline_t), sp, C.c_int]
+    ref.lib.rearrange_baselines(R, barr, hbb.ctypes.data_as(sp), 3)
+    out = (baseline_t * R)()
+    product.lib.dirac_b200_barr_from_hbb.argtypes = [C.c_int, C.c_int, C.c_int, sp, C.POINTER(baseline_t)]
+    assert product.lib.dirac_b200_barr_from_hbb(N, Nbase, T, hbb.ctypes.data_as(sp), out) == 0
+    a, g = barr_to_numpy(barr, R), barr_to_numpy(out, R)
+    assert np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1])
+    assert np.array_equal(g[2], (flags != 0).astype(g[2].dtype))
+    # a row out of the canonical order is refused
+    k = int(np.flatnonzero(flags == 0)[3])
+    hbb[2 * k + 1] += 1
+    assert product.lib.dirac_b200_barr_from_hbb(N, Nbase, T, hbb.ctypes.data_as(sp), out) == -1
+
+
 def test_no_oracle_in_product():
     """the product package must not import, link or execute anything under oracle/"""
     pkg = os.path.join(ROOT, "sagecal_b200")

@@ -54,3 +54,20 @@ def test_link_order_puts_the_hot_path_on_this_library(tmp_path):
     theirs = [s for s, lib in got.items() if lib == "libdirac_ref.so"]
     assert sorted(theirs) == ["my_dnrm2", "my_dscal", "update_w_and_nu"], got
     assert len(ours) == len(got) - 3 and "sagefit_visibilities" in ours and "whiten_data" in ours, got
+
+
+def test_struct_layouts_equal_the_reference_headers(tmp_path):
+    """baseline_t, clus_source_t, exinfo_*, elementcoeff, the prefix of persistent_data_t and the
+    STYPE_ / DOBEAM_ / STAT_ / SM_ constants: same sizes, offsets and values as a caller compiled
+    against the reference's Dirac.h / Dirac_radio.h sees (74 lines compared)."""
+    refinc = "/root/reference/src/lib"
+    if not os.path.isdir(refinc):
+        pytest.skip("reference headers not present on this box")
+    src = os.path.join(ROOT, "tests", "c_caller", "layout.c")
+    outs = []
+    for name, flags in (("ref", ["-DUSE_REF", "-I", refinc + "/Dirac", "-I", refinc + "/Radio"]),
+                        ("ours", ["-I", os.path.join(ROOT, "include")])):
+        exe = os.path.join(str(tmp_path), name)
+        subprocess.check_call(["gcc", "-w", "-o", exe, src] + flags)
+        outs.append(subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout)
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) > 70

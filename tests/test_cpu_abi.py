@@ -106,6 +106,46 @@ def test_barr_from_hbb_inverts_the_reference_rearrangement(product, ref):
     assert product.lib.dirac_b200_barr_from_hbb(N, Nbase, T, hbb.ctypes.data_as(sp), out) == -1
 
 
+def _c_declarations(path):
+    """{function name: [parameter type lists]} of a C header (comments stripped, names dropped)"""
+    t = open(path).read()
+    t = re.sub(r"/\*.*?\*/", "", t, flags=re.S)
+    t = re.sub(r"//[^\n]*", "", t)
+    out = {}
+    for m in re.finditer(r"\b([a-z_0-9]+)\s*\(([^()]*)\)\s*;", t):
+        types = []
+        for a in m.group(2).replace("\n", " ").split(","):
+            a = re.sub(r"\s+", " ", a.strip().replace("complex double", "double").replace("const ", ""))
+            mm = re.match(r"(.*?)([A-Za-z_0-9]+)$", a)
+            types.append((mm.group(1) if mm else a).replace(" ", ""))
+        out.setdefault(m.group(1), []).append(types)
+    return out
+
+
+def test_signatures_equal_the_reference_headers():
+    """every reference-named entry point is declared with the reference's own parameter type list
+    (complex double * spelled double *); the *_hbb pair carries the HAVE_CUDA variant of its name"""
+    refroot = "/root/reference/src/lib"
+    if not os.path.isdir(refroot):
+        pytest.skip("reference headers not present on this box")
+    ours = _c_declarations(os.path.join(ROOT, "include", "dirac_b200.h"))
+    ref = {}
+    for h in ("Dirac/Dirac.h", "Dirac/Dirac_common.h", "Radio/Dirac_radio.h"):
+        for k, v in _c_declarations(os.path.join(refroot, h)).items():
+            ref.setdefault(k, []).extend(v)
+    checked = 0
+    for name, sigs in ours.items():
+        if name.startswith("dirac_b200"):
+            continue
+        base = name[:-4] if name.endswith("_hbb") else name
+        assert base in ref, "%s is not a reference entry point" % name
+        assert sigs[0] in ref[base], (name, sigs[0], ref[base])
+        if name.endswith("_hbb"):  # ... and it is the OTHER variant of the name
+            assert sigs[0] != ours[base][0] and len(ref[base]) == 2
+        checked += 1
+    assert checked >= 30
+
+
 def test_no_oracle_in_product():
     """the product package must not import, link or execute anything under oracle/"""
     pkg = os.path.join(ROOT, "sagecal_b200")
